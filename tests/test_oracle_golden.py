@@ -1,0 +1,110 @@
+"""CPU: pin oracle/port.py (the checker used by every GPU parity test) against fixtures made
+from the reference's own source files (tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+from conftest import assert_close_rel, load_golden
+from oracle import port
+
+MAGNET_CASES = ["magnet_c1", "magnet_k2_weighted", "magnet_k3_none", "magnet_q0",
+                "magnet_sym_lmax", "msconv_signed", "msconv_nonabs_none"]
+
+
+def _magnet_kwargs(name, g):
+    return dict(q=g["q"], normalization="sym" if g["sym"] else None,
+                lambda_max=None if g["lambda_max"] < 0 else g["lambda_max"],
+                signed=name.startswith("msconv"),
+                absolute_degree=(name != "msconv_nonabs_none"))
+
+
+@pytest.mark.parametrize("name", MAGNET_CASES)
+def test_magnet_port_matches_reference(name):
+    g = load_golden(name)
+    ew = g["edge_weight"] if g["has_weight"] else None
+    kw = _magnet_kwargs(name, g)
+    n = g["x_real"].size(0)
+    lam = 2.0 if kw["lambda_max"] is None else kw["lambda_max"]
+    cr = port.magnet_norm(g["edge_index"], ew, n, kw["q"], kw["normalization"], lam,
+                          torch.float32, kw["signed"], kw["absolute_degree"])
+    # integer artefacts: bit exact
+    assert torch.equal(cr[0], g["cached_edge_index_real"])
+    assert torch.equal(cr[1], g["cached_edge_index_imag"])
+    assert_close_rel(cr[2], g["cached_norm_real"], 1e-6, "norm_real")
+    assert_close_rel(cr[3], g["cached_norm_imag"], 1e-6, "norm_imag")
+    o_r, o_i = port.magnet_conv(g["x_real"], g["x_imag"], g["edge_index"], ew, g["weight"],
+                                g["bias"], **kw)
+    assert_close_rel(o_r, g["out_real"], 1e-5, "out_real")
+    assert_close_rel(o_i, g["out_imag"], 1e-5, "out_imag")
+    # fp64 sanity band: the fp32 reference itself sits within 1e-5 of an fp64 evaluation
+    d = lambda t: None if t is None else t.double()
+    o_r64, o_i64 = port.magnet_conv(d(g["x_real"]), d(g["x_imag"]), g["edge_index"], d(ew),
+                                    d(g["weight"]), d(g["bias"]), **kw)
+    assert_close_rel(g["out_real"], o_r64, 2e-5, "fp64 band real")
+    assert_close_rel(g["out_imag"], o_i64, 2e-5, "fp64 band imag")
+
+
+@pytest.mark.parametrize("tag,norm", [("sym", "sym"), ("none", None)])
+def test_laplacian_port(tag, norm):
+    g = load_golden(f"laplacian_{tag}")
+    ei, wr, wi = port.magnetic_laplacian(g["edge_index"], g["edge_weight"], 70, g["q"], norm)
+    assert torch.equal(ei, g["out_edge_index"])
+    assert_close_rel(wr, g["out_real"], 1e-6, "real")
+    assert_close_rel(wi, g["out_imag"], 1e-6, "imag")
+
+
+def test_q11_real_part_of_one_way_edge_is_tiny_but_nonzero():
+    ei = torch.tensor([[0], [1]])
+    _, wr, wi = port.magnetic_laplacian(ei, None, 2, 0.25, "sym")
+    assert 0 < abs(wr[0].item()) < 1e-6 and abs(abs(wi[0].item()) - 1.0) < 1e-6
+
+
+def test_digcn_port():
+    g = load_golden("digcn_conv")
+    y = port.digcn_conv(g["x"], g["edge_index"], g["edge_weight"], g["weight"], g["bias"])
+    assert_close_rel(y, g["out"], 1e-5)
+    g = load_golden("digcn_inception")
+    x0, x1, x2 = port.digcn_inception_block(
+        g["x"], g["edge_index"], g["edge_weight"], g["edge_index2"], g["edge_weight2"],
+        g["ln_weight"], g["ln_bias"], g["conv1_weight"], g["conv1_bias"],
+        g["conv2_weight"], g["conv2_bias"])
+    for a, b in ((x0, g["x0"]), (x1, g["x1"]), (x2, g["x2"])):
+        assert_close_rel(a, b, 1e-5)
+
+
+@pytest.mark.parametrize("name,first,norm_emb", [("sgcn_first", True, False),
+                                                 ("sgcn_second", False, True)])
+def test_sgcn_port(name, first, norm_emb):
+    g = load_golden(name)
+    y = port.sgcn_conv(g["x"], g["pos_edge_index"], g["neg_edge_index"], g["lin_b_weight"],
+                       g["lin_b_bias"], g["lin_u_weight"], g["lin_u_bias"], first, norm_emb)
+    assert_close_rel(y, g["out"], 1e-5)
+
+
+def test_conv_base_and_dimpa_port():
+    g = load_golden("conv_norm_rw")
+    ei, w = port.conv_norm_rw(g["edge_index"], g["fill_value"], g["edge_weight"], 110)
+    assert torch.equal(ei, g["out_edge_index"])
+    assert_close_rel(w, g["out_weight"], 1e-6)
+    g = load_golden("conv_base")
+    assert_close_rel(port.conv_base(g["x"], g["edge_index"], g["edge_weight"], 0.5), g["out"])
+    assert_close_rel(port.conv_base(g["x"], g["edge_index"], None, 0.25),
+                     g["out_unweighted_fill025"])
+    g = load_golden("dimpa")
+    y = port.dimpa(g["x_s"], g["x_t"], g["edge_index"], g["edge_weight"], g["w_s"], g["w_t"], 2)
+    assert_close_rel(y, g["out"], 1e-5)
+
+
+def test_complex_relu_port():
+    g = load_golden("complex_relu")
+    r, i = port.complex_relu(g["real"], g["imag"])
+    assert torch.equal(r, g["out_real"]) and torch.equal(i, g["out_imag"])
+
+
+def test_row_subset_evaluator_matches_full():
+    g = load_golden("magnet_c1")
+    n = g["x_real"].size(0)
+    cr = port.magnet_norm(g["edge_index"], None, n, g["q"], "sym", 2.0)
+    rows = torch.tensor([0, 5, 17, 999, 512])
+    o_r, o_i = port.magnet_conv_rows(rows, g["x_real"], g["x_imag"], cr, g["weight"], g["bias"])
+    assert_close_rel(o_r, g["out_real"][rows], 1e-5)
+    assert_close_rel(o_i, g["out_imag"][rows], 1e-5)
