@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): MagNetConv forward on a
+synthetic DSBM graph, 1M nodes / 20M directed edges / 64 features, fp32, per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one MagNetConv.forward (K=1, q=0.25, 'sym', cached=True, plan already built) over
+the whole graph.  metric = input edges aggregated per second = E_input / t_step.
+  value   : inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e     : the same forward through the public layer API with HOST (pinned) feature buffers:
+            H2D of x_real/x_imag and D2H of out_real/out_imag inside the timed region.
+  roofline: dominant kernel = pgsd_spmm_csr; algorithmic bytes / its CUDA-event duration measured
+            inside the timed region, against MEASURED_PEAKS.json's hbm_gbs.
+  cpu_baseline: oracle/port.py (the reference's CPU op sequence) on a bounded 1/4-scale sample.
+N > 1 ("weak" scaling): the graph grows to N*1M nodes / N*20M edges, destination rows are
+sharded by node range, feature shards travel over NCCL in a ring pipelined with the per-shard
+column-block aggregation (pytorch_geometric_signed_directed_b200/distributed.py).
+`--impl reference` times the CPU port only (rank 0), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1_000_000
+E_PER_GPU = 20_000_000
+FEAT = 64
+METRIC = "edges aggregated/sec (MagNetConv fwd, 1M nodes/20M edges/64d per GPU)"
+UNIT = "edges/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmm_dram_traffic.json")) as fh:
+            return float(json.load(fh)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+
+def cpu_reference_run(steps: int, warmup: int, scale_div: int = 4):
+    """The reference's CPU op sequence (oracle/port.py: index_select -> mul -> scatter_add_, the
+    four Chebyshev chains, 4(K+1) matmuls) on all host cores, on a bounded sample: a DSBM graph
+    with the same mean degree and 1/scale_div of the nodes/edges of the per-GPU workload."""
+    from oracle import port
+    from pytorch_geometric_signed_directed_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n, e = N_PER_GPU // scale_div, E_PER_GPU // scale_div
+    ei, _ = synthetic.dsbm_edges(n, 3, num_edges=e, eta=0.1, size_ratio=1.5, seed=0)
+    g = torch.Generator().manual_seed(0)
+    xr = torch.rand(n, FEAT, generator=g) * 2 - 1
+    xi = torch.rand(n, FEAT, generator=g) * 2 - 1
+    w = torch.rand(2, FEAT, FEAT, generator=g) - 0.5
+    b = torch.zeros(FEAT)
+    with torch.no_grad():
+        cached = port.magnet_norm(ei, None, n, 0.25, "sym", 2.0)       # cached=True steady state
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            port.magnet_conv(xr, xi, ei, None, w, b, 0.25, "sym", cached_result=cached)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    t = sum(times) / len(times)
+    return {"value": ei.size(1) / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"DSBM {n} nodes / {ei.size(1)} edges / {FEAT} feat (1/{scale_div} of the per-GPU "
+                      f"workload, same mean degree), cached operator, {len(times)} timed forwards "
+                      f"after {warmup} warm-up, {t:.3f} s each"}, t
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    base, t = cpu_reference_run(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(n_gpus):
+    return {"workload": f"MagNetConv single-layer forward (K=1, q=0.25, sym, cached=True), synthetic DSBM "
+                        f"(cyclic K=3, eta=0.1, size_ratio=1.5), {n_gpus}x(1M nodes / 20M directed edges), "
+                        f"64->64 features, fp32 (BASELINE configs[1] layer shape)",
+            "nodes_per_gpu": N_PER_GPU, "edges_per_gpu": E_PER_GPU, "feat": FEAT,
+            "parallelism": "single GPU" if n_gpus == 1 else f"node-range row shards x{n_gpus}, NCCL ring halo exchange",
+            "l2": "inputs larger than L2 (x_real+x_imag 512 MB, plan 0.5 GB vs 126 MB L2); no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+
+def run_gpu_arm(args, rank, world):
+    import torch.distributed as dist
+    from pytorch_geometric_signed_directed_b200 import nn, ops, synthetic
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_total, e_total = N_PER_GPU * world, E_PER_GPU * world
+    t0 = time.time()
+    ei, _ = synthetic.dsbm_edges(n_total, 3, num_edges=e_total, eta=0.1, size_ratio=1.5, seed=0, device=dev)
+    e_input = ei.size(1)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    conv = nn.MagNetConv(FEAT, FEAT, K=1, q=0.25, trainable_q=False, cached=True).to(dev)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        conv.weight.copy_(torch.rand(2, FEAT, FEAT) - 0.5)
+        conv.bias.uniform_(-0.1, 0.1)
+
+    if world == 1:
+        n_local = n_total
+        x_real = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
+        x_imag = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
+        conv(x_real, x_imag, ei)                       # builds & caches the plan
+        plan = conv._plan
+        step = lambda: conv(x_real, x_imag, ei)
+        nnz, n_rows = plan.nnz, n_local
+    else:
+        from pytorch_geometric_signed_directed_b200 import distributed as pgd
+        sharded = pgd.ShardedMagNetConv(conv, n_total, rank, world)
+        sharded.build(ei)
+        n_local = sharded.n_local
+        x_real = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
+        x_imag = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
+        step = lambda: sharded(x_real, x_imag)
+        nnz, n_rows = sharded.local_nnz, n_local
+    if world > 1:
+        del ei
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] setup {time.time() - t0:.1f}s: N={n_total} E={e_input} local nnz={nnz}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.TIMING = []
+    launches0 = ops.LAUNCHES
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = ops.LAUNCHES - launches0
+    timing, ops.TIMING = ops.TIMING, None
+    clocks = sampler.stop()
+    kern = {}
+    for name, a, b in timing:
+        kern.setdefault(name, []).append(a.elapsed_time(b))
+    t_ms = torch.tensor([total_ms / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item())
+
+    # ---- end-to-end: host (pinned) features in, host (pinned) outputs back, every step
+    e2e = None
+    if world == 1:
+        hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
+        ho_r = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
+        ho_i = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
+        dx_r, dx_i = torch.empty_like(x_real), torch.empty_like(x_imag)
+
+        def e2e_step():
+            dx_r.copy_(hx_r, non_blocking=True)
+            dx_i.copy_(hx_i, non_blocking=True)
+            o_r, o_i = conv(dx_r, dx_i, ei)
+            ho_r.copy_(o_r, non_blocking=True)
+            ho_i.copy_(o_i, non_blocking=True)
+
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1) / n_e2e
+        e2e = {"value": e_input / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 2 * n_local * FEAT * 4, "d2h_bytes_per_step": 2 * n_local * FEAT * 4,
+               "steps": n_e2e, "note": "pinned host x_real/x_imag -> H2D -> MagNetConv.forward (C ABI) -> D2H "
+                                       "out_real/out_imag; graph plan cached on device (cached=True)"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (pgsd_spmm_csr, n_ops = 2)
+    peak, peak_src = measured_peak_gbs()
+    spmm_ms = statistics.mean(kern["spmm"]) if kern.get("spmm") else None
+    dense_ms = statistics.mean(kern["dense"]) if kern.get("dense") else None
+    # algorithmic bytes per launch: per stored entry 4 (col) + 2*4 (values) +
+    # 2 * F*4 (one feature-row gather per operator, no reuse assumed); per row 4 (row_ptr) +
+    # 2 * F*4 (T_real, T_imag written).
+    b_spmm = nnz * (4 + 8 + 2 * FEAT * 4) + (n_rows + 1) * 4 + 2 * n_rows * FEAT * 4
+    # whole layer: + dense reads of x_r, x_i and writes of out_r, out_i
+    b_layer = nnz * (4 + 8 + 2 * FEAT * 4) + (n_rows + 1) * 4 + 4 * n_rows * FEAT * 4
+    roof = {"bound": "hbm", "kernel": "spmm_rows_kernel (pgsd_spmm_csr, n_ops=2)", "unit": "GB/s",
+            "peak": peak, "peak_source": peak_src, "algorithmic_bytes": b_spmm,
+            "traffic": recorded_traffic()}
+    if spmm_ms:
+        roof["achieved"] = b_spmm / (spmm_ms * 1e-3) / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["kernel_ms"] = spmm_ms
+        roof["share_of_step"] = spmm_ms * (len(kern["spmm"]) / args.steps) / ms_per_step
+    roof["layer"] = {"algorithmic_bytes": b_layer, "achieved": b_layer / (ms_per_step * 1e-3) / 1e9,
+                     "frac": b_layer / (ms_per_step * 1e-3) / 1e9 / peak, "dense_ms": dense_ms}
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        log("timing the CPU baseline (oracle port) on the host cores ...")
+        cpu_base, _ = cpu_reference_run(2, 1)
+
+    line = {
+        "metric": METRIC, "value": e_input / (ms_per_step * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": bench_config(world),
+        "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks, "edges_total": e_input, "nnz_per_rank": nnz,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29511",
+                   os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
+                   "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    run_gpu_arm(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+/*
+ * pgsd_b200 -- C ABI of the B200-native signed/directed message-passing hot path.
+ *
+ * The reference (PyGSD 1.1.1, pure Python) has no FFI of its own: the boundary its models,
+ * examples and tests call is the Python class API (MagNetConv.forward, DiGCNConv.forward,
+ * SGCNConv.forward, Conv_Base.forward, DIMPA.forward).  The drop-in Python classes in
+ * `pytorch_geometric_signed_directed_b200/nn/` keep those signatures and bind the entry
+ * points below through ctypes (see INTEGRATION.md for the stub a reference maintainer
+ * would add).  Each entry point cites the reference code it replaces; paths are relative to
+ * /root/reference/torch_geometric_signed_directed/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *     the plan builders additionally synchronise that stream once to return `nnz`;
+ *   - functions return 0 (PGSD_OK) or a PGSD_ERR_* code; pgsd_last_error() returns the
+ *     message for the calling thread; nothing throws across the ABI;
+ *   - the library never allocates or frees caller memory: scratch space is sized by the
+ *     *_workspace_bytes queries and passed in;
+ *   - indices inside plans are int32 (N, nnz < 2^31); user edge lists are int64 as in PyG.
+ */
+#ifndef PGSD_B200_H
+#define PGSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGSD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PGSD_API __attribute__((visibility("default")))
+#else
+#define PGSD_API
+#endif
+
+#define PGSD_OK 0
+#define PGSD_ERR_INVALID 1     /* bad argument (null pointer, negative size, unsupported F) */
+#define PGSD_ERR_CUDA 2        /* a CUDA runtime call or kernel launch failed              */
+#define PGSD_ERR_WORKSPACE 3   /* workspace too small                                      */
+#define PGSD_ERR_RANGE 4       /* N or nnz exceeds the int32 plan format                   */
+
+typedef void* pgsd_stream_t;
+
+#define PGSD_F32 0
+#define PGSD_BF16 1
+
+PGSD_API int pgsd_abi_version(void);
+PGSD_API const char* pgsd_last_error(void);
+/* sm count / compute capability of the current device (cc must be 10.x for the kernels). */
+PGSD_API int pgsd_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+/* sizeof(pgsd_spmm_args) / sizeof(pgsd_dense_args) as compiled: lets a foreign-language binding
+ * verify its struct mirror before the first call. */
+PGSD_API int pgsd_sizeof_args(size_t* spmm_args_bytes_host, size_t* dense_args_bytes_host);
+
+/* ------------------------------------------------------------------------------------
+ * Plan builders: user COO (int64) -> CSR-by-destination (int32), built once per graph and
+ * cached by the Python layer under the reference's own cache rules.
+ * ---------------------------------------------------------------------------------- */
+
+/* Scratch bytes sufficient for any builder below on (num_nodes, num_edges). */
+PGSD_API int pgsd_plan_workspace_bytes(int64_t num_nodes, int64_t num_edges, size_t* bytes_host);
+
+/* Generic aggregation plan: out[dst] (+)= w * x[src]; duplicates and self-loops are kept as
+ * separate entries, entries of a row stay in edge order (stable).
+ * Replaces the index plumbing of PyG MessagePassing.propagate as used by
+ *   nn/directed/DiGCNConv.py:86-89 (weighted add, dst = edge_index[1]),
+ *   nn/signed/SGCNConv.py:101-118,128-129 (unweighted mean, pass edge_weight = NULL).
+ * row_ptr [num_dst+1], col [E], val [E] (ignored when edge_weight is NULL). */
+PGSD_API int pgsd_build_csr(const int64_t* edge_src, const int64_t* edge_dst, const float* edge_weight,
+                   int64_t num_edges, int64_t num_dst, int64_t num_src,
+                   int32_t* row_ptr, int32_t* col, float* val,
+                   void* workspace, size_t workspace_bytes, pgsd_stream_t stream);
+
+/* Random-walk normalised plan with "remaining" self loops:
+ *   A_hat = A(off-diagonal) + diag(existing self-loop weight, else fill_value);
+ *   w' = w / rowsum_dst(A_hat);   out[dst] = diag[dst]*x[dst] + sum w' * x[src].
+ * Replaces conv_norm_rw + Conv_Base.message, nn/general/conv_base.py:12-31,98-117
+ * (dst = edge_index[0], src = edge_index[1]; DIMPA's transposed call swaps them,
+ * nn/directed/DIMPA.py:50-53).  edge_weight may be NULL (ones).
+ * add_self_loops = 0 reproduces conv_norm_rw(add_self_loops=False): self-loop edges stay
+ * ordinary entries, diag = 0, fill_value is ignored.
+ * row_ptr [N+1], col/val [E] (capacity), diag [N]; *nnz_host = stored entries. */
+PGSD_API int pgsd_build_csr_rw_norm(const int64_t* edge_dst, const int64_t* edge_src,
+                           const float* edge_weight, int64_t num_edges, int64_t num_nodes,
+                           float fill_value, int add_self_loops, int32_t* row_ptr,
+                           int32_t* col, float* val, float* diag, int64_t* nnz_host,
+                           void* workspace, size_t workspace_bytes, pgsd_stream_t stream);
+
+/* Magnetic (Hermitian) Laplacian plan, scaled for the Chebyshev recurrence:
+ *   L~ = 2 L / lambda_max - I,  L = I - D^-1/2 A_s D^-1/2 (.) exp(i 2 pi q Theta)   ('sym')
+ *                               L = D - A_s (.) exp(i 2 pi q Theta)                (none)
+ * with A_s = (A + A^T)/2, Theta = A - A^T, self-loops dropped, duplicate edges summed.
+ * Replaces utils/directed/get_magnetic_Laplacian.py:44-87 + MagNetConv.__norm__
+ * (nn/directed/MagNetConv.py:78-120); signed_mode 1/2 replaces
+ * utils/general/get_magnetic_signed_Laplacian.py:45-92 (absolute_degree True/False) +
+ * nn/general/MSConv.py:76-119.
+ * The plan is stored for the direction the reference actually aggregates in
+ * (source_to_target): row a lists sources b with value L~[b,a]; entries are in
+ * (a,b)-sorted order, which is also the order of the reference's coalesced list, so
+ * `cached_result` can be re-materialised from it (indices bit-exact).
+ *   val_real/val_imag [2E] capacity, diag_real [N] (= 2*diag(L)/lambda_max - 1; the
+ *   imaginary diagonal is identically 0).  normalization: 1 = 'sym', 0 = None. */
+PGSD_API int pgsd_build_magnetic_laplacian(const int64_t* edge_row, const int64_t* edge_col,
+                                  const float* edge_weight, int64_t num_edges,
+                                  int64_t num_nodes, double q, int normalization,
+                                  float lambda_max, int signed_mode,
+                                  int32_t* row_ptr, int32_t* col, float* val_real,
+                                  float* val_imag, float* diag_real, int64_t* nnz_host,
+                                  void* workspace, size_t workspace_bytes,
+                                  pgsd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Sparse aggregation (the hot loop): for every destination row r and operator k < n_ops
+ *   agg_k[r] = diag_k[r] * x_k[r] + sum_{e in row r} val_k[e] * x_k[col[e]]
+ *   agg_k[r] *= 1 / max(row_len(r), 1)                         if mean
+ *   y_k[r]   = alpha * agg_k[r] + beta * z_k[r] + bias         (z_k, bias optional)
+ * The n_ops (1 or 2) operators share (row_ptr, col) and are evaluated in one pass.
+ * Replaces PyG propagate = index_select + message + scatter_add as called from
+ *   nn/directed/MagNetConv.py:196-236,251-252 (n_ops = 2: real & imaginary operator;
+ *     alpha = 2, beta = -1, z = T_{k-2} fuses the Chebyshev recurrence of :214-216),
+ *   nn/directed/DiGCNConv.py:86-94 (bias = update()),
+ *   nn/signed/SGCNConv.py:101-118 (mean, val = NULL),
+ *   nn/general/conv_base.py:111-117.
+ * x/z/y are row-major with leading dimensions in ELEMENTS so column slices of wider
+ * buffers can be aggregated/written in place (SGCNConv.py:109-119 half-width slices).
+ * ---------------------------------------------------------------------------------- */
+typedef struct pgsd_spmm_args {
+  int64_t n_rows;            /* destination rows                                      */
+  int32_t feat;              /* F: feature columns aggregated                         */
+  int32_t n_ops;             /* 1 or 2                                                */
+  int32_t dtype;             /* PGSD_F32 or PGSD_BF16 (x, z, y); accumulation is fp32 */
+  int32_t mean;              /* 1: divide by max(row length, 1)                       */
+  const int32_t* row_ptr;    /* [n_rows + 1]                                          */
+  const int32_t* col;        /* [nnz]                                                 */
+  const float* val[2];       /* [nnz] or NULL (implicit 1.0)                          */
+  const float* diag[2];      /* [n_rows] or NULL (use diag_const)                     */
+  float diag_const[2];       /* 0 disables the diagonal term                          */
+  const void* x[2];          /* [n_src, ldx] gathered features                        */
+  int64_t ldx[2];
+  float alpha, beta;
+  const void* z[2];          /* [n_rows, ldz] or NULL                                 */
+  int64_t ldz[2];
+  void* y[2];                /* [n_rows, ldy]                                         */
+  int64_t ldy[2];
+  const float* bias;         /* [F] or NULL                                           */
+  int32_t variant;           /* 0 = library default; >0 selects a tuning variant      */
+  int32_t reserved;
+} pgsd_spmm_args;
+
+PGSD_API int pgsd_spmm_csr(const pgsd_spmm_args* args, pgsd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense feature transform next to the aggregation:
+ *   acc_g[r, :] = sum_{t : group[t] == g} X_t[r, :k_t] @ W_t          (W_t is [k_t, n_out])
+ *   combine == 0:  y0 = acc_0 + bias
+ *   combine == 1:  y0 = acc_0 - acc_1 + bias ;  y1 = acc_0 + acc_1 + bias
+ * combine == 1 is MagNetConv's real/imag mixing: out_real = A - B + b, out_imag = A + B + b
+ * with A = sum_k T_k(L~_r) x_real W_k (group 0), B = sum_k T_k(L~_i) x_imag W_k (group 1)
+ * (nn/directed/MagNetConv.py:189-247; two of its four chains are duplicates).
+ * combine == 0 replaces torch.matmul / nn.Linear at nn/directed/DiGCNConv.py:66,
+ * nn/directed/DiGCN_Inception_Block.py:44, nn/signed/SGCNConv.py:102-121 (terms = the
+ * column blocks of the concatenated input, so no torch.cat is materialised).
+ * W_t element (k, n) is w[t][k * ldw_k[t] + n * ldw_n[t]] which covers both the
+ * [in, out] Parameter layout and nn.Linear's [out, in] layout (and column slices of it).
+ * fp32 in / fp32 accumulate; PGSD_BF16 reads/writes bf16 X/Y with fp32 weights & accumulate.
+ * ---------------------------------------------------------------------------------- */
+#define PGSD_DENSE_MAX_TERMS 16
+typedef struct pgsd_dense_args {
+  int64_t n_rows;
+  int32_t n_out;
+  int32_t n_terms;
+  int32_t dtype;
+  int32_t combine;
+  const void* x[PGSD_DENSE_MAX_TERMS];
+  int64_t ldx[PGSD_DENSE_MAX_TERMS];
+  int32_t k[PGSD_DENSE_MAX_TERMS];
+  int32_t group[PGSD_DENSE_MAX_TERMS];
+  const float* w[PGSD_DENSE_MAX_TERMS];
+  int64_t ldw_k[PGSD_DENSE_MAX_TERMS];
+  int64_t ldw_n[PGSD_DENSE_MAX_TERMS];
+  const float* bias;         /* [n_out] or NULL */
+  void* y[2];
+  int64_t ldy[2];
+  int32_t relu_mode;         /* 0 none; 1 complex ReLU (mask = y0 >= 0 applied to y0, y1):
+                                nn/directed/complex_relu.py:17-34 (combine == 1 only)   */
+  int32_t variant;
+} pgsd_dense_args;
+
+PGSD_API int pgsd_dense_transform(const pgsd_dense_args* args, pgsd_stream_t stream);
+
+/* Halo pack for the node-range sharded path (no reference counterpart: the reference is
+ * single-device): out[i, :] = x[index[i], :]  -- rows another rank asked for. */
+PGSD_API int pgsd_gather_rows(const void* x, int64_t ldx, const int32_t* index, int64_t n_index,
+                     int32_t feat, int32_t dtype, void* out, int64_t ldo,
+                     pgsd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGSD_B200_H */

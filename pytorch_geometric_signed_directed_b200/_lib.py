@@ -1,0 +1,99 @@
+"""ctypes binding of libpgsd_b200.so (the C ABI declared in include/pgsd_b200.h).
+
+There is deliberately NO fallback: if the CUDA library has not been built, or a layer is fed
+CPU tensors, the call raises.  (The CPU restatement under oracle/ is test infrastructure and
+is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libpgsd_b200.so")
+
+PGSD_F32, PGSD_BF16 = 0, 1
+DENSE_MAX_TERMS = 16
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class SpmmArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", _i64), ("feat", _i32), ("n_ops", _i32), ("dtype", _i32), ("mean", _i32),
+        ("row_ptr", _vp), ("col", _vp),
+        ("val", _vp * 2), ("diag", _vp * 2), ("diag_const", _f32 * 2),
+        ("x", _vp * 2), ("ldx", _i64 * 2),
+        ("alpha", _f32), ("beta", _f32),
+        ("z", _vp * 2), ("ldz", _i64 * 2),
+        ("y", _vp * 2), ("ldy", _i64 * 2),
+        ("bias", _vp), ("variant", _i32), ("reserved", _i32),
+    ]
+
+
+class DenseArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", _i64), ("n_out", _i32), ("n_terms", _i32), ("dtype", _i32), ("combine", _i32),
+        ("x", _vp * DENSE_MAX_TERMS), ("ldx", _i64 * DENSE_MAX_TERMS),
+        ("k", _i32 * DENSE_MAX_TERMS), ("group", _i32 * DENSE_MAX_TERMS),
+        ("w", _vp * DENSE_MAX_TERMS), ("ldw_k", _i64 * DENSE_MAX_TERMS),
+        ("ldw_n", _i64 * DENSE_MAX_TERMS),
+        ("bias", _vp), ("y", _vp * 2), ("ldy", _i64 * 2),
+        ("relu_mode", _i32), ("variant", _i32),
+    ]
+
+
+_PROTOTYPES = {
+    "pgsd_abi_version": (C.c_int, []),
+    "pgsd_last_error": (C.c_char_p, []),
+    "pgsd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "pgsd_sizeof_args": (C.c_int, [C.POINTER(C.c_size_t)] * 2),
+    "pgsd_plan_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(C.c_size_t)]),
+    "pgsd_build_csr": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp,
+                                 C.c_size_t, _vp]),
+    "pgsd_build_csr_rw_norm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp, _vp, _vp,
+                                         _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
+    "pgsd_build_magnetic_laplacian": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_double, C.c_int,
+                                                _f32, C.c_int, _vp, _vp, _vp, _vp, _vp,
+                                                C.POINTER(_i64), _vp, C.c_size_t, _vp]),
+    "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),
+    "pgsd_dense_transform": (C.c_int, [C.POINTER(DenseArgs), _vp]),
+    "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib: Optional[C.CDLL] = None
+
+
+class PgsdError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PgsdError(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(python -m pytorch_geometric_signed_directed_b200.build); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.pgsd_abi_version() != 1:
+            raise PgsdError("libpgsd_b200.so ABI version mismatch; rebuild")
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        lib.pgsd_sizeof_args(C.byref(a), C.byref(b))
+        if (a.value, b.value) != (C.sizeof(SpmmArgs), C.sizeof(DenseArgs)):
+            raise PgsdError("ctypes struct mirror out of sync with include/pgsd_b200.h; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().pgsd_last_error().decode(errors="replace")
+        raise PgsdError(f"{what or 'pgsd'} failed (code {rc}): {msg}")

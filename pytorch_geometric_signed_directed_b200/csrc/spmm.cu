@@ -1,0 +1,423 @@
+// CSR-by-destination sparse aggregation kernels (the hot loop of every layer).
+//
+//   agg_k[r] = diag_k[r] * x_k[r] + sum_{e in row r} val_k[e] * x_k[col[e]]      k < n_ops
+//   y_k[r]   = alpha * agg_k[r] (/ max(len,1) if mean) + beta * z_k[r] + bias
+//
+// Reference semantics: PyG MessagePassing.propagate (index_select -> message -> scatter_add)
+// as driven by nn/directed/MagNetConv.py:196-236,251-252, nn/directed/DiGCNConv.py:86-94,
+// nn/signed/SGCNConv.py:101-118, nn/general/conv_base.py:111-117.  The reference materialises
+// two [nnz, F] temporaries per call; here every destination row is owned by one warp, so
+// there are no atomics, no temporaries and the result is deterministic.
+//
+// Work decomposition (rows kernel): one warp per destination row, persistent grid-stride over
+// rows.  A feature row of R = F*sizeof(elem) bytes is covered by LPR = R/(4*W) lanes that each
+// load W 32-bit words (W=4: LDG.128, W=8: LDG.256), so a warp gathers G = 32/LPR neighbour
+// rows per load instruction and keeps U*n_ops such loads in flight per lane.  Column indices
+// and values are fetched 32 at a time with one coalesced load per array and broadcast with
+// warp shuffles; the G partial sums are combined with an xor-shuffle tree at the end of the
+// row.  Feature gathers carry an L2 evict_last policy (each x row is re-read ~deg times and
+// x is 4x larger than L2 at the north-star size); index/value/output streams carry evict_first.
+#include "common.cuh"
+
+namespace pgsd {
+
+struct SpmmParams {
+  int64_t n_rows;
+  int32_t feat;
+  int32_t lpr_active;  // lanes per row that carry data
+  int32_t mean;
+  const int32_t* row_ptr;
+  const int32_t* col;
+  const float* val[2];
+  const float* diag[2];
+  float diag_const[2];
+  const char* x[2];
+  int64_t ldx_bytes[2];
+  float alpha, beta;
+  const char* z[2];
+  int64_t ldz_bytes[2];
+  char* y[2];
+  int64_t ldy_bytes[2];
+  const float* bias;
+};
+
+// ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
+template <int W, bool BF16>
+struct RowVec {
+  static constexpr int EPL = BF16 ? 2 * W : W;  // fp32 elements per lane
+  static __device__ __forceinline__ void zero(float (&d)[EPL]) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) d[i] = 0.f;
+  }
+  static __device__ __forceinline__ void expand(const float (&w)[W], float (&d)[EPL]) {
+    if constexpr (BF16) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        uint32_t u = __float_as_uint(w[i]);
+        d[2 * i] = bf16_lo(u);
+        d[2 * i + 1] = bf16_hi(u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) d[i] = w[i];
+    }
+  }
+  // gather (L2 evict_last)
+  static __device__ __forceinline__ void gather(const char* p, uint64_t pol, float (&d)[EPL]) {
+    float w[W];
+    if constexpr (W == 8) {
+      float8 t = ld_gather_v8(p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = t.v[i];
+    } else {
+      float4 t = ld_gather_v4(p, pol);
+      w[0] = t.x, w[1] = t.y, w[2] = t.z, w[3] = t.w;
+    }
+    expand(w, d);
+  }
+  // plain read of an owned row (diag / z terms)
+  static __device__ __forceinline__ void load(const char* p, float (&d)[EPL]) {
+    float w[W];
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      w[4 * i] = t.x, w[4 * i + 1] = t.y, w[4 * i + 2] = t.z, w[4 * i + 3] = t.w;
+    }
+    expand(w, d);
+  }
+  static __device__ __forceinline__ void store(char* p, const float (&d)[EPL], uint64_t pol) {
+    float w[W];
+    if constexpr (BF16) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) w[i] = __uint_as_float(pack_bf16(d[2 * i], d[2 * i + 1]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) w[i] = d[i];
+    }
+#pragma unroll
+    for (int i = 0; i < W / 4; ++i)
+      st_stream_v4(p + 16 * i, make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]), pol);
+  }
+};
+
+template <int W, int LPR, int NOPS, int U, bool BF16, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmParams p) {
+  using RV = RowVec<W, BF16>;
+  constexpr int EPL = RV::EPL;
+  constexpr int G = 32 / LPR;
+  constexpr unsigned FULL = 0xffffffffu;
+
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR;
+  const int l = lane % LPR;
+  const bool lane_active = l < p.lpr_active;
+  const int64_t lane_off = int64_t(l) * (W * 4);  // byte offset inside a feature row
+  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_stream = policy_evict_first();
+
+  const int64_t warps_total = int64_t(gridDim.x) * (THREADS / 32);
+  int64_t row = int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5);
+
+  for (; row < p.n_rows; row += warps_total) {
+    const int start = __ldg(p.row_ptr + row);
+    const int end = __ldg(p.row_ptr + row + 1);
+
+    float acc[NOPS][EPL];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
+
+    for (int base = start; base < end; base += 32) {
+      const int e = base + lane;
+      int c = 0;
+      float v[NOPS];
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) v[k] = 0.f;
+      if (e < end) {
+        c = ld_stream_i32(p.col + e, pol_stream);
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k) v[k] = p.val[k] ? ld_stream_f32(p.val[k] + e, pol_stream) : 1.f;
+      }
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; j += G * U) {
+        float d[NOPS][U][EPL];
+        float vv[NOPS][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = j + u * G + g;
+          const int cc = __shfl_sync(FULL, c, idx & 31);
+          const bool ok = (idx < cnt) && lane_active;
+#pragma unroll
+          for (int k = 0; k < NOPS; ++k) {
+            const float t = __shfl_sync(FULL, v[k], idx & 31);
+            vv[k][u] = ok ? t : 0.f;
+            if (ok)
+              RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
+            else
+              RV::zero(d[k][u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
+      }
+    }
+
+    // combine the G neighbour groups
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) acc[k][i] += __shfl_xor_sync(FULL, acc[k][i], off);
+
+    if (g == 0 && lane_active) {
+      const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) {
+        const bool has_diag = p.diag[k] != nullptr;
+        const float dg = has_diag ? __ldg(p.diag[k] + row) : p.diag_const[k];
+        if (has_diag || dg != 0.f) {
+          float xr[EPL];
+          RV::load(p.x[k] + row * p.ldx_bytes[k] + lane_off, xr);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(dg, xr[i], acc[k][i]);
+        }
+        float out[EPL];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) out[i] = p.alpha * (acc[k][i] * inv);
+        if (p.z[k] != nullptr) {
+          float zr[EPL];
+          RV::load(p.z[k] + row * p.ldz_bytes[k] + lane_off, zr);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] = fmaf(p.beta, zr[i], out[i]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + l * EPL + i);
+        }
+        RV::store(p.y[k] + row * p.ldy_bytes[k] + lane_off, out, pol_stream);
+      }
+    }
+  }
+}
+
+// ---- scalar fallback: any F, any alignment (reference tests use F = 2, 3) -------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256) spmm_rows_scalar_kernel(const SpmmParams p, int n_ops) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = int64_t(gridDim.x) * 8;
+  auto rd = [&](const char* base, int64_t ld_bytes, int64_t r, int f) -> float {
+    const char* q = base + r * ld_bytes;
+    if constexpr (BF16)
+      return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(q)[f]);
+    else
+      return reinterpret_cast<const float*>(q)[f];
+  };
+  for (int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5); row < p.n_rows;
+       row += warps_total) {
+    const int start = p.row_ptr[row], end = p.row_ptr[row + 1];
+    const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
+    for (int k = 0; k < n_ops; ++k) {
+      for (int f = lane; f < p.feat; f += 32) {
+        float acc = 0.f;
+        for (int e = start; e < end; ++e) {
+          const float w = p.val[k] ? p.val[k][e] : 1.f;
+          acc = fmaf(w, rd(p.x[k], p.ldx_bytes[k], p.col[e], f), acc);
+        }
+        const bool has_diag = p.diag[k] != nullptr;
+        const float dg = has_diag ? p.diag[k][row] : p.diag_const[k];
+        if (has_diag || dg != 0.f) acc = fmaf(dg, rd(p.x[k], p.ldx_bytes[k], row, f), acc);
+        float out = p.alpha * (acc * inv);
+        if (p.z[k]) out = fmaf(p.beta, rd(p.z[k], p.ldz_bytes[k], row, f), out);
+        if (p.bias) out += p.bias[f];
+        char* q = p.y[k] + row * p.ldy_bytes[k];
+        if constexpr (BF16)
+          reinterpret_cast<__nv_bfloat16*>(q)[f] = __float2bfloat16_rn(out);
+        else
+          reinterpret_cast<float*>(q)[f] = out;
+      }
+    }
+  }
+}
+
+// ---- row gather (halo pack) ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const char* x, int64_t ldx_bytes,
+                                                          const int32_t* index, int64_t n,
+                                                          int row_bytes, char* out,
+                                                          int64_t ldo_bytes) {
+  const int chunks = row_bytes / 16;  // 16-byte chunks per row (host guarantees divisibility)
+  const int64_t total = n * chunks;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+       t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t i = t / chunks;
+    const int ch = int(t % chunks);
+    const float4 v =
+        __ldg(reinterpret_cast<const float4*>(x + int64_t(index[i]) * ldx_bytes) + ch);
+    reinterpret_cast<float4*>(out + i * ldo_bytes)[ch] = v;
+  }
+}
+
+// ---- host dispatch -------------------------------------------------------------------------
+template <int W, int LPR, int NOPS, int U, bool BF16>
+static int launch_rows(const SpmmParams& p, cudaStream_t st) {
+  constexpr int THREADS = 256;
+  // register budget: keep >= 3 CTAs (24 warps) resident when the tile is small
+  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;
+  auto kern = spmm_rows_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
+  int occ = 0;
+  PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  if (occ < 1) occ = 1;
+  int64_t need = ceil_div<int64_t>(p.n_rows, THREADS / 32);
+  int64_t grid = int64_t(sm_count()) * occ;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<dim3((unsigned)grid), dim3(THREADS), 0, st>>>(p);
+  PGSD_LAUNCH_CHECK("spmm_rows_kernel");
+  return PGSD_OK;
+}
+
+template <int W, int NOPS, int U, bool BF16>
+static int dispatch_lpr(int lpr, const SpmmParams& p, cudaStream_t st) {
+  switch (lpr) {
+    case 1: return launch_rows<W, 1, NOPS, U, BF16>(p, st);
+    case 2: return launch_rows<W, 2, NOPS, U, BF16>(p, st);
+    case 4: return launch_rows<W, 4, NOPS, U, BF16>(p, st);
+    case 8: return launch_rows<W, 8, NOPS, U, BF16>(p, st);
+    case 16: return launch_rows<W, 16, NOPS, U, BF16>(p, st);
+    case 32: return launch_rows<W, 32, NOPS, U, BF16>(p, st);
+  }
+  return fail(PGSD_ERR_INVALID, "spmm: bad lanes-per-row %d", lpr);
+}
+
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace pgsd
+
+using namespace pgsd;
+
+extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
+  PGSD_REQUIRE(a != nullptr, "spmm: args is null");
+  PGSD_REQUIRE(a->n_ops == 1 || a->n_ops == 2, "spmm: n_ops must be 1 or 2 (got %d)", a->n_ops);
+  PGSD_REQUIRE(a->dtype == PGSD_F32 || a->dtype == PGSD_BF16, "spmm: bad dtype %d", a->dtype);
+  PGSD_REQUIRE(a->n_rows >= 0 && a->feat >= 0, "spmm: negative size");
+  PGSD_REQUIRE(a->n_rows < (int64_t(1) << 31), "spmm: n_rows exceeds int32 plan format");
+  if (a->n_rows == 0 || a->feat == 0) return PGSD_OK;
+  PGSD_REQUIRE(a->row_ptr && a->col, "spmm: row_ptr/col is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int es = a->dtype == PGSD_BF16 ? 2 : 4;
+
+  SpmmParams p{};
+  p.n_rows = a->n_rows;
+  p.feat = a->feat;
+  p.mean = a->mean;
+  p.row_ptr = a->row_ptr;
+  p.col = a->col;
+  p.alpha = a->alpha;
+  p.beta = a->beta;
+  p.bias = a->bias;
+  bool vec16 = (int64_t(a->feat) * es) % 16 == 0;
+  bool vec32 = (int64_t(a->feat) * es) % 32 == 0;
+  for (int k = 0; k < a->n_ops; ++k) {
+    PGSD_REQUIRE(a->x[k] && a->y[k], "spmm: x[%d]/y[%d] is null", k, k);
+    PGSD_REQUIRE(a->ldx[k] >= a->feat && a->ldy[k] >= a->feat, "spmm: leading dim < feat");
+    p.val[k] = a->val[k];
+    p.diag[k] = a->diag[k];
+    p.diag_const[k] = a->diag_const[k];
+    p.x[k] = static_cast<const char*>(a->x[k]);
+    p.ldx_bytes[k] = a->ldx[k] * es;
+    p.z[k] = static_cast<const char*>(a->z[k]);
+    p.ldz_bytes[k] = a->ldz[k] * es;
+    p.y[k] = static_cast<char*>(a->y[k]);
+    p.ldy_bytes[k] = a->ldy[k] * es;
+    auto ok = [&](size_t al) {
+      return aligned(a->x[k], al) && aligned(a->y[k], al) && p.ldx_bytes[k] % al == 0 &&
+             p.ldy_bytes[k] % al == 0 &&
+             (a->z[k] == nullptr || (aligned(a->z[k], al) && p.ldz_bytes[k] % al == 0));
+    };
+    vec16 = vec16 && ok(16);
+    vec32 = vec32 && ok(32);
+  }
+  const int64_t row_bytes = int64_t(a->feat) * es;
+  // variant encoding (0 = library default): bits 0-3 = loads in flight per lane and operator
+  // (U = 2/4/8), bit 4 = prefer 128-bit gathers, bit 5 = prefer 256-bit gathers.
+  int U = a->variant & 0xf;
+  const bool want128 = (a->variant & 0x10) != 0;
+  const bool want256 = (a->variant & 0x20) != 0;
+  const bool can256 = vec32 && row_bytes <= 32 * 32;
+  const bool can128 = vec16 && row_bytes <= 32 * 16;
+  int W = 0;
+  if (want256 && can256) W = 8;
+  else if (want128 && can128) W = 4;
+  else if (can128) W = 4;
+  else if (can256) W = 8;
+
+  if (W == 0) {
+    // odd widths / unaligned slices (the reference's own tests use F = 2 and 3)
+    int64_t grid = ceil_div<int64_t>(a->n_rows, 8);
+    if (grid > int64_t(sm_count()) * 8) grid = int64_t(sm_count()) * 8;
+    if (a->dtype == PGSD_BF16)
+      spmm_rows_scalar_kernel<true><<<(unsigned)grid, 256, 0, st>>>(p, a->n_ops);
+    else
+      spmm_rows_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(p, a->n_ops);
+    PGSD_LAUNCH_CHECK("spmm_rows_scalar_kernel");
+    return PGSD_OK;
+  }
+
+  p.lpr_active = int(row_bytes / (4 * W));
+  int lpr = 1;
+  while (lpr < p.lpr_active) lpr <<= 1;
+  if (U != 2 && U != 4 && U != 8) U = (W == 8) ? 2 : 4;
+  if (W == 8 && U == 8) U = 4;
+
+  if (a->dtype == PGSD_BF16) {
+    if (a->n_ops == 2) {
+      // two operators in bf16: run them as two single-operator passes
+      pgsd_spmm_args one = *a;
+      one.n_ops = 1;
+      int rc = pgsd_spmm_csr(&one, stream);
+      if (rc != PGSD_OK) return rc;
+      one.val[0] = a->val[1], one.diag[0] = a->diag[1], one.diag_const[0] = a->diag_const[1];
+      one.x[0] = a->x[1], one.ldx[0] = a->ldx[1], one.z[0] = a->z[1], one.ldz[0] = a->ldz[1];
+      one.y[0] = a->y[1], one.ldy[0] = a->ldy[1];
+      return pgsd_spmm_csr(&one, stream);
+    }
+    if (W == 8) return dispatch_lpr<8, 1, 2, true>(lpr, p, st);
+    return dispatch_lpr<4, 1, 4, true>(lpr, p, st);
+  }
+  if (a->n_ops == 2) {
+    if (W == 8) return U == 2 ? dispatch_lpr<8, 2, 2, false>(lpr, p, st)
+                              : dispatch_lpr<8, 2, 4, false>(lpr, p, st);
+    if (U == 2) return dispatch_lpr<4, 2, 2, false>(lpr, p, st);
+    if (U == 8) return dispatch_lpr<4, 2, 8, false>(lpr, p, st);
+    return dispatch_lpr<4, 2, 4, false>(lpr, p, st);
+  }
+  if (W == 8) return U == 2 ? dispatch_lpr<8, 1, 2, false>(lpr, p, st)
+                            : dispatch_lpr<8, 1, 4, false>(lpr, p, st);
+  if (U == 2) return dispatch_lpr<4, 1, 2, false>(lpr, p, st);
+  if (U == 8) return dispatch_lpr<4, 1, 8, false>(lpr, p, st);
+  return dispatch_lpr<4, 1, 4, false>(lpr, p, st);
+}
+
+extern "C" int pgsd_gather_rows(const void* x, int64_t ldx, const int32_t* index,
+                                int64_t n_index, int32_t feat, int32_t dtype, void* out,
+                                int64_t ldo, pgsd_stream_t stream) {
+  PGSD_REQUIRE(dtype == PGSD_F32 || dtype == PGSD_BF16, "gather_rows: bad dtype");
+  if (n_index == 0 || feat == 0) return PGSD_OK;
+  PGSD_REQUIRE(x && index && out, "gather_rows: null pointer");
+  const int es = dtype == PGSD_BF16 ? 2 : 4;
+  const int64_t row_bytes = int64_t(feat) * es;
+  PGSD_REQUIRE(row_bytes % 16 == 0 && (ldx * es) % 16 == 0 && (ldo * es) % 16 == 0 &&
+                   aligned(x, 16) && aligned(out, 16),
+               "gather_rows: rows must be 16-byte aligned multiples of 16 bytes");
+  int64_t total = n_index * (row_bytes / 16);
+  int64_t grid = ceil_div<int64_t>(total, 256);
+  if (grid > int64_t(sm_count()) * 16) grid = int64_t(sm_count()) * 16;
+  gather_rows_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const char*>(x), ldx * es, index, n_index, int(row_bytes),
+      static_cast<char*>(out), ldo * es);
+  PGSD_LAUNCH_CHECK("gather_rows_kernel");
+  return PGSD_OK;
+}

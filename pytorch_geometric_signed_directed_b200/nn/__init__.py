@@ -1,0 +1,11 @@
+"""Host-side mirror of the reference's conv-layer API (torch_geometric_signed_directed.nn):
+same class names, constructor and forward signatures, parameter names and error behaviour,
+backed by the sm_100a kernels in libpgsd_b200.so."""
+from .magnet_conv import MagNetConv, MSConv
+from .digcn_conv import DiGCNConv, DiGCN_InceptionBlock
+from .sgcn_conv import SGCNConv
+from .mixed_path import Conv_Base, DIMPA
+from .complex_relu import complex_relu_layer
+
+__all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv",
+           "Conv_Base", "DIMPA", "complex_relu_layer"]

@@ -1,0 +1,217 @@
+"""Drop-in MagNetConv / MSConv on the B200 kernels.
+
+Same constructor, forward signature, parameter names/shapes (`weight [K+1, in, out]`, `bias
+[out]`, optional `q`), cache rules, error messages and `__repr__` as the reference's
+`nn/directed/MagNetConv.py:44-257` and `nn/general/MSConv.py:42-238`, so model wrappers
+(`MagNet_node_classification.py:79`, `MSGNN.py`) and existing state_dicts work unchanged.
+
+What runs instead of the reference's 4*(K+1) matmuls + 4*K PyG propagates per forward:
+  * plan (once per graph / per call when cached=False): `pgsd_build_magnetic_laplacian`
+  * K launches of `pgsd_spmm_csr` with n_ops = 2 (real & imaginary operator share the
+    pattern; the Chebyshev recurrence 2*L~T_{k-1} - T_{k-2} is the kernel epilogue)
+  * one `pgsd_dense_transform` with combine = 1:  out_real = A - B + b, out_imag = A + B + b
+The reference's quirks are reproduced on purpose: aggregation is source_to_target (the
+`target_to_source` default at MagNetConv.py:51 is dead code) and its four chains
+collapse to A and B (two are duplicates).
+
+Forward only in this round: outputs carry no autograd graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+from torch.nn import Parameter
+
+from .. import ops, plan as _plan
+from .._lib import DENSE_MAX_TERMS
+
+
+def _glorot(t: Tensor) -> None:
+    # PyG inits.glorot: U(-a, a), a = sqrt(6 / (size(-2) + size(-1)))
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+class _MagneticChebConv(torch.nn.Module):
+    _signed = False
+
+    def __init__(self, in_channels: int, out_channels: int, K: int, q: float, trainable_q: bool,
+                 normalization: Optional[str] = 'sym', cached: bool = False, bias: bool = True,
+                 absolute_degree: bool = True, **kwargs):
+        super().__init__()
+        assert K > 0
+        assert normalization in [None, 'sym'], 'Invalid normalization'
+        # accepted for signature compatibility with MessagePassing(**kwargs); the aggregation
+        # direction is fixed to what the reference really does (source_to_target)
+        self.aggr = kwargs.get('aggr', 'add')
+        self.flow = 'source_to_target'
+        self.node_dim = -2
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.normalization = normalization
+        self.cached = cached
+        self.trainable_q = trainable_q
+        self.absolute_degree = absolute_degree
+        if trainable_q:
+            self.q = Parameter(torch.Tensor(1).fill_(q))
+        else:
+            self.q = q
+        self.weight = Parameter(torch.Tensor(K + 1, in_channels, out_channels))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.fused_complex_relu = False  # opt-in epilogue (complex_relu.py:21-22)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _glorot(self.weight)
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+        self._plan = None
+        self._cached_result = None
+        self.cached_num_edges = None
+        self.cached_q = None
+
+    # `cached_result` keeps the reference's tensor layout but is materialised lazily from the
+    # CSR plan (it is 3N + nnz entries of int64 pairs the kernels never read).
+    @property
+    def cached_result(self):
+        if self._plan is None:
+            return None
+        if self._cached_result is None:
+            self._cached_result = _plan.magnetic_cached_result(self._plan)
+        return self._cached_result
+
+    @cached_result.setter
+    def cached_result(self, value):
+        if value is not None:
+            raise AttributeError("cached_result is derived from the CSR plan; assign None to reset")
+        self._plan, self._cached_result = None, None
+
+    def _q_value(self) -> float:
+        return float(self.q.detach().item()) if isinstance(self.q, Tensor) else float(self.q)
+
+    def _signed_mode(self) -> int:
+        if not self._signed:
+            return 0
+        return 1 if self.absolute_degree else 2
+
+    def _lambda_max_unnormalised(self, edge_index, edge_weight, n, q) -> float:
+        """normalization=None without lambda_max: the reference runs scipy eigsh on the CPU
+        (get_magnetic_Laplacian.py:89-92); same here, fed from a GPU-built plan."""
+        import numpy as np
+        import scipy.sparse as sp
+        from scipy.sparse.linalg import eigsh
+        p = _plan.build_magnetic(edge_index, edge_weight, n, q, None, 2.0, self._signed_mode())
+        counts = (p.row_ptr[1:] - p.row_ptr[:-1]).cpu().numpy()
+        rows = np.repeat(np.arange(n), counts)
+        cols = p.col.cpu().numpy()
+        # plan row a / col b holds L[b, a] (scaled by 2/2 = 1)
+        vals = p.val[0].cpu().numpy() + 1j * p.val[1].cpu().numpy()
+        diag = (p.meta["diag_real"].cpu().numpy() + 1.0).astype(np.complex64)
+        L = sp.coo_matrix((np.concatenate([vals, diag]),
+                           (np.concatenate([cols, np.arange(n)]), np.concatenate([rows, np.arange(n)]))),
+                          shape=(n, n)).astype(np.complex64)
+        lam = eigsh(L, k=1, which='LM', return_eigenvectors=False)
+        return float(np.asarray(lam).real.item())
+
+    def forward(self, x_real: Tensor, x_imag: Tensor, edge_index: Tensor,
+                edge_weight: Optional[Tensor] = None, lambda_max=None):
+        if self.trainable_q:
+            self.q = Parameter(torch.clamp(self.q, 0, 0.25))  # reference quirk Q9
+
+        if self.cached and self._plan is not None:
+            if edge_index.size(1) != self.cached_num_edges:
+                raise RuntimeError(
+                    'Cached {} number of edges, but found {}. Please '
+                    'disable the caching behavior of this layer by removing '
+                    'the `cached=True` argument in its constructor.'.format(
+                        self.cached_num_edges, edge_index.size(1)))
+            if self.q != self.cached_q:
+                raise RuntimeError(
+                    'Cached q is {}, but found {} in input. Please '
+                    'disable the caching behavior of this layer by removing '
+                    'the `cached=True` argument in its constructor.'.format(
+                        self.cached_q, self.q))
+
+        _plan.require_cuda(x_real, "x_real")
+        _plan.require_cuda(x_imag, "x_imag")
+        n = x_real.size(self.node_dim)
+
+        if not self.cached or self._plan is None:
+            self.cached_num_edges = edge_index.size(1)
+            self.cached_q = self.q.detach().item() if self.trainable_q else self.q
+            qv = self._q_value()
+            if self.normalization != 'sym' and lambda_max is None:
+                if self.trainable_q:
+                    raise RuntimeError(
+                        'Cannot train q while not calculating maximum eigenvalue of Laplacian!')
+                lambda_max = self._lambda_max_unnormalised(edge_index, edge_weight, n, qv)
+            if lambda_max is None:
+                lambda_max = 2.0
+            if isinstance(lambda_max, Tensor):
+                lambda_max = float(lambda_max.detach().to(torch.float32).item())
+            self._plan = _plan.build_magnetic(edge_index, edge_weight, n, qv, self.normalization,
+                                              float(lambda_max), self._signed_mode())
+            self._cached_result = None
+
+        return self._cheb_forward(x_real, x_imag)
+
+    def _cheb_forward(self, x_real: Tensor, x_imag: Tensor):
+        p = self._plan
+        w = self.weight.detach()
+        k1 = w.size(0)
+        if 2 * k1 > DENSE_MAX_TERMS:
+            raise NotImplementedError(
+                f"K = {k1 - 1}: the fused transform takes at most {DENSE_MAX_TERMS // 2 - 1} Chebyshev orders")
+        dt = x_real.dtype
+        if dt not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"MagNetConv kernels take float32 or bfloat16 features, got {dt}")
+        t0 = [x_real.detach(), x_imag.detach().to(dt)]
+        terms = [(t0[0], w[0], 0), (t0[1], w[0], 1)]
+        if k1 > 1:
+            t1 = ops.spmm(p, t0, (0, 1))
+            terms += [(t1[0], w[1], 0), (t1[1], w[1], 1)]
+            for k in range(2, k1):
+                t2 = ops.spmm(p, t1, (0, 1), alpha=2.0, beta=-1.0, zs=t0)  # MagNetConv.py:214-216
+                terms += [(t2[0], w[k], 0), (t2[1], w[k], 1)]
+                t0, t1 = t1, t2
+        out_real, out_imag = ops.dense(terms, self.out_channels, bias=self.bias, combine=True,
+                                       relu_mode=1 if self.fused_complex_relu else 0)
+        return out_real, out_imag
+
+    def __repr__(self):
+        return '{}({}, {}, filter size={}, normalization={})'.format(
+            self.__class__.__name__, self.in_channels, self.out_channels,
+            self.weight.size(0), self.normalization)
+
+
+class MagNetConv(_MagneticChebConv):
+    """MagNetConv(in_channels, out_channels, K, q, trainable_q, normalization='sym',
+    cached=False, bias=True) -- reference nn/directed/MagNetConv.py:44-45."""
+    _signed = False
+
+    def __init__(self, in_channels: int, out_channels: int, K: int, q: float, trainable_q: bool,
+                 normalization: Optional[str] = 'sym', cached: bool = False, bias: bool = True,
+                 **kwargs):
+        super().__init__(in_channels, out_channels, K, q, trainable_q, normalization, cached, bias,
+                         True, **kwargs)
+
+
+class MSConv(_MagneticChebConv):
+    """MSConv(in_channels, out_channels, K, q, trainable_q, normalization='sym', bias=True,
+    cached=False, absolute_degree=True) -- reference nn/general/MSConv.py:42-43 (note the
+    bias/cached positional order differs from MagNetConv)."""
+    _signed = True
+
+    def __init__(self, in_channels: int, out_channels: int, K: int, q: float, trainable_q: bool,
+                 normalization: Optional[str] = 'sym', bias: bool = True, cached: bool = False,
+                 absolute_degree: bool = True, **kwargs):
+        super().__init__(in_channels, out_channels, K, q, trainable_q, normalization, cached, bias,
+                         absolute_degree, **kwargs)

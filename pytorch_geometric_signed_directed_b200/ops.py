@@ -1,0 +1,188 @@
+"""Thin tensor-level wrappers over the two compute entry points of the C ABI:
+`pgsd_spmm_csr` (sparse aggregation) and `pgsd_dense_transform` (adjacent dense transform).
+PyTorch supplies device memory and the current stream; all arithmetic is in libpgsd_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .plan import CSRPlan, require_cuda
+
+_DT = {torch.float32: _lib.PGSD_F32, torch.bfloat16: _lib.PGSD_BF16}
+
+# tuning knob for experiments (tools/sweep_spmm.py); 0 = library default
+SPMM_VARIANT = int(os.environ.get("PGSD_SPMM_VARIANT", "0"))
+
+# counts kernel launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+# When set to a list, every launch is bracketed by CUDA events on the launching stream and
+# (name, start_event, end_event) is appended -- bench.py uses it to time the dominant kernel
+# inside the timed region without a profiler.
+TIMING = None
+
+
+class _Timed:
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.b.record(torch.cuda.current_stream(self.device))
+            TIMING.append((self.name, self.a, self.b))
+        return False
+
+
+def _dtype_code(t: Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"pgsd_b200 kernels take float32 or bfloat16 features, got {t.dtype}")
+
+
+def _rows2d(t: Tensor, name: str) -> Tensor:
+    require_cuda(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [N, F], got {tuple(t.shape)}")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean: bool = False,
+         alpha: float = 1.0, beta: float = 0.0, zs: Optional[Sequence[Tensor]] = None,
+         bias: Optional[Tensor] = None, out: Optional[Sequence[Tensor]] = None,
+         variant: Optional[int] = None) -> List[Tensor]:
+    """y_k = alpha * (diag_k x_k[r] + sum val_k x_k[col]) (/len if mean) + beta * z_k + bias
+    for the plan operators listed in `ops` (1 or 2 of them), one kernel launch.
+    xs/zs/out may be column slices of wider row-major buffers."""
+    global LAUNCHES
+    n_ops = len(ops)
+    assert n_ops in (1, 2) and len(xs) == n_ops
+    xs = [_rows2d(x.detach(), "x") for x in xs]
+    feat, dt = xs[0].size(1), _dtype_code(xs[0])
+    dev = xs[0].device
+    a = _lib.SpmmArgs()
+    a.n_rows, a.feat, a.n_ops, a.dtype, a.mean = plan.n_dst, feat, n_ops, dt, int(mean)
+    a.row_ptr, a.col = plan.row_ptr.data_ptr(), plan.col.data_ptr()
+    a.alpha, a.beta = float(alpha), float(beta)
+    a.variant = SPMM_VARIANT if variant is None else variant
+    outs = []
+    keep = []
+    for k, op in enumerate(ops):
+        x = xs[k]
+        if x.size(1) != feat or x.dtype != xs[0].dtype:
+            raise ValueError("spmm: operands must share feature width and dtype")
+        if x.size(0) < plan.n_src:
+            raise ValueError(f"spmm: x has {x.size(0)} rows, plan gathers from {plan.n_src}")
+        v, d = plan.val[op], plan.diag[op]
+        a.val[k] = None if v is None else v.data_ptr()
+        a.diag[k] = None if d is None else d.data_ptr()
+        a.diag_const[k] = plan.diag_const[op]
+        a.x[k], a.ldx[k] = x.data_ptr(), x.stride(0)
+        if zs is not None and zs[k] is not None:
+            z = _rows2d(zs[k].detach(), "z")
+            keep.append(z)
+            a.z[k], a.ldz[k] = z.data_ptr(), z.stride(0)
+        if out is not None and out[k] is not None:
+            y = out[k]
+            if y.stride(1) != 1 or y.size(0) != plan.n_dst or y.size(1) != feat or y.dtype != x.dtype:
+                raise ValueError("spmm: bad output buffer")
+        else:
+            y = torch.empty((plan.n_dst, feat), dtype=x.dtype, device=dev)
+        a.y[k], a.ldy[k] = y.data_ptr(), y.stride(0)
+        outs.append(y)
+    if bias is not None:
+        b = bias.detach().float().contiguous()
+        keep.append(b)
+        a.bias = b.data_ptr()
+    lib = _lib.load()
+    with torch.cuda.device(dev), _Timed("spmm", dev):
+        _lib.check(lib.pgsd_spmm_csr(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                   "pgsd_spmm_csr")
+    LAUNCHES += 1
+    return outs
+
+
+def dense(terms: Sequence[Tuple[Tensor, Tensor, int]], n_out: int, *, bias: Optional[Tensor] = None,
+          combine: bool = False, relu_mode: int = 0,
+          out: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
+    """terms: (X [N, k], W viewed as [k, n_out] (any strides), group).  combine=False:
+    y0 = sum X W + b.  combine=True (MagNet): y0 = A - B + b, y1 = A + B + b with group 0 -> A,
+    group 1 -> B; relu_mode=1 applies the complex ReLU mask in the epilogue."""
+    global LAUNCHES
+    if not 1 <= len(terms) <= _lib.DENSE_MAX_TERMS:
+        raise ValueError(f"dense: between 1 and {_lib.DENSE_MAX_TERMS} terms supported")
+    x0 = terms[0][0]
+    require_cuda(x0, "x")
+    dev, n = x0.device, x0.size(0)
+    dt = _dtype_code(x0)
+    a = _lib.DenseArgs()
+    a.n_rows, a.n_out, a.n_terms, a.dtype, a.combine = n, n_out, len(terms), dt, int(combine)
+    a.relu_mode = relu_mode
+    keep = []
+    for t, (x, w, g) in enumerate(terms):
+        x = _rows2d(x.detach(), "x")
+        w = w.detach()
+        if w.dtype != torch.float32:
+            w = w.float()
+        if x.dtype != x0.dtype or x.size(0) != n:
+            raise ValueError("dense: terms must share dtype and row count")
+        if w.dim() != 2 or w.size(0) != x.size(1) or w.size(1) != n_out:
+            raise ValueError(f"dense: W must be [k={x.size(1)}, n_out={n_out}], got {tuple(w.shape)}")
+        keep += [x, w]
+        a.x[t], a.ldx[t], a.k[t], a.group[t] = x.data_ptr(), x.stride(0), x.size(1), int(g)
+        a.w[t], a.ldw_k[t], a.ldw_n[t] = w.data_ptr(), w.stride(0), w.stride(1)
+    if bias is not None:
+        b = bias.detach().float().contiguous()
+        keep.append(b)
+        a.bias = b.data_ptr()
+    n_outs = 2 if combine else 1
+    outs = []
+    for i in range(n_outs):
+        if out is not None and out[i] is not None:
+            y = out[i]
+            if y.stride(1) != 1 or y.size(0) != n or y.size(1) != n_out or y.dtype != x0.dtype:
+                raise ValueError("dense: bad output buffer")
+        else:
+            y = torch.empty((n, n_out), dtype=x0.dtype, device=dev)
+        a.y[i], a.ldy[i] = y.data_ptr(), y.stride(0)
+        outs.append(y)
+    lib = _lib.load()
+    with torch.cuda.device(dev), _Timed("dense", dev):
+        _lib.check(lib.pgsd_dense_transform(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                   "pgsd_dense_transform")
+    LAUNCHES += 1
+    return outs
+
+
+def gather_rows(x: Tensor, index: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """out[i] = x[index[i]] (halo pack); index int32."""
+    global LAUNCHES
+    x = _rows2d(x.detach(), "x")
+    require_cuda(index, "index")
+    idx = index if index.dtype == torch.int32 else index.int()
+    idx = idx.contiguous()
+    if out is None:
+        out = torch.empty((idx.numel(), x.size(1)), dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pgsd_gather_rows(x.data_ptr(), x.stride(0), idx.data_ptr(), idx.numel(),
+                                        x.size(1), _dtype_code(x), out.data_ptr(), out.stride(0),
+                                        torch.cuda.current_stream(x.device).cuda_stream),
+                   "pgsd_gather_rows")
+    LAUNCHES += 1
+    return out

@@ -1,0 +1,220 @@
+"""Graph plans: the reference's COO `(edge_index, edge_weight)` turned into the int32
+CSR-by-destination layout the aggregation kernels consume, built on the GPU through the C ABI
+(`pgsd_build_*`, include/pgsd_b200.h) and cached by the layers under the reference's own cache
+rules (SURVEY §5 "In-layer caching").
+
+HBM layout of a plan (all int32 / fp32, contiguous):
+    row_ptr [n_dst + 1]   destination-row offsets
+    col     [nnz]         source node of every stored entry
+    val[k]  [nnz]         one value array per operator sharing the pattern (MagNet: real, imag)
+    diag[k] [n_dst]       optional per-row diagonal (kept out of the entry list: the reference's
+                          3N explicit self-loop entries collapse to this)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.PgsdError(
+            f"{name} must be a CUDA tensor: pytorch_geometric_signed_directed_b200 has no CPU path")
+
+
+@dataclass
+class CSRPlan:
+    n_dst: int
+    n_src: int
+    nnz: int
+    num_input_edges: int
+    row_ptr: Tensor
+    col: Tensor
+    val: List[Optional[Tensor]] = field(default_factory=list)
+    diag: List[Optional[Tensor]] = field(default_factory=list)
+    diag_const: List[float] = field(default_factory=list)
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def device(self):
+        return self.row_ptr.device
+
+    def bytes(self) -> int:
+        tot = self.row_ptr.numel() * 4 + self.nnz * 4
+        tot += sum(self.nnz * 4 for v in self.val if v is not None)
+        tot += sum(d.numel() * 4 for d in self.diag if d is not None)
+        return tot
+
+
+def _prep_edges(edge_index: Tensor, edge_weight: Optional[Tensor]) -> Tuple[Tensor, Optional[Tensor]]:
+    require_cuda(edge_index, "edge_index")
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
+    ei = edge_index
+    if ei.dtype != torch.int64:
+        ei = ei.long()
+    if not ei.is_contiguous():
+        ei = ei.contiguous()
+    ew = edge_weight
+    if ew is not None:
+        require_cuda(ew, "edge_weight")
+        if ew.numel() != ei.size(1):
+            raise ValueError("edge_weight must have one entry per edge")
+        ew = ew.detach()
+        if ew.dtype != torch.float32:
+            ew = ew.float()
+        ew = ew.contiguous().view(-1)
+    return ei, ew
+
+
+def _workspace(n: int, e: int, device) -> Tensor:
+    lib = _lib.load()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.pgsd_plan_workspace_bytes(n, e, C.byref(nbytes)), "pgsd_plan_workspace_bytes")
+    return torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def build_csr(edge_index: Tensor, edge_weight: Optional[Tensor], n_dst: int, n_src: int,
+              flow: str = "source_to_target") -> CSRPlan:
+    """Generic aggregation plan (`pgsd_build_csr`).  flow as in PyG: source_to_target gathers
+    edge_index[0] and reduces at edge_index[1]."""
+    ei, ew = _prep_edges(edge_index, edge_weight)
+    dev, e = ei.device, ei.size(1)
+    src, dst = (ei[0], ei[1]) if flow == "source_to_target" else (ei[1], ei[0])
+    with torch.cuda.device(dev):
+        row_ptr = torch.empty(n_dst + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        val = torch.empty(max(e, 1), dtype=torch.float32, device=dev) if ew is not None else None
+        ws = _workspace(max(n_dst, n_src), e, dev)
+        lib = _lib.load()
+        _lib.check(lib.pgsd_build_csr(src.data_ptr(), dst.data_ptr(), _ptr(ew), e, n_dst, n_src,
+                                      row_ptr.data_ptr(), col.data_ptr(), _ptr(val),
+                                      ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "pgsd_build_csr")
+    return CSRPlan(n_dst, n_src, e, e, row_ptr, col[:e], [None if val is None else val[:e]],
+                   [None], [0.0])
+
+
+def build_rw_norm(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, fill_value: float,
+                  transpose: bool = False, add_self_loops: bool = True) -> CSRPlan:
+    """conv_norm_rw + target_to_source aggregation plan (`pgsd_build_csr_rw_norm`).
+    transpose=True is DIMPA's `edge_index[[1, 0]]` call without materialising the flip."""
+    ei, ew = _prep_edges(edge_index, edge_weight)
+    dev, e = ei.device, ei.size(1)
+    dst, src = (ei[1], ei[0]) if transpose else (ei[0], ei[1])
+    with torch.cuda.device(dev):
+        row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        val = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
+        diag = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        ws = _workspace(n, e, dev)
+        nnz = C.c_int64(0)
+        lib = _lib.load()
+        _lib.check(lib.pgsd_build_csr_rw_norm(dst.data_ptr(), src.data_ptr(), _ptr(ew), e, n,
+                                              float(fill_value), int(add_self_loops),
+                                              row_ptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                              diag.data_ptr(), C.byref(nnz), ws.data_ptr(),
+                                              ws.numel(), _stream_ptr(dev)),
+                   "pgsd_build_csr_rw_norm")
+    k = nnz.value
+    return CSRPlan(n, n, k, e, row_ptr, col[:k], [val[:k]], [diag[:n]], [0.0])
+
+
+def build_magnetic(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, q: float,
+                   normalization: Optional[str], lambda_max: float,
+                   signed_mode: int = 0) -> CSRPlan:
+    """Scaled magnetic (signed) Laplacian plan (`pgsd_build_magnetic_laplacian`):
+    val[0]/val[1] = real/imag off-diagonals of L~ = 2L/lambda_max - I stored for
+    source_to_target aggregation, diag[0] = its real diagonal (imag diagonal is 0)."""
+    ei, ew = _prep_edges(edge_index, edge_weight)
+    dev, e = ei.device, ei.size(1)
+    cap = max(2 * e, 1)
+    with torch.cuda.device(dev):
+        row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(cap, dtype=torch.int32, device=dev)
+        vr = torch.empty(cap, dtype=torch.float32, device=dev)
+        vi = torch.empty(cap, dtype=torch.float32, device=dev)
+        diag = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        ws = _workspace(n, e, dev)
+        nnz = C.c_int64(0)
+        lib = _lib.load()
+        _lib.check(lib.pgsd_build_magnetic_laplacian(
+            ei[0].data_ptr(), ei[1].data_ptr(), _ptr(ew), e, n, float(q),
+            1 if normalization == "sym" else 0, float(lambda_max), int(signed_mode),
+            row_ptr.data_ptr(), col.data_ptr(), vr.data_ptr(), vi.data_ptr(), diag.data_ptr(),
+            C.byref(nnz), ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
+            "pgsd_build_magnetic_laplacian")
+    k = nnz.value
+    meta = {"q": q, "normalization": normalization, "lambda_max": float(lambda_max), "diag_real": diag[:n]}
+    if normalization == "sym":
+        # diag(L) = 1 for every node, so the real diagonal of L~ is the constant 2/lambda_max - 1
+        # (exactly 0 for the default lambda_max = 2: the reference's 2N cancelling self-loop
+        # entries).  A constant lets the kernel skip the x[row] read when it is 0.
+        import numpy as np
+        dc = float(np.float32(np.float32(2.0) / np.float32(lambda_max)) - np.float32(1.0))
+        return CSRPlan(n, n, k, e, row_ptr, col[:k], [vr[:k], vi[:k]], [None, None], [dc, 0.0], meta=meta)
+    return CSRPlan(n, n, k, e, row_ptr, col[:k], [vr[:k], vi[:k]], [diag[:n], None], [0.0, 0.0], meta=meta)
+
+
+def magnetic_cached_result(plan: CSRPlan):
+    """Re-materialise MagNetConv.cached_result (nn/directed/MagNetConv.py:181) from a plan:
+    (edge_index_real [2, nnz+2N], edge_index_imag [2, nnz+N], norm_real, norm_imag).
+    Index tensors are bit-identical to the reference's (sorted (row, col) block, then the
+    appended loop blocks); values use L~_r[a,b] = L~_r[b,a], L~_i[a,b] = -L~_i[b,a]."""
+    n, dev = plan.n_dst, plan.device
+    counts = (plan.row_ptr[1:] - plan.row_ptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), counts)
+    cols = plan.col.long()
+    loops = torch.arange(n, device=dev)
+    loops2 = torch.stack([loops, loops])
+    block = torch.stack([rows, cols])
+    ei_imag = torch.cat([block, loops2], 1)
+    ei_real = torch.cat([block, loops2, loops2], 1)
+    norm_real = torch.cat([plan.val[0], plan.meta["diag_real"] + 1.0, torch.full((n,), -1.0, device=dev)])
+    norm_imag = torch.cat([-plan.val[1], torch.zeros(n, device=dev)])
+    return ei_real, ei_imag, norm_real, norm_imag
+
+
+class PlanCache:
+    """Small identity cache for layers the reference re-normalises on every call
+    (Conv_Base, conv_base.py:102-108; SGCNConv's index plumbing): a plan is reused only while
+    the very same edge tensors (storage pointer, shape, in-place version counter) come back,
+    so results always follow the tensors passed in, like the reference."""
+
+    def __init__(self, capacity: int = 8):
+        self.capacity = capacity
+        self._items: dict = {}
+
+    @staticmethod
+    def _key(t: Optional[Tensor]):
+        if t is None:
+            return None
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, str(t.device), t.dtype)
+
+    def get(self, tensors, extra, builder):
+        key = (tuple(self._key(t) for t in tensors), extra)
+        hit = self._items.get(key)
+        if hit is not None:
+            return hit[0]
+        plan = builder()
+        if len(self._items) >= self.capacity:
+            self._items.pop(next(iter(self._items)))
+        # keep the key tensors alive so a recycled data_ptr cannot alias a stale plan
+        self._items[key] = (plan, tensors)
+        return plan
+
+    def clear(self):
+        self._items.clear()

@@ -1,0 +1,121 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/pgsd_b200.h
+declares, argument validation fails loudly without touching the GPU, and the host-side layer
+classes mirror the reference's constructor / state_dict / repr / error contracts."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import pytorch_geometric_signed_directed_b200 as pg
+from pytorch_geometric_signed_directed_b200 import _lib, nn, synthetic
+from pytorch_geometric_signed_directed_b200._lib import PgsdError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pgsd_b200.h")).read()
+    declared = set(re.findall(r"PGSD_API\s+[\w\s\*]+?\b(pgsd_\w+)\s*\(", hdr))
+    assert declared, "no prototypes parsed from the header"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pgsd_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.pgsd_abi_version() == 1
+
+
+def test_ctypes_struct_sizes_match_the_compiled_header():
+    lib = _lib.load()
+    a, b = C.c_size_t(0), C.c_size_t(0)
+    assert lib.pgsd_sizeof_args(C.byref(a), C.byref(b)) == 0
+    assert a.value == C.sizeof(_lib.SpmmArgs) and b.value == C.sizeof(_lib.DenseArgs)
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert lib.pgsd_spmm_csr(None, None) == 1
+    assert b"null" in lib.pgsd_last_error()
+    a = _lib.SpmmArgs()
+    a.n_ops = 3
+    assert lib.pgsd_spmm_csr(C.byref(a), None) == 1
+    assert b"n_ops" in lib.pgsd_last_error()
+    d = _lib.DenseArgs()
+    d.n_terms = 0
+    assert lib.pgsd_dense_transform(C.byref(d), None) == 1
+    nbytes = C.c_size_t(0)
+    assert lib.pgsd_plan_workspace_bytes(1000, 5000, C.byref(nbytes)) == 0 and nbytes.value > 5000 * 16
+    assert lib.pgsd_plan_workspace_bytes(10, 2 ** 31, C.byref(nbytes)) == 4   # PGSD_ERR_RANGE
+    with pytest.raises(PgsdError):
+        _lib.check(1, "x")
+
+
+def test_layers_refuse_cpu_tensors_loudly():
+    conv = nn.MagNetConv(4, 4, K=1, q=0.25, trainable_q=False)
+    x = torch.randn(10, 4)
+    ei = torch.randint(0, 10, (2, 30))
+    with pytest.raises(PgsdError, match="no CPU path"):
+        conv(x, x, ei)
+    with pytest.raises(PgsdError):
+        nn.DiGCNConv(4, 4)(x, ei, torch.rand(30))
+    with pytest.raises(PgsdError):
+        nn.SGCNConv(4, 2, True)(x, ei, ei)
+    with pytest.raises(PgsdError):
+        nn.Conv_Base()(x, ei)
+
+
+def test_reference_constructor_contracts():
+    c = nn.MagNetConv(3, 2, K=2, q=0.25, trainable_q=False)
+    assert repr(c) == 'MagNetConv(3, 2, filter size=3, normalization=sym)'   # test/directed_test.py:73-74
+    assert c.weight.shape == (3, 3, 2) and c.bias.shape == (2,) and c.cached is False
+    assert c.cached_result is None and c.cached_num_edges is None
+    assert set(c.state_dict()) == {"weight", "bias"}
+    ct = nn.MagNetConv(3, 2, K=1, q=0.1, trainable_q=True, normalization=None, bias=False)
+    assert set(ct.state_dict()) == {"weight", "q"} and ct.bias is None
+    with pytest.raises(AssertionError):
+        nn.MagNetConv(3, 2, K=0, q=0.25, trainable_q=False)
+    with pytest.raises(AssertionError):
+        nn.MagNetConv(3, 2, K=1, q=0.25, trainable_q=False, normalization='rw')
+    m = nn.MSConv(3, 2, 2, 0.25, False, 'sym', True, True, False)   # bias, cached, absolute_degree order
+    assert m.cached is True and m.absolute_degree is False and repr(m).startswith('MSConv(3, 2')
+    d = nn.DiGCNConv(5, 4)
+    assert d.cached is True and repr(d) == 'DiGCNConv(5, 4)' and set(d.state_dict()) == {"weight", "bias"}
+    b = nn.DiGCN_InceptionBlock(5, 4)
+    assert set(b.state_dict()) == {"ln.weight", "ln.bias", "conv1.weight", "conv1.bias",
+                                   "conv2.weight", "conv2.bias"}
+    s = nn.SGCNConv(8, 5, first_aggr=False)
+    assert repr(s) == 'SGCNConv(8, 5, first_aggr=False)'   # test/signed_test.py:100,103
+    assert s.lin_b.weight.shape == (5, 24) and set(s.state_dict()) == {
+        "lin_b.weight", "lin_b.bias", "lin_u.weight", "lin_u.bias"}
+    assert nn.SGCNConv(8, 5, first_aggr=True).lin_u.weight.shape == (5, 16)
+    dm = nn.DIMPA(hop=2)
+    assert dm._w_s.shape == (3, 1) and float(dm._w_t.sum()) == 3.0
+    assert set(dm.state_dict()) == {"_w_s", "_w_t"}
+
+
+def test_state_dict_round_trip_from_reference_shapes():
+    ref_like = {"weight": torch.randn(2, 6, 4), "bias": torch.randn(4)}
+    c = nn.MagNetConv(6, 4, K=1, q=0.25, trainable_q=False)
+    c.load_state_dict(ref_like)
+    assert torch.equal(c.weight, ref_like["weight"])
+
+
+def test_synthetic_generators_follow_the_reference_distributions():
+    ei, labels = synthetic.dsbm_edges(3000, k=3, num_edges=30000, eta=0.1, size_ratio=1.5, seed=3)
+    assert ei.dtype == torch.int64 and ei.shape[0] == 2 and abs(ei.shape[1] - 30000) < 1500
+    assert int((ei[0] == ei[1]).sum()) == 0
+    assert torch.unique(ei[0] * 3000 + ei[1]).numel() == ei.shape[1]          # simple digraph
+    sizes = torch.bincount(labels)
+    assert sizes.sum() == 3000 and abs(sizes.max().item() / sizes.min().item() - 1.5) < 0.05
+    # cyclic meta-graph: cluster c -> c+1 edges outnumber c+1 -> c by about (1-eta)/eta = 9
+    fwd = ((labels[ei[1]] - labels[ei[0]]) % 3 == 1).sum().item()
+    bwd = ((labels[ei[0]] - labels[ei[1]]) % 3 == 1).sum().item()
+    assert 6.0 < fwd / bwd < 13.0
+    pos, neg, lab = synthetic.ssbm_edges(2000, k=3, num_entries=40000, eta=0.1, seed=4)
+    assert abs(pos.shape[1] + neg.shape[1] - 40000) < 2500
+    inside = (lab[pos[0]] == lab[pos[1]]).float().mean().item()
+    assert inside > 0.7 and (lab[neg[0]] != lab[neg[1]]).float().mean().item() > 0.85
+    # both directions stored
+    assert torch.equal(torch.sort(pos[0] * 2000 + pos[1]).values, torch.sort(pos[1] * 2000 + pos[0]).values)
+    assert synthetic.meta_graph_cyclic(3, 0.1)[0, 1] == pytest.approx(0.9)
