@@ -267,9 +267,10 @@ struct SymSpace {
 };
 
 static size_t cub_temp_bound(int64_t M) {
-  // DoubleBuffer radix sort needs only histogram/scan scratch: O(#tiles) counters.  This bound
-  // (16 B per 1024 items + 1 MB) is far above what CUB asks for and is verified at run time.
-  return size_t(M / 64 + 1) * 16 + (size_t(1) << 20);
+  // DoubleBuffer radix sort needs only histogram + decoupled-lookback scratch: 256 counters per
+  // tile of a few thousand keys (~0.3 B per key).  2 B per key + 8 MB is a safe bound and is
+  // verified against CUB's own query at run time.
+  return size_t(M) * 2 + (size_t(8) << 20);
 }
 
 static SymSpace carve_sym(void* ws, int64_t E, int64_t N) {
