@@ -305,7 +305,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   PGSD_REQUIRE(a->n_rows >= 0 && a->feat >= 0, "spmm: negative size");
   PGSD_REQUIRE(a->n_rows < (int64_t(1) << 31), "spmm: n_rows exceeds int32 plan format");
   if (a->n_rows == 0 || a->feat == 0) return PGSD_OK;
-  PGSD_REQUIRE(a->row_ptr && a->col, "spmm: row_ptr/col is null");
+  PGSD_REQUIRE(a->row_ptr != nullptr, "spmm: row_ptr is null");  // col may be null when nnz == 0
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int es = a->dtype == PGSD_BF16 ? 2 : 4;
 

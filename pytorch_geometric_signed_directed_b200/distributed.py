@@ -1,0 +1,191 @@
+"""Node-range sharded aggregation for one 8xB200 NVLink/NVSwitch box.
+
+The reference is single-process/single-device (no torch.distributed anywhere); this module has
+no reference counterpart.  The path shards by DESTINATION ROWS: rank r owns the nodes
+[bounds[r], bounds[r+1]), their CSR rows, their slice of x_real/x_imag and of the outputs.
+Rows are independent given x, so the only exchange is the feature rows a rank's columns point
+at.  On the randomly permuted DSBM graphs of the benchmark every rank references ~all remote
+nodes, so the halo is the whole matrix and the exchange is an all-gather; it is run as a RING
+of world-1 point-to-point rounds (NCCL send/recv over NVLink) so that the shard that arrived in
+round s is aggregated (one column-block SpMM launch, accumulating into the output through the
+kernel's `beta * z` epilogue) while round s+1 is in flight:
+
+    compute stream :  pack | block[r] | wait(1) block[r-1] | wait(2) block[r-2] | ...
+    NCCL stream    :       | round 1  | round 2            | round 3            | ...
+
+Real and imaginary features travel interleaved as one [n_local, 2F] buffer, so each neighbour
+gather touches one contiguous 2F*4-byte row.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import ops, plan as _plan
+from .plan import CSRPlan
+
+
+def node_bounds(n_total: int, world: int) -> List[int]:
+    """bounds[r] = first node of rank r; bounds[world] = n_total (1-D node-range split)."""
+    return [(r * n_total) // world for r in range(world + 1)]
+
+
+def split_rows(plan: CSRPlan, lo: int, hi: int) -> CSRPlan:
+    """Rows [lo, hi) of a plan, columns still global."""
+    rp = plan.row_ptr[lo:hi + 1]
+    a, b = int(rp[0].item()), int(rp[-1].item())
+    vals = [None if v is None else v[a:b] for v in plan.val]
+    diags = [None if d is None else d[lo:hi] for d in plan.diag]
+    return CSRPlan(hi - lo, plan.n_src, b - a, plan.num_input_edges, (rp - rp[0]).contiguous(),
+                   plan.col[a:b], vals, diags, list(plan.diag_const), dict(plan.meta))
+
+
+def split_columns_by_owner(local: CSRPlan, bounds: Sequence[int], own_rank: int) -> List[CSRPlan]:
+    """Split a row-shard's entries into one CSR block per column owner; block b's columns are
+    re-based to shard b (col - bounds[b]).  Entry order inside a row is preserved (stable), so
+    per-row accumulation order stays deterministic.  The diagonal term lives in block own_rank
+    (x[row] is a local row there); the other blocks have no diagonal."""
+    dev = local.row_ptr.device
+    n_rows, world = local.n_dst, len(bounds) - 1
+    counts = (local.row_ptr[1:] - local.row_ptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), counts)
+    col = local.col.long()
+    b_t = torch.tensor(list(bounds), device=dev, dtype=torch.long)
+    owner = torch.bucketize(col, b_t[1:], right=True)
+    order = torch.sort(owner * n_rows + rows, stable=True).indices
+    owner_s, rows_s, col_s = owner[order], rows[order], col[order]
+    per_owner = torch.bincount(owner_s, minlength=world).tolist()
+    blocks, start = [], 0
+    for b in range(world):
+        m = per_owner[b]
+        sl = slice(start, start + m)
+        rp = torch.zeros(n_rows + 1, dtype=torch.int32, device=dev)
+        if m:
+            rp[1:] = torch.cumsum(torch.bincount(rows_s[sl], minlength=n_rows), 0).int()
+        vals = [None if v is None else v[order[sl]].contiguous() for v in local.val]
+        is_own = b == own_rank
+        diags = [d if is_own else None for d in local.diag]
+        dconst = [c if is_own else 0.0 for c in local.diag_const]
+        blocks.append(CSRPlan(n_rows, bounds[b + 1] - bounds[b], m, local.num_input_edges, rp,
+                              (col_s[sl] - bounds[b]).int().contiguous(), vals, diags, dconst))
+        start += m
+    return blocks
+
+
+class RingExchange:
+    """All-gather of equal-role shards as world-1 send/recv rounds; round s brings the shard of
+    rank (rank - s) mod world.  Works on any backend (NCCL on the box, gloo in the CPU tests)."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = rank, world, group
+
+    def source_of_round(self, s: int) -> int:
+        return (self.rank - s) % self.world
+
+    def start(self, send: Tensor, recv: Sequence[Optional[Tensor]]):
+        """Posts every round; returns [(source_rank, work)] in arrival order.  recv[b] must be a
+        buffer shaped like rank b's shard (recv[rank] is ignored)."""
+        works = []
+        for s in range(1, self.world):
+            dst, src = (self.rank + s) % self.world, self.source_of_round(s)
+            reqs = dist.batch_isend_irecv([
+                dist.P2POp(dist.isend, send, dst, self.group),
+                dist.P2POp(dist.irecv, recv[src], src, self.group)])
+            works.append((src, reqs))
+        return works
+
+
+def _default_aggregate(block: CSRPlan, xs, op_ids, alpha, beta, zs, out):
+    return ops.spmm(block, xs, op_ids, alpha=alpha, beta=beta, zs=zs, out=out)
+
+
+class ShardedAggregator:
+    """y_k[local rows] = alpha * (L_k x_k)[local rows] + beta * z_k for the operators of a
+    row-sharded plan, with the ring exchange overlapped block by block."""
+
+    def __init__(self, local_plan: CSRPlan, bounds: Sequence[int], rank: int, world: int, group=None,
+                 aggregate_fn: Callable = _default_aggregate):
+        self.bounds, self.rank, self.world = list(bounds), rank, world
+        self.blocks = split_columns_by_owner(local_plan, bounds, rank)
+        self.n_local = local_plan.n_dst
+        self.n_ops = len(local_plan.val)
+        self.ring = RingExchange(rank, world, group)
+        self.aggregate_fn = aggregate_fn
+        self._recv = None
+
+    def _buffers(self, like: Tensor, width: int):
+        key = (like.dtype, like.device, width)
+        if self._recv is None or self._recv[0] != key:
+            bufs = [None if b == self.rank else
+                    torch.empty((self.bounds[b + 1] - self.bounds[b], width), dtype=like.dtype,
+                                device=like.device) for b in range(self.world)]
+            self._recv = (key, bufs)
+        return self._recv[1]
+
+    def __call__(self, xs: Sequence[Tensor], alpha: float = 1.0, beta: float = 0.0,
+                 zs: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
+        n_ops, f = len(xs), xs[0].size(1)
+        op_ids = tuple(range(n_ops))
+        # interleave the operands: one [n_local, n_ops*F] send buffer
+        send = xs[0].contiguous() if n_ops == 1 else torch.cat(list(xs), dim=1)
+        recv = self._buffers(send, n_ops * f)
+        works = self.ring.start(send, recv) if self.world > 1 else []
+        views = lambda buf: [buf[:, k * f:(k + 1) * f] for k in range(n_ops)]
+        # own block first: it needs nothing from the network and carries the diagonal + beta*z
+        y = self.aggregate_fn(self.blocks[self.rank], views(send), op_ids, alpha, beta, zs, None)
+        for src, reqs in works:
+            for w in reqs:
+                w.wait()            # NCCL: makes the current stream wait; gloo: blocks the host
+            if self.blocks[src].nnz == 0:
+                continue
+            y = self.aggregate_fn(self.blocks[src], views(recv[src]), op_ids, alpha, 1.0, y, y)
+        return y
+
+
+class ShardedMagNetConv:
+    """MagNetConv forward over node-range shards: rank r passes its rows of x_real/x_imag and
+    receives its rows of (out_real, out_imag).  Weights are replicated (they are [K+1, F, F])."""
+
+    def __init__(self, conv, n_total: int, rank: int, world: int, group=None):
+        self.conv, self.n_total, self.rank, self.world, self.group = conv, n_total, rank, world, group
+        self.bounds = node_bounds(n_total, world)
+        self.n_local = self.bounds[rank + 1] - self.bounds[rank]
+        self.agg = None
+        self.local_nnz = 0
+
+    def build(self, edge_index: Tensor, edge_weight: Optional[Tensor] = None, lambda_max: float = 2.0):
+        """Every rank builds the global operator (replicated preprocessing, outside the timed
+        step) and keeps its row range.  TODO(round 2): distributed build -- all-to-all of the
+        symmetrised edges by row owner + all-gather of deg^-1/2."""
+        c = self.conv
+        full = _plan.build_magnetic(edge_index, edge_weight, self.n_total, c._q_value(), c.normalization,
+                                    lambda_max, c._signed_mode())
+        local = split_rows(full, self.bounds[self.rank], self.bounds[self.rank + 1])
+        # detach the slices from the global arrays so those can be freed
+        local.col = local.col.clone()
+        local.val = [None if v is None else v.clone() for v in local.val]
+        local.diag = [None if d is None else d.clone() for d in local.diag]
+        local.meta = {}
+        self.local_nnz = local.nnz
+        self.agg = ShardedAggregator(local, self.bounds, self.rank, self.world, self.group)
+        del full
+        return self
+
+    def __call__(self, x_real: Tensor, x_imag: Tensor):
+        c = self.conv
+        w = c.weight.detach()
+        k1 = w.size(0)
+        t0 = [x_real.detach(), x_imag.detach()]
+        terms = [(t0[0], w[0], 0), (t0[1], w[0], 1)]
+        if k1 > 1:
+            t1 = self.agg(t0)
+            terms += [(t1[0], w[1], 0), (t1[1], w[1], 1)]
+            for k in range(2, k1):
+                t2 = self.agg(t1, alpha=2.0, beta=-1.0, zs=t0)
+                terms += [(t2[0], w[k], 0), (t2[1], w[k], 1)]
+                t0, t1 = t1, t2
+        return tuple(ops.dense(terms, c.out_channels, bias=c.bias, combine=True,
+                               relu_mode=1 if c.fused_complex_relu else 0))
