@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(DT) dense_ffma_kernel(const DenseParams p) {
   }
 }
 
+int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled);  // dense_tc.cu
+
 }  // namespace pgsd
 
 using namespace pgsd;
@@ -190,8 +192,21 @@ extern "C" int pgsd_dense_transform(const pgsd_dense_args* a, pgsd_stream_t stre
     p.y[i] = static_cast<char*>(a->y[i]);
     p.ldy[i] = a->ldy[i];
   }
-  dim3 grid((unsigned)ceil_div<int64_t>(a->n_rows, BM), (unsigned)ceil_div<int>(a->n_out, BN));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int t = 0; t < a->n_terms; ++t) {
+    PGSD_REQUIRE(a->x[t] && a->w[t] && a->k[t] >= 0, "dense: term %d has a null pointer", t);
+    PGSD_REQUIRE(a->group[t] == 0 || (a->combine == 1 && a->group[t] == 1), "dense: bad group");
+  }
+  // variant: 0 = auto (tcgen05 3xTF32 path when the shape fits, else FFMA), 1 = force FFMA,
+  // 2 = require the tcgen05 path
+  if (a->variant != 1) {
+    int handled = 0;
+    int rc = dense_tc_try(a, st, &handled);
+    if (rc != PGSD_OK) return rc;
+    if (handled) return PGSD_OK;
+    if (a->variant == 2) return fail(PGSD_ERR_INVALID, "dense: shape outside the tcgen05 path's envelope");
+  }
+  dim3 grid((unsigned)ceil_div<int64_t>(a->n_rows, BM), (unsigned)ceil_div<int>(a->n_out, BN));
   if (a->dtype == PGSD_BF16) {
     if (a->combine) dense_ffma_kernel<true, 2><<<grid, DT, 0, st>>>(p);
     else dense_ffma_kernel<true, 1><<<grid, DT, 0, st>>>(p);

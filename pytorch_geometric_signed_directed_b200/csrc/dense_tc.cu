@@ -1,0 +1,425 @@
+// tcgen05 (5th-gen tensor core) path of the dense feature transform, fp32 in / fp32 out.
+//
+//   acc_g[128 x N] (TMEM, fp32) = sum over 32-wide K chunks  X_chunk[128 x 32] @ W_slab[32 x N]
+//   out_real = acc_0 - acc_1 + b, out_imag = acc_0 + acc_1 + b       (combine, MagNetConv.py:242-247)
+//
+// fp32 parity through tensor cores: 3xTF32 error-compensated product.  Every operand is split
+// in registers into hi = rna_tf32(v) and lo = rna_tf32(v - hi) and three kind::tf32 MMAs
+// (hi*hi + lo*hi + hi*lo) accumulate into the same TMEM tile; the dropped lo*lo term is
+// ~2^-22 relative, i.e. the result is fp32-class like the reference's sgemm (allow_tf32=False).
+//
+// Structure (one persistent CTA per SM, 512 threads, every thread plays every role):
+//   * prologue: tcgen05.alloc of GROUPS*N TMEM columns; all weight slabs split into hi/lo and
+//     written once to shared memory in the K-major SWIZZLE_128B canonical layout;
+//   * per 128-row tile, per K chunk: coalesced 128-bit global loads issued PF chunks ahead
+//     (register ring, ~64 KB in flight per SM) -> hi/lo split -> st.shared into a 2-stage
+//     SW128 A buffer -> fence.proxy.async + bar -> one thread issues 12 tcgen05.mma
+//     (M=128, N, K=8) and a tcgen05.commit onto the stage's mbarrier;
+//   * epilogue: tcgen05.ld 32x32b (warp w reads TMEM lane quarter w%4, column block w/4),
+//     real/imag mix + bias (+ complex ReLU mask), 128-bit streaming stores.
+// The tensor work is ~1.6 us per tile against ~3 us of HBM time: the kernel is a streaming
+// kernel whose math rides on the tensor pipe for free ("never the bound").
+#include "common.cuh"
+
+namespace pgsd {
+namespace tc {
+
+constexpr int THREADS = 512;
+constexpr int TILE_M = 128;
+constexpr int CHUNK_K = 32;              // tf32 elements in one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int STAGE_BYTES = 2 * TILE_M * 128;   // hi + lo
+constexpr int PF = 4;                    // chunks in flight per thread (2 x LDG.128 each)
+constexpr int MAX_CHUNKS = 2 * PGSD_DENSE_MAX_TERMS;
+constexpr int MAX_SLABS = 16;
+
+struct Params {
+  int64_t n_rows;
+  int32_t n_chunks, n_slabs, relu_mode, pad;
+  const float* x[MAX_CHUNKS];     // term base + k0
+  int64_t ldx[MAX_CHUNKS];
+  int8_t group[MAX_CHUNKS];
+  int8_t slab[MAX_CHUNKS];
+  int8_t first[MAX_CHUNKS];       // first chunk of its group inside a tile -> overwrite TMEM
+  int8_t kvalid[MAX_CHUNKS];      // valid k in this chunk (multiple of 4, <= 32)
+  const float* w[MAX_SLABS];      // weight base + k0 * ldw_k
+  int64_t ldw_k[MAX_SLABS], ldw_n[MAX_SLABS];
+  int8_t wk[MAX_SLABS];           // valid k rows of the slab
+  const float* bias;
+  float* y[2];
+  int64_t ldy[2];
+};
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a descriptor / barrier bug must surface as a trapped kernel (launch error),
+// never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) = 1024 B
+// between 8-row groups, version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, M=128 (cute::UMMA::InstrDescriptor in idesc)
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int CPW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[CPW]);
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
+  float a[16], b[16];
+  tmem_ld<16>(taddr, a);
+  tmem_ld<16>(taddr + 16, b);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = a[i], v[16 + i] = b[i];
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------ kernel
+template <int N_OUT, int GROUPS>
+__global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_constant__ Params p) {
+  constexpr int CPW = N_OUT / 4;                 // output columns per epilogue warp
+  constexpr int SLAB_BYTES = 2 * N_OUT * 128;    // hi + lo
+  constexpr uint32_t TMEM_COLS = (GROUPS * N_OUT <= 32) ? 32 : (GROUPS * N_OUT <= 64) ? 64
+                               : (GROUPS * N_OUT <= 128) ? 128 : 256;
+  // instruction descriptor: c=F32 [4,6), a=b=TF32 [7,10)/[10,13), K-major both, N>>3 [17,23),
+  // M>>4 [24,29)
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N_OUT >> 3) << 17) |
+                             (uint32_t(TILE_M >> 4) << 24);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_stage = smem;
+  uint8_t* w_smem = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.n_slabs * SLAB_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_addr = smem_u32(a_stage), w_addr = smem_u32(w_smem);
+  const uint32_t bar_addr = smem_u32(bars);
+  const uint64_t pol_stream = policy_evict_first();
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s <= STAGES; ++s) mbar_init(bar_addr + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // weights -> hi/lo slabs, K-major SW128: element (n, k) at n*128 + (((k>>2) ^ (n&7)) << 4) + (k&3)*4
+  for (int idx = tid; idx < p.n_slabs * CHUNK_K * N_OUT; idx += THREADS) {
+    const int s = idx / (CHUNK_K * N_OUT);
+    const int rem = idx - s * (CHUNK_K * N_OUT);
+    const int k = rem / N_OUT, n = rem - k * N_OUT;
+    float v = 0.f;
+    if (k < p.wk[s]) v = __ldg(p.w[s] + k * p.ldw_k[s] + n * p.ldw_n[s]);
+    const float hi = to_tf32(v), lo = to_tf32(v - hi);
+    const int off = n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
+    *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + off) = hi;
+    *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + N_OUT * 128 + off) = lo;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // loader role: rows r0 = tid/8 and r0 + 64 of the tile, 16-byte chunk c16 = tid%8 of the row
+  const int r0 = tid >> 3, c16 = tid & 7;
+  const uint32_t st_off0 = uint32_t(r0) * 128 + uint32_t((c16 ^ (r0 & 7)) << 4);
+  const uint32_t st_off1 = st_off0 + 64 * 128;   // (r0 + 64) & 7 == r0 & 7
+
+  const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+  float4 buf[PF][2];
+  auto issue = [&](int slot, int64_t tile, int c) {
+    const bool kin = (c16 * 4) < p.kvalid[c];
+    const float* base = p.x[c] + c16 * 4;
+    const int64_t ra = tile * TILE_M + r0, rb = ra + 64;
+    buf[slot][0] = (tile < n_tiles && kin && ra < p.n_rows)
+                       ? __ldg(reinterpret_cast<const float4*>(base + ra * p.ldx[c]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    buf[slot][1] = (tile < n_tiles && kin && rb < p.n_rows)
+                       ? __ldg(reinterpret_cast<const float4*>(base + rb * p.ldx[c]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+#pragma unroll
+  for (int u = 0; u < PF; ++u) {
+    buf[u][0] = buf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < p.n_chunks) issue(u, blockIdx.x, u);
+  }
+
+  uint32_t uses = 0;   // chunks staged so far (CTA-uniform)
+  uint32_t tiles_done = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int cb = 0; cb < p.n_chunks; cb += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int c = cb + u;
+        if (c < p.n_chunks) {
+          const uint32_t stage = uses % STAGES;
+          if (uses >= STAGES) mbar_wait(bar_addr + 8 * stage, ((uses / STAGES) - 1) & 1);
+          // split the two rows this thread holds and store them swizzled
+          uint8_t* hi = a_stage + stage * STAGE_BYTES;
+          uint8_t* lo = hi + TILE_M * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 v = buf[u][h];
+            float4 vh, vl;
+            vh.x = to_tf32(v.x), vh.y = to_tf32(v.y), vh.z = to_tf32(v.z), vh.w = to_tf32(v.w);
+            vl.x = to_tf32(v.x - vh.x), vl.y = to_tf32(v.y - vh.y);
+            vl.z = to_tf32(v.z - vh.z), vl.w = to_tf32(v.w - vh.w);
+            const uint32_t off = h ? st_off1 : st_off0;
+            *reinterpret_cast<float4*>(hi + off) = vh;
+            *reinterpret_cast<float4*>(lo + off) = vl;
+          }
+          // refill this register slot with the next chunk that maps to it
+          {
+            int nc = c + PF;
+            int64_t nt = tile;
+            if (nc >= p.n_chunks) nc = u, nt = tile + gridDim.x;
+            issue(u, nt, nc);
+          }
+          fence_async_smem();
+          __syncthreads();
+          if (tid == 0) {
+            tc_fence_after();
+            const uint32_t d = tmem_base + uint32_t(p.group[c]) * N_OUT;
+            const uint32_t a_hi = a_addr + stage * STAGE_BYTES, a_lo = a_hi + TILE_M * 128;
+            const uint32_t w_hi = w_addr + uint32_t(p.slab[c]) * SLAB_BYTES, w_lo = w_hi + N_OUT * 128;
+#pragma unroll
+            for (int j = 0; j < CHUNK_K / 8; ++j) {
+              const uint32_t ko = j * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              const uint32_t acc0 = (p.first[c] && j == 0) ? 0u : 1u;
+              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
+              mma_tf32(d, make_desc(a_lo + ko), make_desc(w_hi + ko), IDESC, 1u);
+              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_lo + ko), IDESC, 1u);
+            }
+            tc_commit(bar_addr + 8 * stage);                      // stage may be overwritten
+            if (c == p.n_chunks - 1) tc_commit(bar_addr + 8 * STAGES);   // accumulators complete
+          }
+          ++uses;
+        }
+      }
+    }
+
+    // ---- epilogue: TMEM -> registers -> global
+    mbar_wait(bar_addr + 8 * STAGES, tiles_done & 1);
+    tc_fence_after();
+    {
+      const int q = warp & 3, cblk = warp >> 2;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(cblk * CPW);
+      float a[CPW], b[CPW];
+      tmem_ld<CPW>(taddr, a);
+      if (GROUPS == 2) tmem_ld<CPW>(taddr + N_OUT, b);
+      tmem_ld_wait();
+      const int64_t row = tile * TILE_M + q * 32 + lane;
+      if (row < p.n_rows) {
+        float o0[CPW], o1[CPW];
+#pragma unroll
+        for (int i = 0; i < CPW; ++i) {
+          const float bs = p.bias ? __ldg(p.bias + cblk * CPW + i) : 0.f;
+          if (GROUPS == 2) {
+            o0[i] = (a[i] - b[i]) + bs;
+            o1[i] = (a[i] + b[i]) + bs;
+            if (p.relu_mode == 1) {
+              const float m = o0[i] >= 0.f ? 1.f : 0.f;
+              o0[i] *= m, o1[i] *= m;
+            }
+          } else {
+            o0[i] = a[i] + bs;
+          }
+        }
+        float* y0 = p.y[0] + row * p.ldy[0] + cblk * CPW;
+#pragma unroll
+        for (int i = 0; i < CPW; i += 4)
+          st_stream_v4(y0 + i, make_float4(o0[i], o0[i + 1], o0[i + 2], o0[i + 3]), pol_stream);
+        if (GROUPS == 2) {
+          float* y1 = p.y[1] + row * p.ldy[1] + cblk * CPW;
+#pragma unroll
+          for (int i = 0; i < CPW; i += 4)
+            st_stream_v4(y1 + i, make_float4(o1[i], o1[i + 1], o1[i + 2], o1[i + 3]), pol_stream);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();     // accumulators are free for the next tile's first MMA
+    ++tiles_done;
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+template <int N_OUT, int GROUPS>
+static int launch(const Params& p, cudaStream_t st) {
+  const size_t smem = 1024 + STAGES * STAGE_BYTES + size_t(p.n_slabs) * 2 * N_OUT * 128 + 8 * (STAGES + 1) + 16;
+  auto kern = dense_tc_kernel<N_OUT, GROUPS>;
+  PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+  int64_t grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  kern<<<unsigned(grid), THREADS, smem, st>>>(p);
+  PGSD_LAUNCH_CHECK("dense_tc_kernel");
+  return PGSD_OK;
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace tc
+
+// Returns PGSD_OK and sets *handled = 1 when the tensor-core path ran; *handled = 0 means the
+// problem is outside its envelope and the caller should use the FFMA kernel.
+int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
+  using namespace tc;
+  *handled = 0;
+  if (a->dtype != PGSD_F32) return PGSD_OK;
+  const int n = a->n_out;
+  if (!(n == 16 || n == 32 || n == 64 || n == 128)) return PGSD_OK;
+  const int groups = a->combine ? 2 : 1;
+  Params p{};
+  p.n_rows = a->n_rows;
+  p.relu_mode = a->relu_mode;
+  p.bias = a->bias;
+  for (int i = 0; i < groups; ++i) {
+    if (!al16(a->y[i]) || (a->ldy[i] & 3)) return PGSD_OK;
+    p.y[i] = static_cast<float*>(a->y[i]);
+    p.ldy[i] = a->ldy[i];
+  }
+  bool seen_group[2] = {false, false};
+  for (int t = 0; t < a->n_terms; ++t) {
+    const float* x = static_cast<const float*>(a->x[t]);
+    if (!al16(x) || (a->ldx[t] & 3) || (a->k[t] & 3) || a->k[t] == 0) return PGSD_OK;
+    for (int k0 = 0; k0 < a->k[t]; k0 += CHUNK_K) {
+      if (p.n_chunks >= MAX_CHUNKS) return PGSD_OK;
+      const int kv = (a->k[t] - k0) < CHUNK_K ? (a->k[t] - k0) : CHUNK_K;
+      const float* wb = a->w[t] + int64_t(k0) * a->ldw_k[t];
+      int s = -1;
+      for (int j = 0; j < p.n_slabs; ++j)
+        if (p.w[j] == wb && p.ldw_k[j] == a->ldw_k[t] && p.ldw_n[j] == a->ldw_n[t] && p.wk[j] == kv) s = j;
+      if (s < 0) {
+        if (p.n_slabs >= MAX_SLABS) return PGSD_OK;
+        s = p.n_slabs++;
+        p.w[s] = wb, p.ldw_k[s] = a->ldw_k[t], p.ldw_n[s] = a->ldw_n[t], p.wk[s] = int8_t(kv);
+      }
+      const int c = p.n_chunks++;
+      p.x[c] = x + k0;
+      p.ldx[c] = a->ldx[t];
+      p.group[c] = int8_t(a->group[t]);
+      p.slab[c] = int8_t(s);
+      p.kvalid[c] = int8_t(kv);
+      p.first[c] = seen_group[a->group[t]] ? 0 : 1;
+      seen_group[a->group[t]] = true;
+    }
+  }
+  if (groups == 2 && !(seen_group[0] && seen_group[1])) return PGSD_OK;
+  const size_t smem = 1024 + STAGES * STAGE_BYTES + size_t(p.n_slabs) * 2 * n * 128 + 8 * (STAGES + 1) + 16;
+  if (smem > 220 * 1024) return PGSD_OK;
+  int rc;
+#define PGSD_TC(N_)                                                                       \
+  rc = groups == 2 ? launch<N_, 2>(p, st) : launch<N_, 1>(p, st);                         \
+  break;
+  switch (n) {
+    case 16: PGSD_TC(16)
+    case 32: PGSD_TC(32)
+    case 64: PGSD_TC(64)
+    default: PGSD_TC(128)
+  }
+#undef PGSD_TC
+  if (rc == PGSD_OK) *handled = 1;
+  return rc;
+}
+
+}  // namespace pgsd

@@ -19,6 +19,9 @@ _DT = {torch.float32: _lib.PGSD_F32, torch.bfloat16: _lib.PGSD_BF16}
 # tuning knob for experiments (tools/sweep_spmm.py); 0 = library default
 SPMM_VARIANT = int(os.environ.get("PGSD_SPMM_VARIANT", "0"))
 
+# 0 = auto (tcgen05 3xTF32 path when the shape fits, else FFMA), 1 = force FFMA, 2 = require tcgen05
+DENSE_VARIANT = int(os.environ.get("PGSD_DENSE_VARIANT", "0"))
+
 # counts kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 
@@ -119,7 +122,7 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
 
 def dense(terms: Sequence[Tuple[Tensor, Tensor, int]], n_out: int, *, bias: Optional[Tensor] = None,
           combine: bool = False, relu_mode: int = 0,
-          out: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
+          out: Optional[Sequence[Tensor]] = None, variant: Optional[int] = None) -> List[Tensor]:
     """terms: (X [N, k], W viewed as [k, n_out] (any strides), group).  combine=False:
     y0 = sum X W + b.  combine=True (MagNet): y0 = A - B + b, y1 = A + B + b with group 0 -> A,
     group 1 -> B; relu_mode=1 applies the complex ReLU mask in the epilogue."""
@@ -133,6 +136,7 @@ def dense(terms: Sequence[Tuple[Tensor, Tensor, int]], n_out: int, *, bias: Opti
     a = _lib.DenseArgs()
     a.n_rows, a.n_out, a.n_terms, a.dtype, a.combine = n, n_out, len(terms), dt, int(combine)
     a.relu_mode = relu_mode
+    a.variant = DENSE_VARIANT if variant is None else variant
     keep = []
     for t, (x, w, g) in enumerate(terms):
         x = _rows2d(x.detach(), "x")

@@ -332,3 +332,62 @@ def test_magnet_full_size_properties(n, e):
     scale_r, scale_i = out_r.abs().max().item(), out_i.abs().max().item()
     assert (out_r[sel.to(DEV)].cpu() - o_r).abs().max().item() <= 1e-5 * scale_r
     assert (out_i[sel.to(DEV)].cpu() - o_i).abs().max().item() <= 1e-5 * scale_i
+
+
+# ------------------------------------------------------------------ dense transform paths
+@pytest.mark.parametrize("n_rows,ks,n_out,combine", [
+    (1000, (64, 64, 64, 64), 64, True),       # MagNet K=1, 64 -> 64
+    (130, (64, 64, 64, 64, 64, 64), 64, True),  # K=2
+    (4097, (32, 32, 32, 32), 32, True),
+    (777, (16, 16, 16, 16), 16, True),        # partial K chunk (16 of 32)
+    (2500, (48, 48), 128, True),
+    (1, (64, 64), 64, True),
+    (3000, (128,), 128, False),               # DiGCN-like single term
+    (3000, (64, 64), 32, False),              # SGCN first layer: two column blocks
+    (999, (32, 32, 32), 32, False),           # SGCN deep layer: three column blocks
+])
+def test_dense_tensor_core_path_matches_fp64(n_rows, ks, n_out, combine):
+    gen = torch.Generator(device=DEV).manual_seed(n_rows + n_out)
+    xs = [torch.randn(n_rows, k, generator=gen, device=DEV) for k in ks]
+    # MagNet-style: consecutive (real, imag) terms share one weight
+    ws = []
+    for t, k in enumerate(ks):
+        if combine and t % 2 == 1:
+            ws.append(ws[-1])
+        else:
+            ws.append(torch.randn(k, n_out, generator=gen, device=DEV) / k ** 0.5)
+    bias = torch.randn(n_out, generator=gen, device=DEV)
+    terms = [(x, w, (t % 2) if combine else 0) for t, (x, w) in enumerate(zip(xs, ws))]
+    acc = [torch.zeros(n_rows, n_out, dtype=torch.float64, device=DEV) for _ in range(2)]
+    for x, w, g in terms:
+        acc[g] += x.double() @ w.double()
+    ref = [acc[0] - acc[1] + bias.double(), acc[0] + acc[1] + bias.double()] if combine \
+        else [acc[0] + bias.double()]
+    tc = ops.dense(terms, n_out, bias=bias, combine=combine, variant=2)     # tcgen05 required
+    ff = ops.dense(terms, n_out, bias=bias, combine=combine, variant=1)     # FFMA
+    for got_tc, got_ff, r in zip(tc, ff, ref):
+        assert_close_rel(got_tc, r, 2e-6, "tcgen05 3xTF32 vs fp64")
+        assert_close_rel(got_ff, r, 2e-6, "ffma vs fp64")
+
+
+def test_dense_tensor_core_strided_operands_and_relu():
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    n = 5000
+    wide = torch.randn(n, 192, generator=gen, device=DEV)
+    lin = torch.randn(64, 128, generator=gen, device=DEV)          # nn.Linear layout [out, in]
+    wt = lin.t()                                                   # [in=128, out=64] view, strides (1, 128)
+    terms = [(wide[:, 64:128], wt[:64], 0), (wide[:, 128:], wt[64:], 0)]
+    out = torch.empty(n, 128, device=DEV)
+    ops.dense(terms, 64, out=[out[:, 64:]], variant=2)
+    ref = wide[:, 64:128].double() @ wt[:64].double() + wide[:, 128:].double() @ wt[64:].double()
+    assert_close_rel(out[:, 64:], ref, 2e-6)
+    x0, x1 = wide[:, :64].contiguous(), wide[:, 64:128].contiguous()
+    w = torch.randn(64, 64, generator=gen, device=DEV) / 8
+    r, i = ops.dense([(x0, w, 0), (x1, w, 1)], 64, combine=True, relu_mode=1, variant=2)
+    a, b = x0.double() @ w.double(), x1.double() @ w.double()
+    mask = ((a - b) >= 0).double()
+    assert_close_rel(r, (a - b) * mask, 2e-6)
+    # the mask is decided on the fp32 value of out_real: tolerate flips where |a-b| ~ 0
+    agree = (((r != 0) | ((a - b).abs() < 1e-5)) == ((mask != 0) | ((a - b).abs() < 1e-5))).all()
+    assert bool(agree)
+    assert_close_rel(i * (r != 0), (a + b) * mask * (r != 0).double(), 2e-6)

@@ -65,7 +65,10 @@ conv(xr, xi, ei)
 w = conv.weight.detach()
 ms = timeit(lambda: ops.dense([(xr, w[0], 0), (xi, w[0], 1), (yr, w[1], 0), (yi, w[1], 1)], F,
                               bias=conv.bias, combine=True))
-emit(what="dense_combine", ms=ms, gflops=4 * 2 * N * F * F / ms / 1e6)
+emit(what="dense_combine_auto", ms=ms, gflops=4 * 2 * N * F * F / ms / 1e6)
+for dv in (1, 2):
+    ms = timeit(lambda: ops.dense([(xr, w[0], 0), (xi, w[0], 1), (yr, w[1], 0), (yi, w[1], 1)], F, bias=conv.bias, combine=True, variant=dv))
+    emit(what="dense_combine", variant=dv, ms=ms, gflops=4 * 2 * N * F * F / ms / 1e6, gbs=6 * N * F * 4 / ms / 1e6)
 emit(what="layer_forward", ms=timeit(lambda: conv(xr, xi, ei)))
 
 # reference points: plain copy bandwidth and a torch gather of the same volume
