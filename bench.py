@@ -290,19 +290,61 @@ def run_gpu_arm(args, rank, world):
             e2e_step()
         e1.record()
         torch.cuda.synchronize()
+        serial_ms = e0.elapsed_time(e1) / n_e2e
+
+        # Same work per step, software-pipelined across steps: the H2D of step i+1 and the D2H of
+        # step i-1 ride on their own streams (PCIe is full duplex) while step i computes.  Every
+        # step still uploads its inputs from pinned memory and downloads its outputs.
+        s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+        dxs = [(dx_r, dx_i), (torch.empty_like(dx_r), torch.empty_like(dx_i))]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+
+        def pipelined(n):
+            for i in range(n):
+                b = i % 2
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_cmp[b])            # compute of step i-2 finished with dxs[b]
+                    dxs[b][0].copy_(hx_r, non_blocking=True)
+                    dxs[b][1].copy_(hx_i, non_blocking=True)
+                    ev_in[b].record(s_in)
+                s_cmp.wait_event(ev_in[b])
+                o_r, o_i = conv(dxs[b][0], dxs[b][1], ei)
+                ev_cmp[b].record(s_cmp)
+                o_r.record_stream(s_out); o_i.record_stream(s_out)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[b])
+                    ho_r.copy_(o_r, non_blocking=True)
+                    ho_i.copy_(o_i, non_blocking=True)
+                    ev_out[b].record(s_out)
+            s_cmp.wait_stream(s_out)
+
+        pipelined(3)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipelined(n_e2e)
+        e1.record()
+        torch.cuda.synchronize()
         e2e_ms = e0.elapsed_time(e1) / n_e2e
         e2e = {"value": e_input / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "serial_ms_per_step": serial_ms,
                "h2d_bytes_per_step": 2 * n_local * FEAT * 4, "d2h_bytes_per_step": 2 * n_local * FEAT * 4,
                "steps": n_e2e, "note": "pinned host x_real/x_imag -> H2D -> MagNetConv.forward (C ABI) -> D2H "
-                                       "out_real/out_imag; graph plan cached on device (cached=True)"}
+                                       "out_real/out_imag every step; graph plan cached on device (cached=True); "
+                                       "copies double-buffered on side streams (serial_ms_per_step = same loop "
+                                       "without overlap)"}
 
     if rank != 0:
         return
 
     # ---- roofline of the dominant kernel (pgsd_spmm_csr, n_ops = 2)
     peak, peak_src = measured_peak_gbs()
-    spmm_ms = statistics.mean(kern["spmm"]) if kern.get("spmm") else None
-    dense_ms = statistics.mean(kern["dense"]) if kern.get("dense") else None
+    # per STEP: the sharded path issues one aggregation launch per column block, their sum is the
+    # step's aggregation time
+    spmm_ms = sum(kern["spmm"]) / args.steps if kern.get("spmm") else None
+    dense_ms = sum(kern["dense"]) / args.steps if kern.get("dense") else None
     # algorithmic bytes per launch: per stored entry 4 (col) + 2*4 (values) +
     # 2 * F*4 (one feature-row gather per operator, no reuse assumed); per row 4 (row_ptr) +
     # 2 * F*4 (T_real, T_imag written).
@@ -316,7 +358,11 @@ def run_gpu_arm(args, rank, world):
         roof["achieved"] = b_spmm / (spmm_ms * 1e-3) / 1e9
         roof["frac"] = roof["achieved"] / peak
         roof["kernel_ms"] = spmm_ms
-        roof["share_of_step"] = spmm_ms * (len(kern["spmm"]) / args.steps) / ms_per_step
+        roof["launches_per_step"] = len(kern["spmm"]) / args.steps
+        roof["share_of_step"] = spmm_ms / ms_per_step
+        if world > 1:
+            roof["note"] = ("rank 0 of the sharded run: kernel_ms sums the per-shard column-block launches of "
+                            "one step; the step is bounded by the NVLink exchange, see DESIGN.md §7")
     roof["layer"] = {"algorithmic_bytes": b_layer, "achieved": b_layer / (ms_per_step * 1e-3) / 1e9,
                      "frac": b_layer / (ms_per_step * 1e-3) / 1e9 / peak, "dense_ms": dense_ms}
 
@@ -360,6 +406,10 @@ def main():
             sys.exit(subprocess.call(cmd))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     run_gpu_arm(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

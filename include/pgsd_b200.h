@@ -148,7 +148,8 @@ typedef struct pgsd_spmm_args {
   int64_t ldy[2];
   const float* bias;         /* [F] or NULL                                           */
   int32_t variant;           /* 0 = library default; >0 selects a tuning variant      */
-  int32_t reserved;
+  int32_t diag_row_offset;   /* x row holding destination row 0 (diag term only): lets x span a
+                                larger node range than the plan's rows (row-sharded plans)  */
 } pgsd_spmm_args;
 
 PGSD_API int pgsd_spmm_csr(const pgsd_spmm_args* args, pgsd_stream_t stream);
@@ -191,6 +192,38 @@ typedef struct pgsd_dense_args {
 } pgsd_dense_args;
 
 PGSD_API int pgsd_dense_transform(const pgsd_dense_args* args, pgsd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Segment-softmax attention over CSR-by-destination plans.
+ *   t_e     = act(s_src[p][j] + s_dst[p][i])        edge e = (j -> i) of type p (one plan per type)
+ *   alpha_e = exp(t_e - max_i) / (sum over ALL entries of row i, both types, + 1e-16)
+ * Replaces SNEAConv.message + PyG utils.softmax (nn/signed/SNEAConv.py:135-146): the
+ * reference's Linear(2*out -> 1) on [x_j || x_i] splits into two per-node scalars
+ * (s_src = X a_j, s_dst = X a_i + c), so the per-edge work is scalar.
+ *   y != NULL        : y[i] = xd[0][i] * sum_{type 0} alpha + xd[1][i] * sum_{type 1} alpha
+ *                      (SNEAConv aggregates the TARGET feature times alpha)
+ *   alpha_out[p] set : alpha_e written per stored entry (GATConv-style layers then run
+ *                      pgsd_spmm_csr with val = alpha_out[p]).
+ * act: 0 = tanh, 1 = leaky_relu(slope).  fp32 only.
+ * ---------------------------------------------------------------------------------- */
+typedef struct pgsd_attn_args {
+  int64_t n_rows;
+  int32_t feat;
+  int32_t n_types;           /* 1 or 2 */
+  int32_t act;
+  float slope;
+  const int32_t* row_ptr[2];
+  const int32_t* col[2];
+  const float* s_src[2];     /* [n_src] */
+  const float* s_dst[2];     /* [n_rows] */
+  const float* xd[2];        /* [n_rows, ldxd] target-side features (mode y) */
+  int64_t ldxd[2];
+  float* y;                  /* [n_rows, ldy] or NULL */
+  int64_t ldy;
+  float* alpha_out[2];       /* [nnz_p] or NULL */
+} pgsd_attn_args;
+
+PGSD_API int pgsd_edge_softmax(const pgsd_attn_args* args, pgsd_stream_t stream);
 
 /* Halo pack for the node-range sharded path (no reference counterpart: the reference is
  * single-device): out[i, :] = x[index[i], :]  -- rows another rank asked for. */

@@ -28,7 +28,7 @@ class SpmmArgs(C.Structure):
         ("alpha", _f32), ("beta", _f32),
         ("z", _vp * 2), ("ldz", _i64 * 2),
         ("y", _vp * 2), ("ldy", _i64 * 2),
-        ("bias", _vp), ("variant", _i32), ("reserved", _i32),
+        ("bias", _vp), ("variant", _i32), ("diag_row_offset", _i32),
     ]
 
 
@@ -41,6 +41,14 @@ class DenseArgs(C.Structure):
         ("ldw_n", _i64 * DENSE_MAX_TERMS),
         ("bias", _vp), ("y", _vp * 2), ("ldy", _i64 * 2),
         ("relu_mode", _i32), ("variant", _i32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", _i64), ("feat", _i32), ("n_types", _i32), ("act", _i32), ("slope", _f32),
+        ("row_ptr", _vp * 2), ("col", _vp * 2), ("s_src", _vp * 2), ("s_dst", _vp * 2),
+        ("xd", _vp * 2), ("ldxd", _i64 * 2), ("y", _vp), ("ldy", _i64), ("alpha_out", _vp * 2),
     ]
 
 
@@ -59,6 +67,7 @@ _PROTOTYPES = {
                                                 C.POINTER(_i64), _vp, C.c_size_t, _vp]),
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),
     "pgsd_dense_transform": (C.c_int, [C.POINTER(DenseArgs), _vp]),
+    "pgsd_edge_softmax": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
 }
 

@@ -39,6 +39,7 @@ struct SpmmParams {
   char* y[2];
   int64_t ldy_bytes[2];
   const float* bias;
+  int64_t diag_row_offset;
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
         const float dg = has_diag ? __ldg(p.diag[k] + row) : p.diag_const[k];
         if (has_diag || dg != 0.f) {
           float xr[EPL];
-          RV::load(p.x[k] + row * p.ldx_bytes[k] + lane_off, xr);
+          RV::load(p.x[k] + (row + p.diag_row_offset) * p.ldx_bytes[k] + lane_off, xr);
 #pragma unroll
           for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(dg, xr[i], acc[k][i]);
         }
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) spmm_rows_scalar_kernel(const SpmmParams 
         }
         const bool has_diag = p.diag[k] != nullptr;
         const float dg = has_diag ? p.diag[k][row] : p.diag_const[k];
-        if (has_diag || dg != 0.f) acc = fmaf(dg, rd(p.x[k], p.ldx_bytes[k], row, f), acc);
+        if (has_diag || dg != 0.f) acc = fmaf(dg, rd(p.x[k], p.ldx_bytes[k], row + p.diag_row_offset, f), acc);
         float out = p.alpha * (acc * inv);
         if (p.z[k]) out = fmaf(p.beta, rd(p.z[k], p.ldz_bytes[k], row, f), out);
         if (p.bias) out += p.bias[f];
@@ -318,6 +319,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   p.alpha = a->alpha;
   p.beta = a->beta;
   p.bias = a->bias;
+  p.diag_row_offset = a->diag_row_offset;
   bool vec16 = (int64_t(a->feat) * es) % 16 == 0;
   bool vec32 = (int64_t(a->feat) * es) % 32 == 0;
   for (int k = 0; k < a->n_ops; ++k) {

@@ -107,9 +107,19 @@ class ShardedAggregator:
     row-sharded plan, with the ring exchange overlapped block by block."""
 
     def __init__(self, local_plan: CSRPlan, bounds: Sequence[int], rank: int, world: int, group=None,
-                 aggregate_fn: Callable = _default_aggregate):
+                 aggregate_fn: Callable = _default_aggregate, mode: Optional[str] = None):
         self.bounds, self.rank, self.world = list(bounds), rank, world
-        self.blocks = split_columns_by_owner(local_plan, bounds, rank)
+        # "ring": per-owner column blocks pipelined with the exchange (wins when the exchange is
+        # long: world >= 3).  "gather": receive every shard into one [N, w] buffer and run ONE
+        # launch over all columns (wins at world <= 2, where splitting rows into short column
+        # blocks + re-reading the output costs more than the 0.7 ms of exposed transfer).
+        self.mode = mode or ("gather" if world <= 2 else "ring")
+        # in gather mode x spans all nodes while the plan's rows are local: tell the kernel where
+        # destination row 0 lives in x (diagonal term)
+        self.local_plan = CSRPlan(local_plan.n_dst, local_plan.n_src, local_plan.nnz, local_plan.num_input_edges,
+                                  local_plan.row_ptr, local_plan.col, local_plan.val, local_plan.diag,
+                                  local_plan.diag_const, {**local_plan.meta, "diag_row_offset": self.bounds[rank]})
+        self.blocks = split_columns_by_owner(local_plan, bounds, rank) if self.mode == "ring" else None
         self.n_local = local_plan.n_dst
         self.n_ops = len(local_plan.val)
         self.ring = RingExchange(rank, world, group)
@@ -129,6 +139,8 @@ class ShardedAggregator:
                  zs: Optional[Sequence[Tensor]] = None) -> List[Tensor]:
         n_ops, f = len(xs), xs[0].size(1)
         op_ids = tuple(range(n_ops))
+        if self.mode == "gather":
+            return self._gather_then_single(xs, op_ids, f, alpha, beta, zs)
         # interleave the operands: one [n_local, n_ops*F] send buffer
         send = xs[0].contiguous() if n_ops == 1 else torch.cat(list(xs), dim=1)
         recv = self._buffers(send, n_ops * f)
@@ -143,6 +155,26 @@ class ShardedAggregator:
                 continue
             y = self.aggregate_fn(self.blocks[src], views(recv[src]), op_ids, alpha, 1.0, y, y)
         return y
+
+
+def _gather_then_single(self, xs, op_ids, f, alpha, beta, zs):
+    n_ops, lo, hi = len(xs), self.bounds[self.rank], self.bounds[self.rank + 1]
+    key = ("full", xs[0].dtype, xs[0].device, n_ops * f)
+    if self._recv is None or self._recv[0] != key:
+        self._recv = (key, torch.empty((self.bounds[-1], n_ops * f), dtype=xs[0].dtype, device=xs[0].device))
+    full = self._recv[1]
+    own = full[lo:hi]
+    for k in range(n_ops):
+        own[:, k * f:(k + 1) * f].copy_(xs[k])
+    recv = [full[self.bounds[b]:self.bounds[b + 1]] for b in range(self.world)]
+    for _, reqs in (self.ring.start(own, recv) if self.world > 1 else []):
+        for w in reqs:
+            w.wait()
+    views = [full[:, k * f:(k + 1) * f] for k in range(n_ops)]
+    return self.aggregate_fn(self.local_plan, views, op_ids, alpha, beta, zs, None)
+
+
+ShardedAggregator._gather_then_single = _gather_then_single
 
 
 class ShardedMagNetConv:

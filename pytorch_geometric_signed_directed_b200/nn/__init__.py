@@ -4,8 +4,9 @@ backed by the sm_100a kernels in libpgsd_b200.so."""
 from .magnet_conv import MagNetConv, MSConv
 from .digcn_conv import DiGCNConv, DiGCN_InceptionBlock
 from .sgcn_conv import SGCNConv
+from .snea_conv import SNEAConv
 from .mixed_path import Conv_Base, DIMPA
 from .complex_relu import complex_relu_layer
 
-__all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv",
+__all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv", "SNEAConv",
            "Conv_Base", "DIMPA", "complex_relu_layer"]

@@ -83,13 +83,14 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
     a.row_ptr, a.col = plan.row_ptr.data_ptr(), plan.col.data_ptr()
     a.alpha, a.beta = float(alpha), float(beta)
     a.variant = SPMM_VARIANT if variant is None else variant
+    a.diag_row_offset = int(plan.meta.get("diag_row_offset", 0))
     outs = []
     keep = []
     for k, op in enumerate(ops):
         x = xs[k]
         if x.size(1) != feat or x.dtype != xs[0].dtype:
             raise ValueError("spmm: operands must share feature width and dtype")
-        if x.size(0) < plan.n_src:
+        if x.size(0) < plan.n_src or x.size(0) < plan.n_dst + a.diag_row_offset:
             raise ValueError(f"spmm: x has {x.size(0)} rows, plan gathers from {plan.n_src}")
         v, d = plan.val[op], plan.diag[op]
         a.val[k] = None if v is None else v.data_ptr()
@@ -190,3 +191,47 @@ def gather_rows(x: Tensor, index: Tensor, out: Optional[Tensor] = None) -> Tenso
                    "pgsd_gather_rows")
     LAUNCHES += 1
     return out
+
+
+def edge_softmax(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Sequence[Tensor], *,
+                 act: str = "tanh", slope: float = 0.2, xd: Optional[Sequence[Tensor]] = None,
+                 want_alpha: bool = False):
+    """Segment softmax over the rows of 1 or 2 CSR plans (`pgsd_edge_softmax`).
+    xd given   -> returns y = xd[0] * sum_type0(alpha) + xd[1] * sum_type1(alpha)   (SNEAConv)
+    want_alpha -> returns the per-entry alpha tensors (one per plan)              (GAT-style)."""
+    global LAUNCHES
+    n_types = len(plans)
+    assert n_types in (1, 2) and len(s_src) == n_types and len(s_dst) == n_types
+    dev = plans[0].device
+    a = _lib.AttnArgs()
+    a.n_rows, a.n_types = plans[0].n_dst, n_types
+    a.act, a.slope = (0 if act == "tanh" else 1), float(slope)
+    keep, alphas, y = [], [], None
+    for t in range(n_types):
+        ss = s_src[t].detach().float().contiguous().view(-1)
+        sd = s_dst[t].detach().float().contiguous().view(-1)
+        if ss.numel() < plans[t].n_src or sd.numel() < plans[t].n_dst:
+            raise ValueError("edge_softmax: score vectors shorter than the plan's node ranges")
+        keep += [ss, sd]
+        a.row_ptr[t], a.col[t] = plans[t].row_ptr.data_ptr(), plans[t].col.data_ptr()
+        a.s_src[t], a.s_dst[t] = ss.data_ptr(), sd.data_ptr()
+        if want_alpha:
+            al = torch.empty(max(plans[t].nnz, 1), dtype=torch.float32, device=dev)
+            alphas.append(al[:plans[t].nnz])
+            a.alpha_out[t] = al.data_ptr()
+    if xd is not None:
+        xs = [_rows2d(x.detach(), "xd") for x in xd]
+        if any(x.dtype != torch.float32 for x in xs):
+            raise TypeError("edge_softmax takes float32 features")
+        a.feat = xs[0].size(1)
+        y = torch.empty((plans[0].n_dst, a.feat), dtype=torch.float32, device=dev)
+        for t in range(n_types):
+            a.xd[t], a.ldxd[t] = xs[t].data_ptr(), xs[t].stride(0)
+        a.y, a.ldy = y.data_ptr(), y.stride(0)
+        keep += xs
+    lib = _lib.load()
+    with torch.cuda.device(dev), _Timed("edge_softmax", dev):
+        _lib.check(lib.pgsd_edge_softmax(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                   "pgsd_edge_softmax")
+    LAUNCHES += 1
+    return y, alphas

@@ -24,7 +24,7 @@ def _plan_from_oracle(ei, n, q=0.25):
     rp = torch.zeros(n + 1, dtype=torch.int32)
     rp[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0).int()
     return CSRPlan(n, n, nnz, ei.size(1), rp, src[order].int(), [nr[:nnz][order], ni[:nnz][order]],
-                   [None, None], [0.0, 0.0])
+                   [None, None], [0.25, 0.0])      # non-zero real diagonal (lambda_max != 2)
 
 
 def _torch_aggregate(block, xs, op_ids, alpha, beta, zs, out):
@@ -36,7 +36,8 @@ def _torch_aggregate(block, xs, op_ids, alpha, beta, zs, out):
         if block.nnz:
             agg.index_add_(0, rows, block.val[op].view(-1, 1) * xs[k][block.col.long()])
         if block.diag_const[op] != 0.0:
-            agg += block.diag_const[op] * xs[k][:block.n_dst]
+            off = block.meta.get("diag_row_offset", 0)
+            agg += block.diag_const[op] * xs[k][off:off + block.n_dst]
         y = alpha * agg
         if zs is not None and zs[k] is not None:
             y = y + beta * zs[k]
@@ -57,7 +58,10 @@ def _worker(rank, world, port_no, n, e, f):
         lo, hi = bounds[rank], bounds[rank + 1]
         local = pgd.split_rows(full, lo, hi)
         assert local.n_dst == hi - lo
-        agg = pgd.ShardedAggregator(local, bounds, rank, world, aggregate_fn=_torch_aggregate)
+        # the single-launch "gather" mode must agree with the pipelined "ring" mode
+        agg_g = pgd.ShardedAggregator(local, bounds, rank, world, aggregate_fn=_torch_aggregate, mode="gather")
+        tg = agg_g([xr[lo:hi], xi[lo:hi]])
+        agg = pgd.ShardedAggregator(local, bounds, rank, world, aggregate_fn=_torch_aggregate, mode="ring")
         assert sum(b.nnz for b in agg.blocks) == local.nnz
         for b, blk in enumerate(agg.blocks):
             assert blk.n_src == bounds[b + 1] - bounds[b]
@@ -68,6 +72,7 @@ def _worker(rank, world, port_no, n, e, f):
         t1 = agg([xr[lo:hi], xi[lo:hi]])
         for k in range(2):
             assert torch.allclose(t1[k], ref[k][lo:hi], atol=1e-5), f"rank {rank} op {k}"
+            assert torch.allclose(tg[k], ref[k][lo:hi], atol=1e-5), f"rank {rank} gather-mode op {k}"
         # Chebyshev step: T2 = 2 L T1 - T0 with a second exchange
         ref2 = _torch_aggregate(full, ref, (0, 1), 2.0, -1.0, [xr, xi], None)
         t2 = agg(t1, alpha=2.0, beta=-1.0, zs=[xr[lo:hi], xi[lo:hi]])
