@@ -76,4 +76,5 @@ def ref_classes():
     out["SIMPA"] = load("nn.signed.SIMPA").SIMPA
     out["DGCNConv"] = load("nn.directed.DGCNConv").DGCNConv
     out["complex_relu_layer"] = load("nn.directed.complex_relu").complex_relu_layer
+    out["SNEAConv"] = load("nn.signed.SNEAConv").SNEAConv
     return out

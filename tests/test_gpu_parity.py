@@ -391,3 +391,38 @@ def test_dense_tensor_core_strided_operands_and_relu():
     agree = (((r != 0) | ((a - b).abs() < 1e-5)) == ((mask != 0) | ((a - b).abs() < 1e-5))).all()
     assert bool(agree)
     assert_close_rel(i * (r != 0), (a + b) * mask * (r != 0).double(), 2e-6)
+
+
+# ------------------------------------------------------------------------------- SNEAConv
+def _make_snea(g, first):
+    fo, fi = g["lin_b_weight"].shape
+    conv = nn.SNEAConv(fi, fo, first_aggr=first).to(DEV)
+    with torch.no_grad():
+        for nm in ("lin_b", "lin_u", "alpha_b", "alpha_u"):
+            getattr(conv, nm).weight.copy_(g[nm + "_weight"])
+            getattr(conv, nm).bias.copy_(g[nm + "_bias"])
+    return conv
+
+
+@pytest.mark.parametrize("name,first", [("snea_first", True), ("snea_second", False)])
+def test_snea_golden(name, first):
+    g = load_golden(name, DEV)
+    y = _make_snea(g, first)(g["x"], g["pos_edge_index"], g["neg_edge_index"])
+    assert_close_rel(y, g["out"], 1e-5)
+
+
+def test_snea_two_layer_vs_oracle_wide():
+    n = 5000
+    pos, neg, _ = synthetic.ssbm_edges(n, 3, num_entries=100_000, eta=0.1, seed=5)
+    x = torch.randn(n, 64, generator=torch.Generator().manual_seed(2))
+    torch.manual_seed(3)
+    c1 = nn.SNEAConv(64, 32, first_aggr=True).to(DEV)
+    c2 = nn.SNEAConv(32, 32, first_aggr=False).to(DEV)
+    z1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))
+    z2 = c2(torch.tanh(z1), pos.to(DEV), neg.to(DEV))
+    cpu = lambda m: [t.detach().cpu() for t in (m.lin_b.weight, m.lin_b.bias, m.lin_u.weight, m.lin_u.bias,
+                                                m.alpha_b.weight, m.alpha_b.bias, m.alpha_u.weight, m.alpha_u.bias)]
+    r1 = port.snea_conv(x, pos, neg, *cpu(c1), True)
+    r2 = port.snea_conv(torch.tanh(r1), pos, neg, *cpu(c2), False)
+    assert_close_rel(z1, r1, 1e-5)
+    assert_close_rel(z2, r2, 1e-5)

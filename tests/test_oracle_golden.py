@@ -108,3 +108,18 @@ def test_row_subset_evaluator_matches_full():
     o_r, o_i = port.magnet_conv_rows(rows, g["x_real"], g["x_imag"], cr, g["weight"], g["bias"])
     assert_close_rel(o_r, g["out_real"][rows], 1e-5)
     assert_close_rel(o_i, g["out_imag"][rows], 1e-5)
+
+
+@pytest.mark.parametrize("name,first", [("snea_first", True), ("snea_second", False)])
+def test_snea_port(name, first):
+    g = load_golden(name)
+    y = port.snea_conv(g["x"], g["pos_edge_index"], g["neg_edge_index"], g["lin_b_weight"], g["lin_b_bias"],
+                       g["lin_u_weight"], g["lin_u_bias"], g["alpha_b_weight"], g["alpha_b_bias"],
+                       g["alpha_u_weight"], g["alpha_u_bias"], first)
+    assert_close_rel(y, g["out"], 1e-5)
+    if first:
+        # quirk Q7: the message is the target's own feature times alpha, so the first layer is
+        # lin(x) on every node that has a (self-)loop, and exactly 0 on ids above the largest edge id
+        h = torch.nn.functional.linear(g["x"], g["lin_b_weight"], g["lin_b_bias"])
+        assert_close_rel(g["out"][:134, :6], h[:134], 1e-5)
+        assert float(g["out"][134:].abs().max()) == 0.0

@@ -80,3 +80,23 @@ del big, big2
 idx = torch.randint(0, N, (nnz // 4,), device=dev)
 ms = timeit(lambda: xr.index_select(0, idx), 5, 2)
 emit(what="torch_index_select_quarter", ms=ms, gbs=(nnz // 4) * F * 4 * 2 / ms / 1e6)
+
+# ---- experiment: column-segmented multi-pass aggregation (L2-resident segments, output RMW)
+if os.environ.get("SWEEP_SEGMENTS", "1") == "1":
+    from pytorch_geometric_signed_directed_b200 import distributed as pgd
+    for S in (4, 8, 16):
+        bounds = pgd.node_bounds(N, S)
+        blocks = pgd.split_columns_by_owner(p, bounds, own_rank=0)
+        xs = [(xr[bounds[b]:bounds[b + 1]], xi[bounds[b]:bounds[b + 1]]) for b in range(S)]
+
+        def run():
+            y = ops.spmm(blocks[0], list(xs[0]), (0, 1), out=[yr, yi])
+            for b in range(1, S):
+                y = ops.spmm(blocks[b], list(xs[b]), (0, 1), beta=1.0, zs=y, out=y)
+            return y
+        ms = timeit(run, 5, 2)
+        ref = ops.spmm(p, [xr, xi], (0, 1))
+        got = run()
+        err = (got[0] - ref[0]).abs().max().item() / ref[0].abs().max().item()
+        emit(what="spmm2_segmented", segments=S, ms=ms, rel_err=err)
+        del blocks
