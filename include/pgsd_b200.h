@@ -150,6 +150,9 @@ typedef struct pgsd_spmm_args {
   int32_t variant;           /* 0 = library default; >0 selects a tuning variant      */
   int32_t diag_row_offset;   /* x row holding destination row 0 (diag term only): lets x span a
                                 larger node range than the plan's rows (row-sharded plans)  */
+  float op_scale[2];         /* per-operator multiplier of alpha (0 is read as 1): -1 on the
+                                antisymmetric imaginary operator gives the transposed
+                                aggregation of the backward pass from the same plan        */
 } pgsd_spmm_args;
 
 PGSD_API int pgsd_spmm_csr(const pgsd_spmm_args* args, pgsd_stream_t stream);
@@ -224,6 +227,15 @@ typedef struct pgsd_attn_args {
 } pgsd_attn_args;
 
 PGSD_API int pgsd_edge_softmax(const pgsd_attn_args* args, pgsd_stream_t stream);
+
+/* Weight / bias gradient of y = X W (backward pass):
+ *   dw[k, n] += sum_r x[r, k] * g[r, n];   db[n] += sum_r g[r, n]   (db may be NULL)
+ * x: [n_rows, k], g: [n_rows, n] (fp32 or bf16), dw/db fp32 accumulated with atomics: the
+ * caller zero-initialises them.  Replaces autograd's matmul backward for the call sites listed
+ * under pgsd_dense_transform. */
+PGSD_API int pgsd_xtg_accumulate(const void* x, int64_t ldx, const void* g, int64_t ldg, int64_t n_rows,
+                                 int32_t k, int32_t n, int32_t dtype, float* dw, int64_t lddw, float* db,
+                                 pgsd_stream_t stream);
 
 /* Halo pack for the node-range sharded path (no reference counterpart: the reference is
  * single-device): out[i, :] = x[index[i], :]  -- rows another rank asked for. */

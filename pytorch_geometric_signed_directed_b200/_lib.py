@@ -29,6 +29,7 @@ class SpmmArgs(C.Structure):
         ("z", _vp * 2), ("ldz", _i64 * 2),
         ("y", _vp * 2), ("ldy", _i64 * 2),
         ("bias", _vp), ("variant", _i32), ("diag_row_offset", _i32),
+        ("op_scale", _f32 * 2),
     ]
 
 
@@ -68,6 +69,7 @@ _PROTOTYPES = {
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),
     "pgsd_dense_transform": (C.c_int, [C.POINTER(DenseArgs), _vp]),
     "pgsd_edge_softmax": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "pgsd_xtg_accumulate": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
 }
 

@@ -40,6 +40,7 @@ struct SpmmParams {
   int64_t ldy_bytes[2];
   const float* bias;
   int64_t diag_row_offset;
+  float alpha_op[2];   // alpha * op_scale[k]
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
         }
         float out[EPL];
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) out[i] = p.alpha * (acc[k][i] * inv);
+        for (int i = 0; i < EPL; ++i) out[i] = p.alpha_op[k] * (acc[k][i] * inv);
         if (p.z[k] != nullptr) {
           float zr[EPL];
           RV::load(p.z[k] + row * p.ldz_bytes[k] + lane_off, zr);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) spmm_rows_scalar_kernel(const SpmmParams 
         const bool has_diag = p.diag[k] != nullptr;
         const float dg = has_diag ? p.diag[k][row] : p.diag_const[k];
         if (has_diag || dg != 0.f) acc = fmaf(dg, rd(p.x[k], p.ldx_bytes[k], row + p.diag_row_offset, f), acc);
-        float out = p.alpha * (acc * inv);
+        float out = p.alpha_op[k] * (acc * inv);
         if (p.z[k]) out = fmaf(p.beta, rd(p.z[k], p.ldz_bytes[k], row, f), out);
         if (p.bias) out += p.bias[f];
         char* q = p.y[k] + row * p.ldy_bytes[k];
@@ -320,6 +321,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   p.beta = a->beta;
   p.bias = a->bias;
   p.diag_row_offset = a->diag_row_offset;
+  for (int k = 0; k < 2; ++k) p.alpha_op[k] = a->alpha * (a->op_scale[k] == 0.f ? 1.f : a->op_scale[k]);
   bool vec16 = (int64_t(a->feat) * es) % 16 == 0;
   bool vec32 = (int64_t(a->feat) * es) % 32 == 0;
   for (int k = 0; k < a->n_ops; ++k) {
@@ -382,6 +384,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
       int rc = pgsd_spmm_csr(&one, stream);
       if (rc != PGSD_OK) return rc;
       one.val[0] = a->val[1], one.diag[0] = a->diag[1], one.diag_const[0] = a->diag_const[1];
+      one.op_scale[0] = a->op_scale[1];
       one.x[0] = a->x[1], one.ldx[0] = a->ldx[1], one.z[0] = a->z[1], one.ldz[0] = a->ldz[1];
       one.y[0] = a->y[1], one.ldy[0] = a->ldy[1];
       return pgsd_spmm_csr(&one, stream);

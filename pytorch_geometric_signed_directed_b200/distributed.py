@@ -40,7 +40,8 @@ def split_rows(plan: CSRPlan, lo: int, hi: int) -> CSRPlan:
     vals = [None if v is None else v[a:b] for v in plan.val]
     diags = [None if d is None else d[lo:hi] for d in plan.diag]
     return CSRPlan(hi - lo, plan.n_src, b - a, plan.num_input_edges, (rp - rp[0]).contiguous(),
-                   plan.col[a:b], vals, diags, list(plan.diag_const), dict(plan.meta))
+                   plan.col[a:b], vals, diags, list(plan.diag_const),
+                   {k: v for k, v in plan.meta.items() if k != "hermitian"})
 
 
 def split_columns_by_owner(local: CSRPlan, bounds: Sequence[int], own_rank: int) -> List[CSRPlan]:

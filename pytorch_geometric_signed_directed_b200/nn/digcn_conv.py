@@ -17,7 +17,7 @@ import torch
 from torch import Tensor
 from torch.nn import Linear, Parameter
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, plan as _plan
 
 
 class DiGCNConv(torch.nn.Module):
@@ -72,11 +72,11 @@ class DiGCNConv(torch.nn.Module):
             n = xw.size(0)
             self._plan = _plan.build_csr(edge_index, edge_weight, n, n, "source_to_target")
             self._cached_inputs = (edge_index, edge_weight)
-        return ops.spmm(self._plan, [xw], (0,), bias=self.bias, out=None if out is None else [out])[0]
+        return ag.spmm(self._plan, [xw], (0,), bias=self.bias, out=None if out is None else [out])[0]
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None) -> Tensor:
         _plan.require_cuda(x, "x")
-        xw = ops.dense([(x, self.weight, 0)], self.out_channels)[0]
+        xw = ag.dense([(x, self.weight, 0)], self.out_channels)[0]
         return self._aggregate(xw, edge_index, edge_weight)
 
     def __repr__(self):
@@ -105,13 +105,12 @@ class DiGCN_InceptionBlock(torch.nn.Module):
                 edge_weight2: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         _plan.require_cuda(x, "x")
         out_dim = self.conv1.out_channels
-        w_all = torch.cat([self.ln.weight.detach().t().float(), self.conv1.weight.detach().float(),
-                           self.conv2.weight.detach().float()], dim=1)          # [in, 3*out]
+        w_all = torch.cat([self.ln.weight.t().float(), self.conv1.weight.float(),
+                           self.conv2.weight.float()], dim=1)                   # [in, 3*out]
         b_all = None
         if self.ln.bias is not None:
-            b_all = torch.cat([self.ln.bias.detach().float(),
-                               torch.zeros(2 * out_dim, device=x.device)])
-        buf = ops.dense([(x, w_all, 0)], 3 * out_dim, bias=b_all)[0]              # [N, 3*out]
+            b_all = torch.cat([self.ln.bias.float(), torch.zeros(2 * out_dim, device=x.device)])
+        buf = ag.dense([(x, w_all, 0)], 3 * out_dim, bias=b_all)[0]               # [N, 3*out]
         x0 = buf[:, :out_dim]
         x1 = self.conv1._aggregate(buf[:, out_dim:2 * out_dim], edge_index, edge_weight)
         x2 = self.conv2._aggregate(buf[:, 2 * out_dim:], edge_index2, edge_weight2)

@@ -14,7 +14,9 @@ The reference's quirks are reproduced on purpose: aggregation is source_to_targe
 `target_to_source` default at MagNetConv.py:51 is dead code) and its four chains
 collapse to A and B (two are duplicates).
 
-Forward only in this round: outputs carry no autograd graph.
+Autograd: x_real / x_imag / weight / bias are differentiable through `autograd.py` (the
+backward aggregation reuses the same plan: L~_r is symmetric, L~_i antisymmetric); edge weights
+and a trainable q receive no gradient.
 """
 from __future__ import annotations
 
@@ -25,7 +27,7 @@ import torch
 from torch import Tensor
 from torch.nn import Parameter
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, plan as _plan
 from .._lib import DENSE_MAX_TERMS
 
 
@@ -165,7 +167,7 @@ class _MagneticChebConv(torch.nn.Module):
 
     def _cheb_forward(self, x_real: Tensor, x_imag: Tensor):
         p = self._plan
-        w = self.weight.detach()
+        w = self.weight
         k1 = w.size(0)
         if 2 * k1 > DENSE_MAX_TERMS:
             raise NotImplementedError(
@@ -173,17 +175,17 @@ class _MagneticChebConv(torch.nn.Module):
         dt = x_real.dtype
         if dt not in (torch.float32, torch.bfloat16):
             raise TypeError(f"MagNetConv kernels take float32 or bfloat16 features, got {dt}")
-        t0 = [x_real.detach(), x_imag.detach().to(dt)]
+        t0 = [x_real, x_imag.to(dt)]
         terms = [(t0[0], w[0], 0), (t0[1], w[0], 1)]
         if k1 > 1:
-            t1 = ops.spmm(p, t0, (0, 1))
+            t1 = ag.spmm(p, t0, (0, 1))
             terms += [(t1[0], w[1], 0), (t1[1], w[1], 1)]
             for k in range(2, k1):
-                t2 = ops.spmm(p, t1, (0, 1), alpha=2.0, beta=-1.0, zs=t0)  # MagNetConv.py:214-216
+                t2 = ag.spmm(p, t1, (0, 1), alpha=2.0, beta=-1.0, zs=t0)  # MagNetConv.py:214-216
                 terms += [(t2[0], w[k], 0), (t2[1], w[k], 1)]
                 t0, t1 = t1, t2
-        out_real, out_imag = ops.dense(terms, self.out_channels, bias=self.bias, combine=True,
-                                       relu_mode=1 if self.fused_complex_relu else 0)
+        out_real, out_imag = ag.dense(terms, self.out_channels, bias=self.bias, combine=True,
+                                      relu_mode=1 if self.fused_complex_relu else 0)
         return out_real, out_imag
 
     def __repr__(self):

@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 from torch.nn.parameter import Parameter
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, ops, plan as _plan
 
 
 class Conv_Base(torch.nn.Module):
@@ -53,7 +53,7 @@ class Conv_Base(torch.nn.Module):
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None) -> Tensor:
         _plan.require_cuda(x, "x")
         p = self.plan_for(edge_index, edge_weight, x.size(self.node_dim))
-        return ops.spmm(p, [x], (0,))[0]
+        return ag.spmm(p, [x], (0,))[0]
 
 
 class DIMPA(torch.nn.Module):
@@ -74,6 +74,15 @@ class DIMPA(torch.nn.Module):
         n, f = x_s.size(0), x_s.size(1)
         p_s = self.conv_layer.plan_for(edge_index, edge_weight, n, transpose=False)
         p_t = self.conv_layer.plan_for(edge_index, edge_weight, n, transpose=True)
+        if ag._needs_grad([x_s, x_t, self._w_s, self._w_t]):
+            feat_s, feat_t = self._w_s[0] * x_s, self._w_t[0] * x_t
+            cur_s, cur_t = x_s, x_t
+            for h in range(1, 1 + self._hop):
+                cur_s = ag.spmm(p_s, [cur_s], (0,))[0]
+                cur_t = ag.spmm(p_t, [cur_t], (0,))[0]
+                feat_s = feat_s + self._w_s[h] * cur_s
+                feat_t = feat_t + self._w_t[h] * cur_t
+            return torch.cat([feat_s, feat_t], dim=1)
         w_s, w_t = self._w_s.detach(), self._w_t.detach()
         feat = torch.empty((n, 2 * f), dtype=x_s.dtype, device=x_s.device)
         feat_s, feat_t = feat[:, :f], feat[:, f:]

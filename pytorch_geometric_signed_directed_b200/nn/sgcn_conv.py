@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, ops, plan as _plan
 
 
 class _Lin(torch.nn.Module):
@@ -75,21 +75,24 @@ class SGCNConv(torch.nn.Module):
         pos = self._plan_for(pos_edge_index, n_dst, n_src)
         neg = self._plan_for(neg_edge_index, n_dst, n_src)
         fi, fo = self.in_dim, self.out_dim
-        wb, wu = self.lin_b.weight.detach().t(), self.lin_u.weight.detach().t()   # [mult*in, out] views
-        out = torch.empty((n_dst, 2 * fo), dtype=x_src.dtype, device=x_src.device)
-        m_pos = ops.spmm(pos, [x_src], (0,), mean=True)[0]
-        m_neg = ops.spmm(neg, [x_src], (0,), mean=True)[0]
+        wb, wu = self.lin_b.weight.t(), self.lin_u.weight.t()          # [mult*in, out] views
+        m_pos = ag.spmm(pos, [x_src], (0,), mean=True)[0]
+        m_neg = ag.spmm(neg, [x_src], (0,), mean=True)[0]
         if self.first_aggr:
-            ops.dense([(m_pos, wb[:fi], 0), (x_dst, wb[fi:], 0)], fo, bias=self.lin_b.bias,
-                      out=[out[:, :fo]])
-            ops.dense([(m_neg, wu[:fi], 0), (x_dst, wu[fi:], 0)], fo, bias=self.lin_u.bias,
-                      out=[out[:, fo:]])
+            terms_b = [(m_pos, wb[:fi], 0), (x_dst, wb[fi:], 0)]
+            terms_u = [(m_neg, wu[:fi], 0), (x_dst, wu[fi:], 0)]
         else:
             # x = [x_b | x_u]; m_pos = [mean+(x_b) | mean+(x_u)], m_neg = [mean-(x_b) | mean-(x_u)]
-            ops.dense([(m_pos[:, :fi], wb[:fi], 0), (m_neg[:, fi:], wb[fi:2 * fi], 0),
-                       (x_dst[:, :fi], wb[2 * fi:], 0)], fo, bias=self.lin_b.bias, out=[out[:, :fo]])
-            ops.dense([(m_pos[:, fi:], wu[:fi], 0), (m_neg[:, :fi], wu[fi:2 * fi], 0),
-                       (x_dst[:, fi:], wu[2 * fi:], 0)], fo, bias=self.lin_u.bias, out=[out[:, fo:]])
+            terms_b = [(m_pos[:, :fi], wb[:fi], 0), (m_neg[:, fi:], wb[fi:2 * fi], 0), (x_dst[:, :fi], wb[2 * fi:], 0)]
+            terms_u = [(m_pos[:, fi:], wu[:fi], 0), (m_neg[:, :fi], wu[fi:2 * fi], 0), (x_dst[:, fi:], wu[2 * fi:], 0)]
+        track = [x_src, x_dst, self.lin_b.weight, self.lin_u.weight, self.lin_b.bias, self.lin_u.bias]
+        if ag._needs_grad(track):
+            out = torch.cat([ag.dense(terms_b, fo, bias=self.lin_b.bias)[0],
+                             ag.dense(terms_u, fo, bias=self.lin_u.bias)[0]], dim=-1)
+        else:   # inference: both halves are written in place into one buffer (no torch.cat)
+            out = torch.empty((n_dst, 2 * fo), dtype=x_src.dtype, device=x_src.device)
+            ops.dense(terms_b, fo, bias=self.lin_b.bias, out=[out[:, :fo]])
+            ops.dense(terms_u, fo, bias=self.lin_u.bias, out=[out[:, fo:]])
         if self.norm_emb:
             out = F.normalize(out, p=2, dim=-1)
         return out

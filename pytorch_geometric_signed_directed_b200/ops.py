@@ -68,7 +68,7 @@ def _rows2d(t: Tensor, name: str) -> Tensor:
 def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean: bool = False,
          alpha: float = 1.0, beta: float = 0.0, zs: Optional[Sequence[Tensor]] = None,
          bias: Optional[Tensor] = None, out: Optional[Sequence[Tensor]] = None,
-         variant: Optional[int] = None) -> List[Tensor]:
+         variant: Optional[int] = None, op_scale: Optional[Sequence[float]] = None) -> List[Tensor]:
     """y_k = alpha * (diag_k x_k[r] + sum val_k x_k[col]) (/len if mean) + beta * z_k + bias
     for the plan operators listed in `ops` (1 or 2 of them), one kernel launch.
     xs/zs/out may be column slices of wider row-major buffers."""
@@ -84,15 +84,21 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
     a.alpha, a.beta = float(alpha), float(beta)
     a.variant = SPMM_VARIANT if variant is None else variant
     a.diag_row_offset = int(plan.meta.get("diag_row_offset", 0))
+    if op_scale is not None:
+        for k, sc in enumerate(op_scale):
+            a.op_scale[k] = float(sc)
     outs = []
     keep = []
     for k, op in enumerate(ops):
         x = xs[k]
         if x.size(1) != feat or x.dtype != xs[0].dtype:
             raise ValueError("spmm: operands must share feature width and dtype")
-        if x.size(0) < plan.n_src or x.size(0) < plan.n_dst + a.diag_row_offset:
-            raise ValueError(f"spmm: x has {x.size(0)} rows, plan gathers from {plan.n_src}")
         v, d = plan.val[op], plan.diag[op]
+        has_diag = d is not None or plan.diag_const[op] != 0.0
+        if x.size(0) < plan.n_src or (has_diag and x.size(0) < plan.n_dst + a.diag_row_offset):
+            raise ValueError(f"spmm: x has {x.size(0)} rows, plan gathers from {plan.n_src}"
+                             + (f" and reads the diagonal at rows up to {plan.n_dst + a.diag_row_offset}"
+                                if has_diag else ""))
         a.val[k] = None if v is None else v.data_ptr()
         a.diag[k] = None if d is None else d.data_ptr()
         a.diag_const[k] = plan.diag_const[op]
@@ -235,3 +241,21 @@ def edge_softmax(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Seque
                    "pgsd_edge_softmax")
     LAUNCHES += 1
     return y, alphas
+
+
+def xtg_accumulate(x: Tensor, g: Tensor, dw: Tensor, db: Optional[Tensor] = None) -> None:
+    """dw[k, n] += sum_r x[r, k] g[r, n]; db[n] += sum_r g[r, n]  (`pgsd_xtg_accumulate`)."""
+    global LAUNCHES
+    x, g = _rows2d(x.detach(), "x"), _rows2d(g.detach(), "g")
+    if x.dtype != g.dtype or x.size(0) != g.size(0):
+        raise ValueError("xtg: x and g must share dtype and row count")
+    if dw.dtype != torch.float32 or not dw.is_contiguous() or tuple(dw.shape) != (x.size(1), g.size(1)):
+        raise ValueError("xtg: dw must be a contiguous fp32 [k, n] tensor")
+    lib = _lib.load()
+    with torch.cuda.device(x.device), _Timed("xtg", x.device):
+        _lib.check(lib.pgsd_xtg_accumulate(x.data_ptr(), x.stride(0), g.data_ptr(), g.stride(0), x.size(0),
+                                           x.size(1), g.size(1), _dtype_code(x), dw.data_ptr(), dw.stride(0),
+                                           None if db is None else db.data_ptr(),
+                                           torch.cuda.current_stream(x.device).cuda_stream),
+                   "pgsd_xtg_accumulate")
+    LAUNCHES += 1

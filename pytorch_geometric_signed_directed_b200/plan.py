@@ -158,7 +158,8 @@ def build_magnetic(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, q:
             C.byref(nnz), ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
             "pgsd_build_magnetic_laplacian")
     k = nnz.value
-    meta = {"q": q, "normalization": normalization, "lambda_max": float(lambda_max), "diag_real": diag[:n]}
+    meta = {"q": q, "normalization": normalization, "lambda_max": float(lambda_max), "diag_real": diag[:n],
+            "hermitian": True}   # real part symmetric, imaginary part antisymmetric: M^T = (M_r, -M_i)
     if normalization == "sym":
         # diag(L) = 1 for every node, so the real diagonal of L~ is the constant 2/lambda_max - 1
         # (exactly 0 for the default lambda_max = 2: the reference's 2N cancelling self-loop

@@ -1,0 +1,84 @@
+"""Timings of the other BASELINE configs (parity-test cases, not bench lines): C3 DiGCN inception
+block 500k nodes / 2x10M edges / 128 bf16, C4 SGCN 2M nodes / 40M signed entries / 64 fp32, and
+DIMPA.  Writes gpurun_out/configs.jsonl with algorithmic GB/s per layer (SURVEY §8d formula)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pytorch_geometric_signed_directed_b200 import nn, ops, synthetic  # noqa: E402
+
+dev = torch.device("cuda", 0)
+os.makedirs("gpurun_out", exist_ok=True)
+fh = open("gpurun_out/configs.jsonl", "a")
+PEAK = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+    fh.write(json.dumps(kw) + "\n")
+    fh.flush()
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+with torch.no_grad():
+    # ---- C3: DiGCN_InceptionBlock, 500k nodes, two 10M-nnz operators, 128 features, bf16
+    n, e, f = 500_000, 10_000_000, 128
+    ei1, _ = synthetic.dsbm_edges(n, 3, num_edges=e, seed=1, device=dev)
+    ei2, _ = synthetic.dsbm_edges(n, 3, num_edges=e, seed=2, device=dev)
+    w1, w2 = synthetic.sym_norm_weights(ei1, n), synthetic.sym_norm_weights(ei2, n)
+    x = (torch.rand(n, f, device=dev) * 2 - 1).bfloat16()
+    blk = nn.DiGCN_InceptionBlock(f, f).to(dev)
+    blk(x, ei1, w1, ei2, w2)
+    nnz = ei1.size(1) + ei2.size(1)
+    b_alg = nnz * 8 + 2 * (n + 1) * 4 + nnz * f * 2 + n * f * 2 * (1 + 3 + 2 + 2)   # x, buf(3), 2 gathers src, x1, x2
+    ms = timeit(lambda: blk(x, ei1, w1, ei2, w2))
+    emit(config="C3 DiGCN_InceptionBlock 500k/2x10M/128 bf16", ms=ms, edges_per_s=nnz / ms * 1e3,
+         alg_gb=b_alg / 1e9, alg_gbs=b_alg / ms / 1e6, frac=b_alg / ms / 1e6 / PEAK)
+    del ei1, ei2, w1, w2, x, blk
+    torch.cuda.empty_cache()
+
+    # ---- C4: SGCN (in=64, out=64 -> conv1 64->32|32, conv2 (32|32)->32|32), 2M nodes, 40M signed entries
+    n = 2_000_000
+    pos, neg, _ = synthetic.ssbm_edges(n, 3, num_entries=40_000_000, eta=0.1, seed=0, device=dev)
+    x = torch.randn(n, 64, device=dev)
+    c1 = nn.SGCNConv(64, 32, first_aggr=True).to(dev)
+    c2 = nn.SGCNConv(32, 32, first_aggr=False).to(dev)
+    z1 = torch.tanh(c1(x, pos, neg))
+    c2(z1, pos, neg)
+    nnz = pos.size(1) + neg.size(1)
+    b1 = nnz * 4 + 2 * (n + 1) * 4 + nnz * 64 * 4 + n * 64 * 4 * (2 + 1 + 1)     # 2 mean outs, x read, out
+    ms1 = timeit(lambda: c1(x, pos, neg))
+    ms2 = timeit(lambda: c2(z1, pos, neg))
+    emit(config="C4 SGCNConv layer 1 2M/40M/64 fp32", ms=ms1, edges_per_s=nnz / ms1 * 1e3, alg_gb=b1 / 1e9,
+         alg_gbs=b1 / ms1 / 1e6, frac=b1 / ms1 / 1e6 / PEAK)
+    emit(config="C4 SGCNConv layer 2 2M/40M/(32|32) fp32", ms=ms2, edges_per_s=nnz / ms2 * 1e3, alg_gb=b1 / 1e9,
+         alg_gbs=b1 / ms2 / 1e6, frac=b1 / ms2 / 1e6 / PEAK)
+    del pos, neg, x, z1
+    torch.cuda.empty_cache()
+
+    # ---- DIMPA hop=2 on 1M nodes / 20M edges / 64
+    n = 1_000_000
+    ei, _ = synthetic.dsbm_edges(n, 3, num_edges=20_000_000, seed=0, device=dev)
+    ew = torch.rand(ei.size(1), device=dev) + 0.5
+    xs, xt = torch.rand(n, 64, device=dev), torch.rand(n, 64, device=dev)
+    dm = nn.DIMPA(hop=2).to(dev)
+    dm(xs, xt, ei, ew)
+    ms = timeit(lambda: dm(xs, xt, ei, ew))
+    b = 4 * (ei.size(1) * (8 + 256) + (n + 1) * 4 + n * 256 * 2) + 4 * n * 256 * 3
+    emit(config="DIMPA hop=2 1M/20M/64 fp32", ms=ms, edges_per_s=4 * ei.size(1) / ms * 1e3, alg_gb=b / 1e9,
+         alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK)
