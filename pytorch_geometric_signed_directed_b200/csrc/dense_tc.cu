@@ -26,7 +26,6 @@ namespace tc {
 
 constexpr int THREADS = 512;
 constexpr int TILE_M = 128;
-constexpr int CHUNK_K = 32;              // tf32 elements in one 128-byte swizzle row
 constexpr int STAGES = 2;
 constexpr int STAGE_BYTES = 2 * TILE_M * 128;   // hi + lo
 constexpr int PF = 4;                    // chunks in flight per thread (2 x LDG.128 each)
@@ -35,19 +34,19 @@ constexpr int MAX_SLABS = 16;
 
 struct Params {
   int64_t n_rows;
-  int32_t n_chunks, n_slabs, relu_mode, pad;
-  const float* x[MAX_CHUNKS];     // term base + k0
-  int64_t ldx[MAX_CHUNKS];
+  int32_t n_chunks, n_slabs, relu_mode, n_total;   // n_total: full output width (N tiles over grid.y)
+  const char* x[MAX_CHUNKS];      // term base + k0 (bytes already applied)
+  int64_t ldx_bytes[MAX_CHUNKS];
   int8_t group[MAX_CHUNKS];
   int8_t slab[MAX_CHUNKS];
   int8_t first[MAX_CHUNKS];       // first chunk of its group inside a tile -> overwrite TMEM
-  int8_t kvalid[MAX_CHUNKS];      // valid k in this chunk (multiple of 4, <= 32)
+  int8_t kvalid[MAX_CHUNKS];      // valid k in this chunk (fp32: <= 32, bf16: <= 64)
   const float* w[MAX_SLABS];      // weight base + k0 * ldw_k
   int64_t ldw_k[MAX_SLABS], ldw_n[MAX_SLABS];
   int8_t wk[MAX_SLABS];           // valid k rows of the slab
   const float* bias;
-  float* y[2];
-  int64_t ldy[2];
+  char* y[2];
+  int64_t ldy_bytes[2];
 };
 
 // ------------------------------------------------------------------------------ PTX helpers
@@ -162,16 +161,38 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------ kernel
-template <int N_OUT, int GROUPS>
+// BF16 = false: fp32 operands, 3xTF32 (hi/lo split), 32 k per 128-byte chunk row.
+// BF16 = true : bf16 operands fed to kind::f16 directly, 64 k per 128-byte chunk row, bf16 output.
+// grid.y tiles the output width in N_OUT-column tiles (weights / bias / outputs offset by n0).
+template <int N_OUT, int GROUPS, bool BF16>
 __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_constant__ Params p) {
   constexpr int CPW = N_OUT / 4;                 // output columns per epilogue warp
-  constexpr int SLAB_BYTES = 2 * N_OUT * 128;    // hi + lo
+  constexpr int ES = BF16 ? 2 : 4;               // operand element size
+  constexpr int EPC = 16 / ES;                   // elements per 16-byte unit
+  constexpr int CK = 128 / ES;                   // k per chunk
+  constexpr int HALF = N_OUT * 128;              // one [N_OUT x 128 B] weight image
+  constexpr int SLAB_BYTES = BF16 ? HALF : 2 * HALF;
+  constexpr int UMMA_K_BYTES = 32;               // 8 tf32 or 16 bf16
   constexpr uint32_t TMEM_COLS = (GROUPS * N_OUT <= 32) ? 32 : (GROUPS * N_OUT <= 64) ? 64
                                : (GROUPS * N_OUT <= 128) ? 128 : 256;
-  // instruction descriptor: c=F32 [4,6), a=b=TF32 [7,10)/[10,13), K-major both, N>>3 [17,23),
-  // M>>4 [24,29)
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N_OUT >> 3) << 17) |
+  // instruction descriptor: c=F32 [4,6), a/b format [7,10)/[10,13) (TF32 = 2, BF16 = 1), K-major
+  // both, N>>3 [17,23), M>>4 [24,29)
+  constexpr uint32_t FMT = BF16 ? 1u : 2u;
+  constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | (uint32_t(N_OUT >> 3) << 17) |
                              (uint32_t(TILE_M >> 4) << 24);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -183,6 +204,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * N_OUT;             // first output column of this CTA
   const uint32_t a_addr = smem_u32(a_stage), w_addr = smem_u32(w_smem);
   const uint32_t bar_addr = smem_u32(bars);
   const uint64_t pol_stream = policy_evict_first();
@@ -197,17 +219,22 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
     for (int s = 0; s <= STAGES; ++s) mbar_init(bar_addr + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // weights -> hi/lo slabs, K-major SW128: element (n, k) at n*128 + (((k>>2) ^ (n&7)) << 4) + (k&3)*4
-  for (int idx = tid; idx < p.n_slabs * CHUNK_K * N_OUT; idx += THREADS) {
-    const int s = idx / (CHUNK_K * N_OUT);
-    const int rem = idx - s * (CHUNK_K * N_OUT);
+  // weights -> K-major SW128 images: element (n, k) lives in 16-byte unit (k / EPC) ^ (n & 7) of
+  // row n (128 B per row).  fp32: hi image then lo image; bf16: one rounded image.
+  for (int idx = tid; idx < p.n_slabs * CK * N_OUT; idx += THREADS) {
+    const int s = idx / (CK * N_OUT);
+    const int rem = idx - s * (CK * N_OUT);
     const int k = rem / N_OUT, n = rem - k * N_OUT;
     float v = 0.f;
-    if (k < p.wk[s]) v = __ldg(p.w[s] + k * p.ldw_k[s] + n * p.ldw_n[s]);
-    const float hi = to_tf32(v), lo = to_tf32(v - hi);
-    const int off = n * 128 + (((k >> 2) ^ (n & 7)) << 4) + (k & 3) * 4;
-    *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + off) = hi;
-    *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + N_OUT * 128 + off) = lo;
+    if (k < p.wk[s] && n0 + n < p.n_total) v = __ldg(p.w[s] + k * p.ldw_k[s] + (n0 + n) * p.ldw_n[s]);
+    const int off = n * 128 + (((k / EPC) ^ (n & 7)) << 4) + (k % EPC) * ES;
+    if constexpr (BF16) {
+      *reinterpret_cast<__nv_bfloat16*>(w_smem + s * SLAB_BYTES + off) = __float2bfloat16_rn(v);
+    } else {
+      const float hi = to_tf32(v), lo = to_tf32(v - hi);
+      *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + off) = hi;
+      *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + HALF + off) = lo;
+    }
   }
   fence_async_smem();
   tc_fence_before();
@@ -215,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // loader role: rows r0 = tid/8 and r0 + 64 of the tile, 16-byte chunk c16 = tid%8 of the row
+  // loader role: rows r0 = tid/8 and r0 + 64 of the tile, 16-byte unit c16 = tid%8 of the row
   const int r0 = tid >> 3, c16 = tid & 7;
   const uint32_t st_off0 = uint32_t(r0) * 128 + uint32_t((c16 ^ (r0 & 7)) << 4);
   const uint32_t st_off1 = st_off0 + 64 * 128;   // (r0 + 64) & 7 == r0 & 7
@@ -223,14 +250,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
   float4 buf[PF][2];
   auto issue = [&](int slot, int64_t tile, int c) {
-    const bool kin = (c16 * 4) < p.kvalid[c];
-    const float* base = p.x[c] + c16 * 4;
+    const bool kin = (c16 * EPC) < p.kvalid[c];
+    const char* base = p.x[c] + c16 * 16;
     const int64_t ra = tile * TILE_M + r0, rb = ra + 64;
     buf[slot][0] = (tile < n_tiles && kin && ra < p.n_rows)
-                       ? __ldg(reinterpret_cast<const float4*>(base + ra * p.ldx[c]))
+                       ? __ldg(reinterpret_cast<const float4*>(base + ra * p.ldx_bytes[c]))
                        : make_float4(0.f, 0.f, 0.f, 0.f);
     buf[slot][1] = (tile < n_tiles && kin && rb < p.n_rows)
-                       ? __ldg(reinterpret_cast<const float4*>(base + rb * p.ldx[c]))
+                       ? __ldg(reinterpret_cast<const float4*>(base + rb * p.ldx_bytes[c]))
                        : make_float4(0.f, 0.f, 0.f, 0.f);
   };
 #pragma unroll
@@ -249,19 +276,22 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
         if (c < p.n_chunks) {
           const uint32_t stage = uses % STAGES;
           if (uses >= STAGES) mbar_wait(bar_addr + 8 * stage, ((uses / STAGES) - 1) & 1);
-          // split the two rows this thread holds and store them swizzled
           uint8_t* hi = a_stage + stage * STAGE_BYTES;
           uint8_t* lo = hi + TILE_M * 128;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 v = buf[u][h];
-            float4 vh, vl;
-            vh.x = to_tf32(v.x), vh.y = to_tf32(v.y), vh.z = to_tf32(v.z), vh.w = to_tf32(v.w);
-            vl.x = to_tf32(v.x - vh.x), vl.y = to_tf32(v.y - vh.y);
-            vl.z = to_tf32(v.z - vh.z), vl.w = to_tf32(v.w - vh.w);
             const uint32_t off = h ? st_off1 : st_off0;
-            *reinterpret_cast<float4*>(hi + off) = vh;
-            *reinterpret_cast<float4*>(lo + off) = vl;
+            if constexpr (BF16) {
+              *reinterpret_cast<float4*>(hi + off) = v;      // 8 bf16, already in operand format
+            } else {                                          // split the fp32 values into tf32 hi/lo
+              float4 vh, vl;
+              vh.x = to_tf32(v.x), vh.y = to_tf32(v.y), vh.z = to_tf32(v.z), vh.w = to_tf32(v.w);
+              vl.x = to_tf32(v.x - vh.x), vl.y = to_tf32(v.y - vh.y);
+              vl.z = to_tf32(v.z - vh.z), vl.w = to_tf32(v.w - vh.w);
+              *reinterpret_cast<float4*>(hi + off) = vh;
+              *reinterpret_cast<float4*>(lo + off) = vl;
+            }
           }
           // refill this register slot with the next chunk that maps to it
           {
@@ -276,14 +306,18 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
             tc_fence_after();
             const uint32_t d = tmem_base + uint32_t(p.group[c]) * N_OUT;
             const uint32_t a_hi = a_addr + stage * STAGE_BYTES, a_lo = a_hi + TILE_M * 128;
-            const uint32_t w_hi = w_addr + uint32_t(p.slab[c]) * SLAB_BYTES, w_lo = w_hi + N_OUT * 128;
+            const uint32_t w_hi = w_addr + uint32_t(p.slab[c]) * SLAB_BYTES, w_lo = w_hi + HALF;
 #pragma unroll
-            for (int j = 0; j < CHUNK_K / 8; ++j) {
-              const uint32_t ko = j * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+            for (int j = 0; j < 128 / UMMA_K_BYTES; ++j) {
+              const uint32_t ko = j * UMMA_K_BYTES;   // one MMA's K extent inside the 128-byte swizzle row
               const uint32_t acc0 = (p.first[c] && j == 0) ? 0u : 1u;
-              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
-              mma_tf32(d, make_desc(a_lo + ko), make_desc(w_hi + ko), IDESC, 1u);
-              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_lo + ko), IDESC, 1u);
+              if constexpr (BF16) {
+                mma_bf16(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
+              } else {
+                mma_tf32(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
+                mma_tf32(d, make_desc(a_lo + ko), make_desc(w_hi + ko), IDESC, 1u);
+                mma_tf32(d, make_desc(a_hi + ko), make_desc(w_lo + ko), IDESC, 1u);
+              }
             }
             tc_commit(bar_addr + 8 * stage);                      // stage may be overwritten
             if (c == p.n_chunks - 1) tc_commit(bar_addr + 8 * STAGES);   // accumulators complete
@@ -304,11 +338,12 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
       if (GROUPS == 2) tmem_ld<CPW>(taddr + N_OUT, b);
       tmem_ld_wait();
       const int64_t row = tile * TILE_M + q * 32 + lane;
-      if (row < p.n_rows) {
+      const int ncol = n0 + cblk * CPW;            // first global output column of this thread
+      if (row < p.n_rows && ncol < p.n_total) {
         float o0[CPW], o1[CPW];
 #pragma unroll
         for (int i = 0; i < CPW; ++i) {
-          const float bs = p.bias ? __ldg(p.bias + cblk * CPW + i) : 0.f;
+          const float bs = p.bias ? __ldg(p.bias + ncol + i) : 0.f;
           if (GROUPS == 2) {
             o0[i] = (a[i] - b[i]) + bs;
             o1[i] = (a[i] + b[i]) + bs;
@@ -320,15 +355,25 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
             o0[i] = a[i] + bs;
           }
         }
-        float* y0 = p.y[0] + row * p.ldy[0] + cblk * CPW;
 #pragma unroll
-        for (int i = 0; i < CPW; i += 4)
-          st_stream_v4(y0 + i, make_float4(o0[i], o0[i + 1], o0[i + 2], o0[i + 3]), pol_stream);
-        if (GROUPS == 2) {
-          float* y1 = p.y[1] + row * p.ldy[1] + cblk * CPW;
+        for (int g = 0; g < GROUPS; ++g) {
+          const float* o = g ? o1 : o0;
+          char* yp = p.y[g] + row * p.ldy_bytes[g] + int64_t(ncol) * ES;
+          if constexpr (BF16) {
 #pragma unroll
-          for (int i = 0; i < CPW; i += 4)
-            st_stream_v4(y1 + i, make_float4(o1[i], o1[i + 1], o1[i + 2], o1[i + 3]), pol_stream);
+            for (int i = 0; i < CPW; i += 8) {
+              float4 pk;
+              pk.x = __uint_as_float(pack_bf16(o[i], o[i + 1]));
+              pk.y = __uint_as_float(pack_bf16(o[i + 2], o[i + 3]));
+              pk.z = __uint_as_float(pack_bf16(o[i + 4], o[i + 5]));
+              pk.w = __uint_as_float(pack_bf16(o[i + 6], o[i + 7]));
+              st_stream_v4(yp + i * 2, pk, pol_stream);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CPW; i += 4)
+              st_stream_v4(yp + i * 4, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]), pol_stream);
+          }
         }
       }
     }
@@ -344,14 +389,21 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
   }
 }
 
-template <int N_OUT, int GROUPS>
+static size_t smem_bytes(int n_slabs, int n_tile, bool bf16) {
+  return 1024 + STAGES * STAGE_BYTES + size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (STAGES + 1) + 16;
+}
+
+template <int N_OUT, int GROUPS, bool BF16>
 static int launch(const Params& p, cudaStream_t st) {
-  const size_t smem = 1024 + STAGES * STAGE_BYTES + size_t(p.n_slabs) * 2 * N_OUT * 128 + 8 * (STAGES + 1) + 16;
-  auto kern = dense_tc_kernel<N_OUT, GROUPS>;
+  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16);
+  auto kern = dense_tc_kernel<N_OUT, GROUPS, BF16>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
-  int64_t grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  kern<<<unsigned(grid), THREADS, smem, st>>>(p);
+  const int n_col_tiles = (p.n_total + N_OUT - 1) / N_OUT;
+  int64_t gx = sm_count() / n_col_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  kern<<<dim3(unsigned(gx), unsigned(n_col_tiles)), THREADS, smem, st>>>(p);
   PGSD_LAUNCH_CHECK("dense_tc_kernel");
   return PGSD_OK;
 }
@@ -365,26 +417,32 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   using namespace tc;
   *handled = 0;
-  if (a->dtype != PGSD_F32) return PGSD_OK;
+  const bool bf16 = a->dtype == PGSD_BF16;
+  const int es = bf16 ? 2 : 4, ck = 128 / es, kal = 16 / es;
   const int n = a->n_out;
-  if (!(n == 16 || n == 32 || n == 64 || n == 128)) return PGSD_OK;
+  // output tile width: the whole width when it is a supported tile, else 128-column tiles
+  int n_tile = 0;
+  if (n == 16 || n == 32 || n == 64 || n == 128) n_tile = n;
+  else if (n > 128 && n % 128 == 0) n_tile = 128;
+  if (n_tile == 0 || (bf16 && n_tile < 32)) return PGSD_OK;
   const int groups = a->combine ? 2 : 1;
   Params p{};
   p.n_rows = a->n_rows;
+  p.n_total = n;
   p.relu_mode = a->relu_mode;
   p.bias = a->bias;
   for (int i = 0; i < groups; ++i) {
-    if (!al16(a->y[i]) || (a->ldy[i] & 3)) return PGSD_OK;
-    p.y[i] = static_cast<float*>(a->y[i]);
-    p.ldy[i] = a->ldy[i];
+    if (!al16(a->y[i]) || ((a->ldy[i] * es) & 15)) return PGSD_OK;
+    p.y[i] = static_cast<char*>(a->y[i]);
+    p.ldy_bytes[i] = a->ldy[i] * es;
   }
   bool seen_group[2] = {false, false};
   for (int t = 0; t < a->n_terms; ++t) {
-    const float* x = static_cast<const float*>(a->x[t]);
-    if (!al16(x) || (a->ldx[t] & 3) || (a->k[t] & 3) || a->k[t] == 0) return PGSD_OK;
-    for (int k0 = 0; k0 < a->k[t]; k0 += CHUNK_K) {
+    const char* x = static_cast<const char*>(a->x[t]);
+    if (!al16(x) || ((a->ldx[t] * es) & 15) || (a->k[t] % kal) || a->k[t] == 0) return PGSD_OK;
+    for (int k0 = 0; k0 < a->k[t]; k0 += ck) {
       if (p.n_chunks >= MAX_CHUNKS) return PGSD_OK;
-      const int kv = (a->k[t] - k0) < CHUNK_K ? (a->k[t] - k0) : CHUNK_K;
+      const int kv = (a->k[t] - k0) < ck ? (a->k[t] - k0) : ck;
       const float* wb = a->w[t] + int64_t(k0) * a->ldw_k[t];
       int s = -1;
       for (int j = 0; j < p.n_slabs; ++j)
@@ -395,8 +453,8 @@ int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
         p.w[s] = wb, p.ldw_k[s] = a->ldw_k[t], p.ldw_n[s] = a->ldw_n[t], p.wk[s] = int8_t(kv);
       }
       const int c = p.n_chunks++;
-      p.x[c] = x + k0;
-      p.ldx[c] = a->ldx[t];
+      p.x[c] = x + int64_t(k0) * es;
+      p.ldx_bytes[c] = a->ldx[t] * es;
       p.group[c] = int8_t(a->group[t]);
       p.slab[c] = int8_t(s);
       p.kvalid[c] = int8_t(kv);
@@ -405,14 +463,16 @@ int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
     }
   }
   if (groups == 2 && !(seen_group[0] && seen_group[1])) return PGSD_OK;
-  const size_t smem = 1024 + STAGES * STAGE_BYTES + size_t(p.n_slabs) * 2 * n * 128 + 8 * (STAGES + 1) + 16;
-  if (smem > 220 * 1024) return PGSD_OK;
-  int rc;
-#define PGSD_TC(N_)                                                                       \
-  rc = groups == 2 ? launch<N_, 2>(p, st) : launch<N_, 1>(p, st);                         \
+  if (smem_bytes(p.n_slabs, n_tile, bf16) > 220 * 1024) return PGSD_OK;
+  int rc = PGSD_OK;
+#define PGSD_TC(N_)                                                                             \
+  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st) : launch<N_, 1, true>(p, st);         \
+  else rc = groups == 2 ? launch<N_, 2, false>(p, st) : launch<N_, 1, false>(p, st);            \
   break;
-  switch (n) {
-    case 16: PGSD_TC(16)
+  switch (n_tile) {
+    case 16:
+      rc = groups == 2 ? launch<16, 2, false>(p, st) : launch<16, 1, false>(p, st);
+      break;
     case 32: PGSD_TC(32)
     case 64: PGSD_TC(64)
     default: PGSD_TC(128)

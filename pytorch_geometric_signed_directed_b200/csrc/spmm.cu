@@ -355,6 +355,9 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   int W = 0;
   if (want256 && can256) W = 8;
   else if (want128 && can128) W = 4;
+  // measured defaults (profiles/r01_sweep_v*.jsonl): one operator -> 256-bit gathers with 4 loads
+  // in flight (1.68 ms vs 2.21 ms at 40M nnz, F=64); two operators -> 128-bit gathers, U = 4
+  else if (a->n_ops == 1 && can256 && row_bytes >= 128) W = 8;
   else if (can128) W = 4;
   else if (can256) W = 8;
 
@@ -373,7 +376,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   p.lpr_active = int(row_bytes / (4 * W));
   int lpr = 1;
   while (lpr < p.lpr_active) lpr <<= 1;
-  if (U != 2 && U != 4 && U != 8) U = (W == 8) ? 2 : 4;
+  if (U != 2 && U != 4 && U != 8) U = (W == 8 && a->n_ops == 2) ? 2 : 4;
   if (W == 8 && U == 8) U = 4;
 
   if (a->dtype == PGSD_BF16) {
@@ -389,7 +392,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
       one.y[0] = a->y[1], one.ldy[0] = a->ldy[1];
       return pgsd_spmm_csr(&one, stream);
     }
-    if (W == 8) return dispatch_lpr<8, 1, 2, true>(lpr, p, st);
+    if (W == 8) return dispatch_lpr<8, 1, 4, true>(lpr, p, st);
     return dispatch_lpr<4, 1, 4, true>(lpr, p, st);
   }
   if (a->n_ops == 2) {

@@ -426,3 +426,25 @@ def test_snea_two_layer_vs_oracle_wide():
     r2 = port.snea_conv(torch.tanh(r1), pos, neg, *cpu(c2), False)
     assert_close_rel(z1, r1, 1e-5)
     assert_close_rel(z2, r2, 1e-5)
+
+
+@pytest.mark.parametrize("n_rows,k,n_out,dtype", [
+    (3000, 128, 384, torch.bfloat16),     # inception block: one pass over x for [W_ln | W_1 | W_2], 3 column tiles
+    (1000, 64, 128, torch.bfloat16),
+    (515, 72, 64, torch.bfloat16),        # partial K chunk (72 = 64 + 8)
+    (2000, 64, 256, torch.float32),       # fp32 with two 128-column tiles
+])
+def test_dense_tensor_core_bf16_and_column_tiles(n_rows, k, n_out, dtype):
+    gen = torch.Generator(device=DEV).manual_seed(n_rows + k)
+    x = torch.randn(n_rows, k, generator=gen, device=DEV).to(dtype)
+    w = (torch.randn(k, n_out, generator=gen, device=DEV) / k ** 0.5)
+    if dtype == torch.bfloat16:
+        w = w.bfloat16().float()          # bf16-representable parameters (a bf16 model)
+    bias = torch.randn(n_out, generator=gen, device=DEV)
+    ref = x.double() @ w.double() + bias.double()
+    tc = ops.dense([(x, w, 0)], n_out, bias=bias, variant=2)[0]
+    ff = ops.dense([(x, w, 0)], n_out, bias=bias, variant=1)[0]
+    tol = 6e-3 if dtype == torch.bfloat16 else 2e-6      # one bf16 output rounding = 2^-9 relative
+    assert tc.dtype == dtype
+    assert_close_rel(tc.double(), ref, tol, "tcgen05")
+    assert_close_rel(ff.double(), ref, tol, "ffma")
