@@ -41,6 +41,7 @@ struct SpmmParams {
   const float* bias;
   int64_t diag_row_offset;
   float alpha_op[2];   // alpha * op_scale[k]
+  int use_groups;      // host-side switch: group-per-row kernel for short rows
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -206,6 +207,136 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
   }
 }
 
+// ---- group-per-row variant for SHORT rows --------------------------------------------------
+// Each LPR-lane group owns a whole destination row (no cross-group reduction), so a warp keeps
+// 32/LPR rows in flight, and the NEXT row's pointers and first index batch are fetched while the
+// current row's gathers are outstanding (the index latency leaves the critical path).  Used when
+// the mean row length is small: per-owner column blocks of the sharded path (~deg/world entries
+// per row), low-degree graphs (SGCN's per-sign lists), L2-blocked column segments.
+template <int W, int LPR, int NOPS, int U, bool BF16, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmParams p) {
+  using RV = RowVec<W, BF16>;
+  constexpr int EPL = RV::EPL;
+  constexpr int G = 32 / LPR;
+  constexpr unsigned FULL = 0xffffffffu;
+
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR;
+  const int l = lane % LPR;
+  const bool lane_active = l < p.lpr_active;
+  const int64_t lane_off = int64_t(l) * (W * 4);
+  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_stream = policy_evict_first();
+
+  const int64_t groups_total = int64_t(gridDim.x) * (THREADS / 32) * G;
+  int64_t row = (int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5)) * G + g;
+
+  // software pipeline state: pointers and first index batch of the row about to be processed
+  auto load_ptrs = [&](int64_t r, int& s, int& e) {
+    s = e = 0;
+    if (r < p.n_rows) s = __ldg(p.row_ptr + r), e = __ldg(p.row_ptr + r + 1);
+  };
+  auto load_batch = [&](int base, int end, int& c, float (&v)[NOPS]) {
+    c = 0;
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) v[k] = 0.f;
+    const int e = base + l;
+    if (e < end) {
+      c = ld_stream_i32(p.col + e, pol_stream);
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) v[k] = p.val[k] ? ld_stream_f32(p.val[k] + e, pol_stream) : 1.f;
+    }
+  };
+  int start, end, c;
+  float v[NOPS];
+  load_ptrs(row, start, end);
+  load_batch(start, end, c, v);
+
+  while (__any_sync(FULL, row < p.n_rows)) {
+    const bool row_ok = row < p.n_rows;
+    // (1) next row's pointers: in flight during this row's gathers
+    const int64_t nrow = row + groups_total;
+    int nstart, nend;
+    load_ptrs(nrow, nstart, nend);
+
+    float acc[NOPS][EPL];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
+
+    int nc = 0;
+    float nv[NOPS];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) nv[k] = 0.f;
+    bool next_issued = false;
+    for (int base = start; __any_sync(FULL, base < end); base += LPR) {
+      if (base != start) load_batch(base, end, c, v);      // later batches of a long row
+      const int cnt = min(LPR, end - base);                // <= 0 once this group's row is done
+      for (int j = 0; __any_sync(FULL, j < cnt); j += U) {
+        float d[NOPS][U][EPL];
+        float vv[NOPS][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = j + u;
+          const int cc = __shfl_sync(FULL, c, idx & (LPR - 1), LPR);
+          const bool ok = (idx < cnt) && lane_active;
+#pragma unroll
+          for (int k = 0; k < NOPS; ++k) {
+            const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
+            vv[k][u] = ok ? t : 0.f;
+            if (ok)
+              RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
+            else
+              RV::zero(d[k][u]);
+          }
+        }
+        if (!next_issued) {      // (2) next row's first index batch, issued behind the first gathers
+          load_batch(nstart, nend, nc, nv);
+          next_issued = true;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
+      }
+    }
+    if (!next_issued) load_batch(nstart, nend, nc, nv);    // every row of this warp was empty
+
+    if (row_ok && lane_active) {
+      const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) {
+        const bool has_diag = p.diag[k] != nullptr;
+        const float dg = has_diag ? __ldg(p.diag[k] + row) : p.diag_const[k];
+        if (has_diag || dg != 0.f) {
+          float xr[EPL];
+          RV::load(p.x[k] + (row + p.diag_row_offset) * p.ldx_bytes[k] + lane_off, xr);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(dg, xr[i], acc[k][i]);
+        }
+        float out[EPL];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) out[i] = p.alpha_op[k] * (acc[k][i] * inv);
+        if (p.z[k] != nullptr) {
+          float zr[EPL];
+          RV::load(p.z[k] + row * p.ldz_bytes[k] + lane_off, zr);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] = fmaf(p.beta, zr[i], out[i]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + l * EPL + i);
+        }
+        RV::store(p.y[k] + row * p.ldy_bytes[k] + lane_off, out, pol_stream);
+      }
+    }
+    row = nrow, start = nstart, end = nend, c = nc;
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) v[k] = nv[k];
+  }
+}
+
 // ---- scalar fallback: any F, any alignment (reference tests use F = 2, 3) -------------------
 template <bool BF16>
 __global__ void __launch_bounds__(256) spmm_rows_scalar_kernel(const SpmmParams p, int n_ops) {
@@ -264,7 +395,26 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const char* x, int64_t
 
 // ---- host dispatch -------------------------------------------------------------------------
 template <int W, int LPR, int NOPS, int U, bool BF16>
+static int launch_groups(const SpmmParams& p, cudaStream_t st) {
+  constexpr int THREADS = 256;
+  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;
+  constexpr int G = 32 / LPR;
+  auto kern = spmm_groups_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
+  int occ = 0;
+  PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  if (occ < 1) occ = 1;
+  int64_t need = ceil_div<int64_t>(p.n_rows, (THREADS / 32) * G);
+  int64_t grid = int64_t(sm_count()) * occ;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<dim3((unsigned)grid), dim3(THREADS), 0, st>>>(p);
+  PGSD_LAUNCH_CHECK("spmm_groups_kernel");
+  return PGSD_OK;
+}
+
+template <int W, int LPR, int NOPS, int U, bool BF16>
 static int launch_rows(const SpmmParams& p, cudaStream_t st) {
+  if (p.use_groups) return launch_groups<W, LPR, NOPS, (U > 4 ? 4 : U), BF16>(p, st);
   constexpr int THREADS = 256;
   // register budget: keep >= 3 CTAs (24 warps) resident when the tile is small
   constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;
@@ -346,10 +496,12 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   }
   const int64_t row_bytes = int64_t(a->feat) * es;
   // variant encoding (0 = library default): bits 0-3 = loads in flight per lane and operator
-  // (U = 2/4/8), bit 4 = prefer 128-bit gathers, bit 5 = prefer 256-bit gathers.
+  // (U = 2/4/8), bit 4 = prefer 128-bit gathers, bit 5 = prefer 256-bit gathers, bit 6 = the
+  // group-per-row kernel (every LPR-lane group owns a row; for short rows).
   int U = a->variant & 0xf;
   const bool want128 = (a->variant & 0x10) != 0;
   const bool want256 = (a->variant & 0x20) != 0;
+  p.use_groups = (a->variant & 0x40) != 0;   // group-per-row kernel (short rows)
   const bool can256 = vec32 && row_bytes <= 32 * 32;
   const bool can128 = vec16 && row_bytes <= 32 * 16;
   int W = 0;

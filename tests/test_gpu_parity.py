@@ -448,3 +448,29 @@ def test_dense_tensor_core_bf16_and_column_tiles(n_rows, k, n_out, dtype):
     assert tc.dtype == dtype
     assert_close_rel(tc.double(), ref, tol, "tcgen05")
     assert_close_rel(ff.double(), ref, tol, "ffma")
+
+
+@pytest.mark.parametrize("f,dtype,n_ops", [(64, torch.float32, 2), (64, torch.float32, 1), (16, torch.float32, 2),
+                                           (32, torch.float32, 1), (128, torch.float32, 2), (48, torch.float32, 1),
+                                           (128, torch.bfloat16, 1), (64, torch.bfloat16, 1)])
+def test_group_per_row_kernel_matches_row_kernel(f, dtype, n_ops):
+    """variant bit 0x40: the short-row kernel (each lane group owns a row, next row's indices
+    prefetched) against the warp-per-row kernel, all epilogues, ragged / empty / long rows."""
+    g = torch.Generator().manual_seed(f + n_ops)
+    n = 3001
+    e = 9000
+    ei = torch.randint(0, n - 40, (2, e), generator=g)          # last 40 rows empty
+    ei[1, :700] = 5                                               # one long row (700 entries)
+    ei = ei.to(DEV)
+    p = planmod.build_magnetic(ei, None, n, 0.25, "sym", 1.6)    # non-zero real diagonal
+    xs = [(torch.rand(n, f, generator=g) * 2 - 1).to(DEV).to(dtype) for _ in range(n_ops)]
+    zs = [(torch.rand(n, f, generator=g) * 2 - 1).to(DEV).to(dtype) for _ in range(n_ops)]
+    bias = torch.randn(f, generator=g).to(DEV)
+    ops_ids = (0, 1)[:n_ops] if n_ops == 2 else (1,)
+    tol = 2e-6 if dtype == torch.float32 else 1e-2
+    for kw in (dict(), dict(alpha=2.0, beta=-1.0, zs=zs), dict(bias=bias), dict(mean=True)):
+        ref = ops.spmm(p, xs, ops_ids, variant=0x10 | 4, **kw)
+        for variant in (0x40, 0x40 | 2, 0x40 | 0x20 | 2, 0x40 | 0x10 | 4):
+            got = ops.spmm(p, xs, ops_ids, variant=variant, **kw)
+            for a, b in zip(got, ref):
+                assert_close_rel(a.float(), b.float(), tol, f"variant {variant:#x} {list(kw)}")
