@@ -148,8 +148,8 @@ typedef struct pgsd_spmm_args {
   int64_t ldy[2];
   const float* bias;         /* [F] or NULL                                           */
   int32_t variant;           /* 0 = library default; bits 0-3 loads in flight (2/4/8), 0x10 /
-                                0x20 prefer 128- / 256-bit gathers, 0x40 group-per-row kernel
-                                (recommended when nnz / n_rows < ~16)                       */
+                                0x20 prefer 128- / 256-bit gathers, 0x80 warp-per-row kernel
+                                instead of the default group-per-row kernel                 */
   int32_t diag_row_offset;   /* x row holding destination row 0 (diag term only): lets x span a
                                 larger node range than the plan's rows (row-sharded plans)  */
   float op_scale[2];         /* per-operator multiplier of alpha (0 is read as 1): -1 on the

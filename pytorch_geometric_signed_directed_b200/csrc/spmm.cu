@@ -247,93 +247,106 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
       for (int k = 0; k < NOPS; ++k) v[k] = p.val[k] ? ld_stream_f32(p.val[k] + e, pol_stream) : 1.f;
     }
   };
+  // pipeline state: current batch = entries [base, base+LPR) of `row`; (c, v) hold lane l's entry
   int start, end, c;
   float v[NOPS];
   load_ptrs(row, start, end);
   load_batch(start, end, c, v);
+  int base = start;
+  int64_t nrow = row + groups_total;
+  int nstart, nend;
+  load_ptrs(nrow, nstart, nend);           // next row's pointers are always one row ahead
+
+  float acc[NOPS][EPL];
+#pragma unroll
+  for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
 
   while (__any_sync(FULL, row < p.n_rows)) {
-    const bool row_ok = row < p.n_rows;
-    // (1) next row's pointers: in flight during this row's gathers
-    const int64_t nrow = row + groups_total;
-    int nstart, nend;
-    load_ptrs(nrow, nstart, nend);
-
-    float acc[NOPS][EPL];
-#pragma unroll
-    for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
-
+    const int cnt = min(LPR, end - base);                  // <= 0 for an empty / finished row
+    const bool more = base + LPR < end;                    // this row continues with another batch
     int nc = 0;
     float nv[NOPS];
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) nv[k] = 0.f;
     bool next_issued = false;
-    for (int base = start; __any_sync(FULL, base < end); base += LPR) {
-      if (base != start) load_batch(base, end, c, v);      // later batches of a long row
-      const int cnt = min(LPR, end - base);                // <= 0 once this group's row is done
-      for (int j = 0; __any_sync(FULL, j < cnt); j += U) {
-        float d[NOPS][U][EPL];
-        float vv[NOPS][U];
+    for (int j = 0; __any_sync(FULL, j < cnt); j += U) {
+      float d[NOPS][U][EPL];
+      float vv[NOPS][U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int idx = j + u;
-          const int cc = __shfl_sync(FULL, c, idx & (LPR - 1), LPR);
-          const bool ok = (idx < cnt) && lane_active;
+      for (int u = 0; u < U; ++u) {
+        const int idx = j + u;
+        const int cc = __shfl_sync(FULL, c, idx & (LPR - 1), LPR);
+        const bool ok = (idx < cnt) && lane_active;
 #pragma unroll
-          for (int k = 0; k < NOPS; ++k) {
-            const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
-            vv[k][u] = ok ? t : 0.f;
-            if (ok)
-              RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
-            else
-              RV::zero(d[k][u]);
-          }
+        for (int k = 0; k < NOPS; ++k) {
+          const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
+          vv[k][u] = ok ? t : 0.f;
+          if (ok)
+            RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
+          else
+            RV::zero(d[k][u]);
         }
-        if (!next_issued) {      // (2) next row's first index batch, issued behind the first gathers
-          load_batch(nstart, nend, nc, nv);
-          next_issued = true;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int k = 0; k < NOPS; ++k)
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
       }
+      if (!next_issued) {
+        // the NEXT batch's indices (same row, or the first batch of the next row) go out right
+        // behind the first gathers, so their latency overlaps the feature traffic
+        if (more) load_batch(base + LPR, end, nc, nv);
+        else load_batch(nstart, nend, nc, nv);
+        next_issued = true;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
     }
-    if (!next_issued) load_batch(nstart, nend, nc, nv);    // every row of this warp was empty
+    if (!next_issued) {                                     // no group of this warp had entries
+      if (more) load_batch(base + LPR, end, nc, nv);
+      else load_batch(nstart, nend, nc, nv);
+    }
 
-    if (row_ok && lane_active) {
-      const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
+    if (more) {
+      base += LPR;
+    } else {
+      if (row < p.n_rows && lane_active) {
+        const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
 #pragma unroll
-      for (int k = 0; k < NOPS; ++k) {
-        const bool has_diag = p.diag[k] != nullptr;
-        const float dg = has_diag ? __ldg(p.diag[k] + row) : p.diag_const[k];
-        if (has_diag || dg != 0.f) {
-          float xr[EPL];
-          RV::load(p.x[k] + (row + p.diag_row_offset) * p.ldx_bytes[k] + lane_off, xr);
+        for (int k = 0; k < NOPS; ++k) {
+          const bool has_diag = p.diag[k] != nullptr;
+          const float dg = has_diag ? __ldg(p.diag[k] + row) : p.diag_const[k];
+          if (has_diag || dg != 0.f) {
+            float xr[EPL];
+            RV::load(p.x[k] + (row + p.diag_row_offset) * p.ldx_bytes[k] + lane_off, xr);
 #pragma unroll
-          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(dg, xr[i], acc[k][i]);
+            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(dg, xr[i], acc[k][i]);
+          }
+          float out[EPL];
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] = p.alpha_op[k] * (acc[k][i] * inv);
+          if (p.z[k] != nullptr) {
+            float zr[EPL];
+            RV::load(p.z[k] + row * p.ldz_bytes[k] + lane_off, zr);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) out[i] = fmaf(p.beta, zr[i], out[i]);
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + l * EPL + i);
+          }
+          RV::store(p.y[k] + row * p.ldy_bytes[k] + lane_off, out, pol_stream);
         }
-        float out[EPL];
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) out[i] = p.alpha_op[k] * (acc[k][i] * inv);
-        if (p.z[k] != nullptr) {
-          float zr[EPL];
-          RV::load(p.z[k] + row * p.ldz_bytes[k] + lane_off, zr);
-#pragma unroll
-          for (int i = 0; i < EPL; ++i) out[i] = fmaf(p.beta, zr[i], out[i]);
-        }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + l * EPL + i);
-        }
-        RV::store(p.y[k] + row * p.ldy_bytes[k] + lane_off, out, pol_stream);
       }
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
+      row = nrow, start = nstart, end = nend, base = nstart;
+      nrow += groups_total;
+      load_ptrs(nrow, nstart, nend);
     }
-    row = nrow, start = nstart, end = nend, c = nc;
+    c = nc;
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) v[k] = nv[k];
+    __syncwarp();
   }
 }
 
@@ -397,7 +410,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const char* x, int64_t
 template <int W, int LPR, int NOPS, int U, bool BF16>
 static int launch_groups(const SpmmParams& p, cudaStream_t st) {
   constexpr int THREADS = 256;
-  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;
+  constexpr int MINB = (NOPS * U * (BF16 ? 2 * W : W) >= 64) ? 2 : 3;   // fp32 values held per lane
   constexpr int G = 32 / LPR;
   auto kern = spmm_groups_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
   int occ = 0;
@@ -417,7 +430,7 @@ static int launch_rows(const SpmmParams& p, cudaStream_t st) {
   if (p.use_groups) return launch_groups<W, LPR, NOPS, (U > 4 ? 4 : U), BF16>(p, st);
   constexpr int THREADS = 256;
   // register budget: keep >= 3 CTAs (24 warps) resident when the tile is small
-  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;
+  constexpr int MINB = (NOPS * U * (BF16 ? 2 * W : W) >= 64) ? 2 : 3;   // fp32 values held per lane
   auto kern = spmm_rows_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
   int occ = 0;
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
@@ -496,12 +509,14 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   }
   const int64_t row_bytes = int64_t(a->feat) * es;
   // variant encoding (0 = library default): bits 0-3 = loads in flight per lane and operator
-  // (U = 2/4/8), bit 4 = prefer 128-bit gathers, bit 5 = prefer 256-bit gathers, bit 6 = the
-  // group-per-row kernel (every LPR-lane group owns a row; for short rows).
+  // (U = 2/4/8), bit 4 = prefer 128-bit gathers, bit 5 = prefer 256-bit gathers, bit 7 = use the
+  // warp-per-row kernel instead of the default group-per-row kernel.
   int U = a->variant & 0xf;
   const bool want128 = (a->variant & 0x10) != 0;
   const bool want256 = (a->variant & 0x20) != 0;
-  p.use_groups = (a->variant & 0x40) != 0;   // group-per-row kernel (short rows)
+  // group-per-row kernel unless the warp-per-row kernel is requested (bit 7); measured faster at
+  // every row length tried (2.91 vs 3.18 ms at 40 entries/row, 2-3x at 5 entries/row)
+  p.use_groups = (a->variant & 0x80) == 0;
   const bool can256 = vec32 && row_bytes <= 32 * 32;
   const bool can128 = vec16 && row_bytes <= 32 * 16;
   int W = 0;

@@ -22,9 +22,6 @@ SPMM_VARIANT = int(os.environ.get("PGSD_SPMM_VARIANT", "0"))
 # 0 = auto (tcgen05 3xTF32 path when the shape fits, else FFMA), 1 = force FFMA, 2 = require tcgen05
 DENSE_VARIANT = int(os.environ.get("PGSD_DENSE_VARIANT", "0"))
 
-# mean row length below which the group-per-row aggregation kernel is selected
-SHORT_ROW_MEAN = float(os.environ.get("PGSD_SHORT_ROW_MEAN", "16"))
-
 # counts kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 
@@ -86,8 +83,6 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
     a.row_ptr, a.col = plan.row_ptr.data_ptr(), plan.col.data_ptr()
     a.alpha, a.beta = float(alpha), float(beta)
     a.variant = SPMM_VARIANT if variant is None else variant
-    if variant is None and SPMM_VARIANT == 0 and plan.nnz < SHORT_ROW_MEAN * max(plan.n_dst, 1):
-        a.variant = 0x40          # short rows: group-per-row kernel
     a.diag_row_offset = int(plan.meta.get("diag_row_offset", 0))
     if op_scale is not None:
         for k, sc in enumerate(op_scale):

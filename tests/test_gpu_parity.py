@@ -129,7 +129,7 @@ def test_spmm_variants_agree_and_fused_relu():
     x1 = (torch.rand(n, f, generator=g) * 2 - 1).to(DEV)
     p = planmod.build_magnetic(ei, None, n, 0.25, "sym", 2.0)
     base = ops.spmm(p, [x0, x1], (0, 1), variant=0)
-    for variant in (2, 4, 8, 0x10 | 2, 0x20 | 2, 0x20 | 4):
+    for variant in (2, 4, 8, 0x10 | 2, 0x20 | 2, 0x20 | 4, 0x80, 0x80 | 2, 0x80 | 8, 0x80 | 0x20 | 2):
         got = ops.spmm(p, [x0, x1], (0, 1), variant=variant)
         assert_close_rel(got[0], base[0], 2e-6, f"variant {variant:#x} op0")
         assert_close_rel(got[1], base[1], 2e-6, f"variant {variant:#x} op1")
@@ -469,8 +469,8 @@ def test_group_per_row_kernel_matches_row_kernel(f, dtype, n_ops):
     ops_ids = (0, 1)[:n_ops] if n_ops == 2 else (1,)
     tol = 2e-6 if dtype == torch.float32 else 1e-2
     for kw in (dict(), dict(alpha=2.0, beta=-1.0, zs=zs), dict(bias=bias), dict(mean=True)):
-        ref = ops.spmm(p, xs, ops_ids, variant=0x10 | 4, **kw)
-        for variant in (0x40, 0x40 | 2, 0x40 | 0x20 | 2, 0x40 | 0x10 | 4):
+        ref = ops.spmm(p, xs, ops_ids, variant=0x80 | 0x10 | 4, **kw)        # warp-per-row kernel
+        for variant in (0, 2, 0x20 | 2, 0x10 | 4, 0x20 | 4):                  # group-per-row kernel
             got = ops.spmm(p, xs, ops_ids, variant=variant, **kw)
             for a, b in zip(got, ref):
                 assert_close_rel(a.float(), b.float(), tol, f"variant {variant:#x} {list(kw)}")

@@ -52,11 +52,11 @@ emit(what="plan_build_ms", ms=timeit(lambda: planmod.build_magnetic(ei, None, N,
 nnz = p.nnz
 b_alg = nnz * (12 + 2 * F * 4) + (N + 1) * 4 + 2 * N * F * 4
 yr, yi = torch.empty_like(xr), torch.empty_like(xi)
-for variant in (0x10 | 2, 0x10 | 4, 0x10 | 8, 0x20 | 2, 0x20 | 4, 0x40 | 0x10 | 4, 0x40 | 0x10 | 2, 0x40 | 0x20 | 2):
+for variant in (0x80 | 0x10 | 4, 0x80 | 0x20 | 2, 0x10 | 2, 0x10 | 4, 0x20 | 2, 0x20 | 4):
     ms = timeit(lambda: ops.spmm(p, [xr, xi], (0, 1), out=[yr, yi], variant=variant))
     emit(what="spmm2", variant=hex(variant), ms=ms, gbs=b_alg / ms / 1e6, nnz=nnz)
 b1 = nnz * (8 + F * 4) + (N + 1) * 4 + N * F * 4
-for variant in (0x10 | 4, 0x10 | 8, 0x20 | 2, 0x20 | 4, 0x40 | 0x10 | 4, 0x40 | 0x20 | 2, 0x40 | 0x20 | 4):
+for variant in (0x80 | 0x20 | 2, 0x80 | 0x20 | 4, 0x10 | 4, 0x20 | 2, 0x20 | 4):
     ms = timeit(lambda: ops.spmm(p, [xr], (0,), out=[yr], variant=variant))
     emit(what="spmm1", variant=hex(variant), ms=ms, gbs=b1 / ms / 1e6)
 
@@ -84,7 +84,7 @@ emit(what="torch_index_select_quarter", ms=ms, gbs=(nnz // 4) * F * 4 * 2 / ms /
 # ---- experiment: column-segmented multi-pass aggregation (L2-resident segments, output RMW)
 if os.environ.get("SWEEP_SEGMENTS", "1") == "1":
     from pytorch_geometric_signed_directed_b200 import distributed as pgd
-    for S in (2, 4, 8, 16):
+    for S in (2, 4, 8):
         bounds = pgd.node_bounds(N, S)
         blocks = pgd.split_columns_by_owner(p, bounds, own_rank=0)
         xs = [(xr[bounds[b]:bounds[b + 1]], xi[bounds[b]:bounds[b + 1]]) for b in range(S)]
@@ -95,7 +95,7 @@ if os.environ.get("SWEEP_SEGMENTS", "1") == "1":
                 y = ops.spmm(blocks[b], list(xs[b]), (0, 1), beta=1.0, zs=y, out=y)
             return y
         ms = timeit(run, 5, 2)
-        for variant in (0x10 | 4, 0x40 | 0x10 | 4, 0x40 | 0x10 | 2, 0x40 | 0x20 | 2):
+        for variant in (0x10 | 4, 0x10 | 2, 0x20 | 2):
             def run_v():
                 y = ops.spmm(blocks[0], list(xs[0]), (0, 1), out=[yr, yi], variant=variant)
                 for b in range(1, S):
