@@ -197,14 +197,14 @@ extern "C" int pgsd_dense_transform(const pgsd_dense_args* a, pgsd_stream_t stre
     PGSD_REQUIRE(a->x[t] && a->w[t] && a->k[t] >= 0, "dense: term %d has a null pointer", t);
     PGSD_REQUIRE(a->group[t] == 0 || (a->combine == 1 && a->group[t] == 1), "dense: bad group");
   }
-  // variant: 0 = auto (tcgen05 3xTF32 path when the shape fits, else FFMA), 1 = force FFMA,
-  // 2 = require the tcgen05 path
+  // variant: 0 = auto (tcgen05 path when the shape fits, else FFMA), 1 = force FFMA,
+  // 2 = require the tcgen05 path, 4 = require its warp-specialised kernel
   if (a->variant != 1) {
     int handled = 0;
     int rc = dense_tc_try(a, st, &handled);
     if (rc != PGSD_OK) return rc;
     if (handled) return PGSD_OK;
-    if (a->variant == 2) return fail(PGSD_ERR_INVALID, "dense: shape outside the tcgen05 path's envelope");
+    if (a->variant == 2 || a->variant == 4) return fail(PGSD_ERR_INVALID, "dense: shape outside the tcgen05 path's envelope");
   }
   dim3 grid((unsigned)ceil_div<int64_t>(a->n_rows, BM), (unsigned)ceil_div<int>(a->n_out, BN));
   if (a->dtype == PGSD_BF16) {

@@ -728,7 +728,10 @@ int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   if (groups == 2 && !(seen_group[0] && seen_group[1])) return PGSD_OK;
   if (smem_bytes(p.n_slabs, n_tile, bf16) > 220 * 1024) return PGSD_OK;
   int rc = PGSD_OK;
-  const bool sync_kernel = a->variant == 3;   // A/B switch: the original synchronous kernel
+  // variant 4 selects the warp-specialised kernel (measured 0.589 ms vs 0.556 ms for the
+  // synchronous one at 1M x (4 x 64) -> 64: both are instruction-issue bound on the hi/lo split and
+  // address arithmetic, see profiles/README.md), so the synchronous kernel stays the default
+  const bool sync_kernel = a->variant != 4;
 #define PGSD_TC(N_)                                                                                   \
   if (sync_kernel) {                                                                                  \
     if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st) : launch<N_, 1, true>(p, st);             \

@@ -363,8 +363,8 @@ def test_dense_tensor_core_path_matches_fp64(n_rows, ks, n_out, combine):
         acc[g] += x.double() @ w.double()
     ref = [acc[0] - acc[1] + bias.double(), acc[0] + acc[1] + bias.double()] if combine \
         else [acc[0] + bias.double()]
-    tc = ops.dense(terms, n_out, bias=bias, combine=combine, variant=2)     # tcgen05, warp-specialised
-    ts = ops.dense(terms, n_out, bias=bias, combine=combine, variant=3)     # tcgen05, synchronous kernel
+    tc = ops.dense(terms, n_out, bias=bias, combine=combine, variant=4)     # tcgen05, warp-specialised
+    ts = ops.dense(terms, n_out, bias=bias, combine=combine, variant=2)     # tcgen05, synchronous kernel
     ff = ops.dense(terms, n_out, bias=bias, combine=combine, variant=1)     # FFMA
     for got_tc, got_ts, got_ff, r in zip(tc, ts, ff, ref):
         assert_close_rel(got_tc, r, 2e-6, "tcgen05 3xTF32 (warp-specialised) vs fp64")
@@ -373,10 +373,12 @@ def test_dense_tensor_core_path_matches_fp64(n_rows, ks, n_out, combine):
     # many tiles per CTA: exercises the TMEM double buffer and every mbarrier phase wrap
     if n_rows < 5000:
         big = [(x.repeat(40, 1), w, g) for x, w, g in terms]
-        b1 = ops.dense(big, n_out, bias=bias, combine=combine, variant=2)
+        b1 = ops.dense(big, n_out, bias=bias, combine=combine, variant=4)
+        b2 = ops.dense(big, n_out, bias=bias, combine=combine, variant=2)
         b3 = ops.dense(big, n_out, bias=bias, combine=combine, variant=1)
-        for u, v in zip(b1, b3):
-            assert_close_rel(u, v, 2e-6, "long run: tcgen05 vs ffma")
+        for u, u2, v in zip(b1, b2, b3):
+            assert_close_rel(u, v, 2e-6, "long run: tcgen05 (warp-specialised) vs ffma")
+            assert_close_rel(u2, v, 2e-6, "long run: tcgen05 (synchronous) vs ffma")
 
 
 def test_dense_tensor_core_strided_operands_and_relu():

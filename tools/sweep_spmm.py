@@ -66,7 +66,7 @@ w = conv.weight.detach()
 ms = timeit(lambda: ops.dense([(xr, w[0], 0), (xi, w[0], 1), (yr, w[1], 0), (yi, w[1], 1)], F,
                               bias=conv.bias, combine=True))
 emit(what="dense_combine_auto", ms=ms, gflops=4 * 2 * N * F * F / ms / 1e6)
-for dv in (1, 2, 3):
+for dv in (1, 2, 4):
     ms = timeit(lambda: ops.dense([(xr, w[0], 0), (xi, w[0], 1), (yr, w[1], 0), (yi, w[1], 1)], F, bias=conv.bias, combine=True, variant=dv))
     emit(what="dense_combine", variant=dv, ms=ms, gflops=4 * 2 * N * F * F / ms / 1e6, gbs=6 * N * F * 4 / ms / 1e6)
 emit(what="layer_forward", ms=timeit(lambda: conv(xr, xi, ei)))
