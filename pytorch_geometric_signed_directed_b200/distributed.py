@@ -18,6 +18,7 @@ gather touches one contiguous 2F*4-byte row.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -110,11 +111,10 @@ class ShardedAggregator:
     def __init__(self, local_plan: CSRPlan, bounds: Sequence[int], rank: int, world: int, group=None,
                  aggregate_fn: Callable = _default_aggregate, mode: Optional[str] = None):
         self.bounds, self.rank, self.world = list(bounds), rank, world
-        # "ring": per-owner column blocks pipelined with the exchange (wins when the exchange is
-        # long: world >= 3).  "gather": receive every shard into one [N, w] buffer and run ONE
-        # launch over all columns (wins at world <= 2, where splitting rows into short column
-        # blocks + re-reading the output costs more than the 0.7 ms of exposed transfer).
-        self.mode = mode or ("gather" if world <= 2 else "ring")
+        # "ring" (default): per-owner column blocks pipelined with the exchange.  "gather": receive
+        # every shard into one [N, w] buffer, then ONE launch over all columns (exposes the whole
+        # transfer; kept for comparison and for plans whose rows are too short to split).
+        self.mode = mode or os.environ.get("PGSD_SHARD_MODE", "ring")
         # in gather mode x spans all nodes while the plan's rows are local: tell the kernel where
         # destination row 0 lives in x (diagonal term)
         self.local_plan = CSRPlan(local_plan.n_dst, local_plan.n_src, local_plan.nnz, local_plan.num_input_edges,
