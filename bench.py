@@ -46,6 +46,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print to stdout behind our back (NCCL's
+# "NCCL version ..." banner when NCCL_DEBUG=VERSION is set on the box), so the real stdout is
+# parked on a private descriptor, fd 1 is pointed at stderr for the whole run, and only the
+# result line is written to the parked descriptor.
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -176,7 +199,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def bench_config(n_gpus):
@@ -379,7 +402,7 @@ def run_gpu_arm(args, rank, world):
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "edges_total": e_input, "nnz_per_rank": nnz,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def main():
@@ -390,6 +413,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -403,7 +427,7 @@ def main():
                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29511",
                    os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
                    "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
-            sys.exit(subprocess.call(cmd))
+            sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     run_gpu_arm(args, rank, world)
     if world > 1:

