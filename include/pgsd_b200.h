@@ -155,6 +155,16 @@ typedef struct pgsd_spmm_args {
   float op_scale[2];         /* per-operator multiplier of alpha (0 is read as 1): -1 on the
                                 antisymmetric imaginary operator gives the transposed
                                 aggregation of the backward pass from the same plan        */
+  /* hub rows (optional; fp32 only): rows longer than long_row_threshold are listed in
+   * long_rows[n_long_rows]; their entries are aggregated in long_chunk-entry slices by a
+   * second launch (fp32 atomics), long_chunk_ptr[n_long_rows + 1] = exclusive prefix of the
+   * slices per hub row.  Leave n_long_rows = 0 to process every row in the main kernel.       */
+  const int32_t* long_rows;
+  const int32_t* long_chunk_ptr;
+  int32_t n_long_rows;
+  int32_t long_row_threshold;
+  int32_t long_chunk;
+  int32_t reserved;
 } pgsd_spmm_args;
 
 PGSD_API int pgsd_spmm_csr(const pgsd_spmm_args* args, pgsd_stream_t stream);

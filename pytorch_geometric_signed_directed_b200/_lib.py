@@ -30,6 +30,8 @@ class SpmmArgs(C.Structure):
         ("y", _vp * 2), ("ldy", _i64 * 2),
         ("bias", _vp), ("variant", _i32), ("diag_row_offset", _i32),
         ("op_scale", _f32 * 2),
+        ("long_rows", _vp), ("long_chunk_ptr", _vp), ("n_long_rows", _i32),
+        ("long_row_threshold", _i32), ("long_chunk", _i32), ("reserved", _i32),
     ]
 
 

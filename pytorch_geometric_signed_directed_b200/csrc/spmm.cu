@@ -42,6 +42,7 @@ struct SpmmParams {
   int64_t diag_row_offset;
   float alpha_op[2];   // alpha * op_scale[k]
   int use_groups;      // host-side switch: group-per-row kernel for short rows
+  int long_thr;        // rows longer than this are aggregated by spmm_long_rows_kernel (0 = off)
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -123,7 +124,9 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
 
   for (; row < p.n_rows; row += warps_total) {
     const int start = __ldg(p.row_ptr + row);
-    const int end = __ldg(p.row_ptr + row + 1);
+    int end = __ldg(p.row_ptr + row + 1);
+    const int true_len = end - start;
+    if (p.long_thr > 0 && true_len > p.long_thr) end = start;   // hub row: entries handled elsewhere
 
     float acc[NOPS][EPL];
 #pragma unroll
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
         for (int i = 0; i < EPL; ++i) acc[k][i] += __shfl_xor_sync(FULL, acc[k][i], off);
 
     if (g == 0 && lane_active) {
-      const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
+      const float inv = p.mean ? 1.f / float(max(true_len, 1)) : 1.f;
 #pragma unroll
       for (int k = 0; k < NOPS; ++k) {
         const bool has_diag = p.diag[k] != nullptr;
@@ -232,9 +235,11 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
   int64_t row = (int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5)) * G + g;
 
   // software pipeline state: pointers and first index batch of the row about to be processed
-  auto load_ptrs = [&](int64_t r, int& s, int& e) {
+  auto load_ptrs = [&](int64_t r, int& s, int& e, int& tl) {
     s = e = 0;
     if (r < p.n_rows) s = __ldg(p.row_ptr + r), e = __ldg(p.row_ptr + r + 1);
+    tl = e - s;
+    if (p.long_thr > 0 && tl > p.long_thr) e = s;              // hub row: entries handled elsewhere
   };
   auto load_batch = [&](int base, int end, int& c, float (&v)[NOPS]) {
     c = 0;
@@ -248,14 +253,14 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
     }
   };
   // pipeline state: current batch = entries [base, base+LPR) of `row`; (c, v) hold lane l's entry
-  int start, end, c;
+  int start, end, true_len, c;
   float v[NOPS];
-  load_ptrs(row, start, end);
+  load_ptrs(row, start, end, true_len);
   load_batch(start, end, c, v);
   int base = start;
   int64_t nrow = row + groups_total;
-  int nstart, nend;
-  load_ptrs(nrow, nstart, nend);           // next row's pointers are always one row ahead
+  int nstart, nend, ntrue_len;
+  load_ptrs(nrow, nstart, nend, ntrue_len);   // next row's pointers are always one row ahead
 
   float acc[NOPS][EPL];
 #pragma unroll
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
       base += LPR;
     } else {
       if (row < p.n_rows && lane_active) {
-        const float inv = p.mean ? 1.f / float(max(end - start, 1)) : 1.f;
+        const float inv = p.mean ? 1.f / float(max(true_len, 1)) : 1.f;
 #pragma unroll
         for (int k = 0; k < NOPS; ++k) {
           const bool has_diag = p.diag[k] != nullptr;
@@ -339,15 +344,117 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
       }
 #pragma unroll
       for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
-      row = nrow, start = nstart, end = nend, base = nstart;
+      row = nrow, start = nstart, end = nend, base = nstart, true_len = ntrue_len;
       nrow += groups_total;
-      load_ptrs(nrow, nstart, nend);
+      load_ptrs(nrow, nstart, nend, ntrue_len);
     }
     c = nc;
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) v[k] = nv[k];
     __syncwarp();
   }
+}
+
+// ---- hub rows -------------------------------------------------------------------------------
+// Rows longer than `long_thr` (power-law graphs: one node with 10^5..10^6 neighbours) would pin a
+// single lane group for milliseconds.  The main kernels skip their entries (they still write the
+// diagonal / beta*z / bias part of the row) and this kernel spreads them over the whole GPU: one
+// warp per `chunk`-entry slice of a hub row, partial sums added with fp32 atomics (the only
+// place where the summation order is not fixed).  fp32 features only.
+template <int W, int LPR, int NOPS>
+__global__ void __launch_bounds__(256) spmm_long_rows_kernel(const SpmmParams p, const int32_t* __restrict__ long_rows,
+                                                             const int32_t* __restrict__ chunk_ptr, int n_long,
+                                                             int chunk) {
+  using RV = RowVec<W, false>;
+  constexpr int EPL = RV::EPL;
+  constexpr int G = 32 / LPR;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+  const bool lane_active = l < p.lpr_active;
+  const int64_t lane_off = int64_t(l) * (W * 4);
+  const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+  const int total = __ldg(chunk_ptr + n_long);
+  for (int ck = blockIdx.x * 8 + (threadIdx.x >> 5); ck < total; ck += gridDim.x * 8) {
+    int lo = 0, hi = n_long;                       // largest i with chunk_ptr[i] <= ck
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(chunk_ptr + mid) <= ck) lo = mid; else hi = mid;
+    }
+    const int64_t row = __ldg(long_rows + lo);
+    const int rs = __ldg(p.row_ptr + row), re = __ldg(p.row_ptr + row + 1);
+    const int start = rs + (ck - __ldg(chunk_ptr + lo)) * chunk;
+    const int end = min(re, start + chunk);
+    float acc[NOPS][EPL];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) RV::zero(acc[k]);
+    for (int base = start; base < end; base += 32) {
+      const int e = base + lane;
+      int c = 0;
+      float v[NOPS];
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) v[k] = 0.f;
+      if (e < end) {
+        c = ld_stream_i32(p.col + e, pol_stream);
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k) v[k] = p.val[k] ? ld_stream_f32(p.val[k] + e, pol_stream) : 1.f;
+      }
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; j += G * 4) {
+        float d[NOPS][4][EPL], vv[NOPS][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = j + u * G + g;
+          const int cc = __shfl_sync(FULL, c, idx & 31);
+          const bool ok = (idx < cnt) && lane_active;
+#pragma unroll
+          for (int k = 0; k < NOPS; ++k) {
+            const float t = __shfl_sync(FULL, v[k], idx & 31);
+            vv[k][u] = ok ? t : 0.f;
+            if (ok) RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
+            else RV::zero(d[k][u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
+      }
+    }
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) acc[k][i] += __shfl_xor_sync(FULL, acc[k][i], off);
+    if (g == 0 && lane_active) {
+      const float inv = p.mean ? 1.f / float(max(re - rs, 1)) : 1.f;
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) {
+        float* y = reinterpret_cast<float*>(p.y[k] + row * p.ldy_bytes[k] + lane_off);
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) atomicAdd(y + i, p.alpha_op[k] * (acc[k][i] * inv));
+      }
+    }
+  }
+}
+
+template <int W, int NOPS>
+static int launch_long(int lpr, const SpmmParams& p, const pgsd_spmm_args* a, cudaStream_t st) {
+  const int grid = sm_count() * 4;
+#define PGSD_LONG(L)                                                                                        \
+  case L:                                                                                                   \
+    spmm_long_rows_kernel<W, L, NOPS><<<grid, 256, 0, st>>>(p, a->long_rows, a->long_chunk_ptr, a->n_long_rows, \
+                                                            a->long_chunk);                                 \
+    break;
+  switch (lpr) {
+    PGSD_LONG(1) PGSD_LONG(2) PGSD_LONG(4) PGSD_LONG(8) PGSD_LONG(16) PGSD_LONG(32)
+    default: return fail(PGSD_ERR_INVALID, "spmm: bad lanes-per-row %d", lpr);
+  }
+#undef PGSD_LONG
+  PGSD_LAUNCH_CHECK("spmm_long_rows_kernel");
+  return PGSD_OK;
 }
 
 // ---- scalar fallback: any F, any alignment (reference tests use F = 2, 3) -------------------
@@ -463,6 +570,38 @@ static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<u
 
 using namespace pgsd;
 
+static int dispatch_main(const pgsd_spmm_args* a, const SpmmParams& p, int W, int U, int lpr, cudaStream_t st,
+                         pgsd_stream_t stream) {
+  if (a->dtype == PGSD_BF16) {
+    if (a->n_ops == 2) {
+      // two operators in bf16: run them as two single-operator passes
+      pgsd_spmm_args one = *a;
+      one.n_ops = 1;
+      int rc = pgsd_spmm_csr(&one, stream);
+      if (rc != PGSD_OK) return rc;
+      one.val[0] = a->val[1], one.diag[0] = a->diag[1], one.diag_const[0] = a->diag_const[1];
+      one.op_scale[0] = a->op_scale[1];
+      one.x[0] = a->x[1], one.ldx[0] = a->ldx[1], one.z[0] = a->z[1], one.ldz[0] = a->ldz[1];
+      one.y[0] = a->y[1], one.ldy[0] = a->ldy[1];
+      return pgsd_spmm_csr(&one, stream);
+    }
+    if (W == 8) return dispatch_lpr<8, 1, 4, true>(lpr, p, st);
+    return dispatch_lpr<4, 1, 4, true>(lpr, p, st);
+  }
+  if (a->n_ops == 2) {
+    if (W == 8) return U == 2 ? dispatch_lpr<8, 2, 2, false>(lpr, p, st)
+                              : dispatch_lpr<8, 2, 4, false>(lpr, p, st);
+    if (U == 2) return dispatch_lpr<4, 2, 2, false>(lpr, p, st);
+    if (U == 8) return dispatch_lpr<4, 2, 8, false>(lpr, p, st);
+    return dispatch_lpr<4, 2, 4, false>(lpr, p, st);
+  }
+  if (W == 8) return U == 2 ? dispatch_lpr<8, 1, 2, false>(lpr, p, st)
+                            : dispatch_lpr<8, 1, 4, false>(lpr, p, st);
+  if (U == 2) return dispatch_lpr<4, 1, 2, false>(lpr, p, st);
+  if (U == 8) return dispatch_lpr<4, 1, 8, false>(lpr, p, st);
+  return dispatch_lpr<4, 1, 4, false>(lpr, p, st);
+}
+
 extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   PGSD_REQUIRE(a != nullptr, "spmm: args is null");
   PGSD_REQUIRE(a->n_ops == 1 || a->n_ops == 2, "spmm: n_ops must be 1 or 2 (got %d)", a->n_ops);
@@ -546,34 +685,13 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   if (U != 2 && U != 4 && U != 8) U = (W == 8 && a->n_ops == 2) ? 2 : 4;
   if (W == 8 && U == 8) U = 4;
 
-  if (a->dtype == PGSD_BF16) {
-    if (a->n_ops == 2) {
-      // two operators in bf16: run them as two single-operator passes
-      pgsd_spmm_args one = *a;
-      one.n_ops = 1;
-      int rc = pgsd_spmm_csr(&one, stream);
-      if (rc != PGSD_OK) return rc;
-      one.val[0] = a->val[1], one.diag[0] = a->diag[1], one.diag_const[0] = a->diag_const[1];
-      one.op_scale[0] = a->op_scale[1];
-      one.x[0] = a->x[1], one.ldx[0] = a->ldx[1], one.z[0] = a->z[1], one.ldz[0] = a->ldz[1];
-      one.y[0] = a->y[1], one.ldy[0] = a->ldy[1];
-      return pgsd_spmm_csr(&one, stream);
-    }
-    if (W == 8) return dispatch_lpr<8, 1, 4, true>(lpr, p, st);
-    return dispatch_lpr<4, 1, 4, true>(lpr, p, st);
-  }
-  if (a->n_ops == 2) {
-    if (W == 8) return U == 2 ? dispatch_lpr<8, 2, 2, false>(lpr, p, st)
-                              : dispatch_lpr<8, 2, 4, false>(lpr, p, st);
-    if (U == 2) return dispatch_lpr<4, 2, 2, false>(lpr, p, st);
-    if (U == 8) return dispatch_lpr<4, 2, 8, false>(lpr, p, st);
-    return dispatch_lpr<4, 2, 4, false>(lpr, p, st);
-  }
-  if (W == 8) return U == 2 ? dispatch_lpr<8, 1, 2, false>(lpr, p, st)
-                            : dispatch_lpr<8, 1, 4, false>(lpr, p, st);
-  if (U == 2) return dispatch_lpr<4, 1, 2, false>(lpr, p, st);
-  if (U == 8) return dispatch_lpr<4, 1, 8, false>(lpr, p, st);
-  return dispatch_lpr<4, 1, 4, false>(lpr, p, st);
+  const bool hubs = a->n_long_rows > 0 && a->long_rows && a->long_chunk_ptr && a->long_row_threshold > 0 &&
+                    a->long_chunk > 0 && a->dtype == PGSD_F32;
+  p.long_thr = hubs ? a->long_row_threshold : 0;
+  int rc = dispatch_main(a, p, W, U, lpr, st, stream);
+  if (rc != PGSD_OK || !hubs) return rc;
+  if (a->n_ops == 2) return W == 8 ? launch_long<8, 2>(lpr, p, a, st) : launch_long<4, 2>(lpr, p, a, st);
+  return W == 8 ? launch_long<8, 1>(lpr, p, a, st) : launch_long<4, 1>(lpr, p, a, st);
 }
 
 extern "C" int pgsd_gather_rows(const void* x, int64_t ldx, const int32_t* index,

@@ -22,6 +22,10 @@ SPMM_VARIANT = int(os.environ.get("PGSD_SPMM_VARIANT", "0"))
 # 0 = auto (tcgen05 3xTF32 path when the shape fits, else FFMA), 1 = force FFMA, 2 = require tcgen05
 DENSE_VARIANT = int(os.environ.get("PGSD_DENSE_VARIANT", "0"))
 
+# rows with more stored entries than this are aggregated by the hub-row kernel in slices
+HUB_ROW_THRESHOLD = int(os.environ.get("PGSD_HUB_ROW_THRESHOLD", "4096"))
+HUB_ROW_CHUNK = 1024
+
 # counts kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 
@@ -87,6 +91,10 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
     if op_scale is not None:
         for k, sc in enumerate(op_scale):
             a.op_scale[k] = float(sc)
+    hubs = plan.hub_rows()
+    if hubs is not None and dt == _lib.PGSD_F32:
+        a.long_rows, a.long_chunk_ptr = hubs[0].data_ptr(), hubs[1].data_ptr()
+        a.n_long_rows, a.long_row_threshold, a.long_chunk = hubs[0].numel(), HUB_ROW_THRESHOLD, HUB_ROW_CHUNK
     outs = []
     keep = []
     for k, op in enumerate(ops):

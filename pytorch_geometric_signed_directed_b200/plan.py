@@ -49,6 +49,25 @@ class CSRPlan:
     def device(self):
         return self.row_ptr.device
 
+    def hub_rows(self):
+        """(hub row ids int32, exclusive prefix of their 1024-entry slices int32) or None.
+        Computed once per plan (one device->host sync) and cached."""
+        cached = getattr(self, "_hubs", 0)
+        if cached != 0:
+            return cached
+        from . import ops
+        res = None
+        if self.nnz > ops.HUB_ROW_THRESHOLD and self.row_ptr.is_cuda:
+            lens = self.row_ptr[1:] - self.row_ptr[:-1]
+            if int(lens.max().item()) > ops.HUB_ROW_THRESHOLD:
+                rows = torch.nonzero(lens > ops.HUB_ROW_THRESHOLD).view(-1)
+                slices = (lens[rows].long() + ops.HUB_ROW_CHUNK - 1) // ops.HUB_ROW_CHUNK
+                ptr = torch.zeros(rows.numel() + 1, dtype=torch.int32, device=self.row_ptr.device)
+                ptr[1:] = torch.cumsum(slices, 0).int()
+                res = (rows.int().contiguous(), ptr)
+        self._hubs = res
+        return res
+
     def bytes(self) -> int:
         tot = self.row_ptr.numel() * 4 + self.nnz * 4
         tot += sum(self.nnz * 4 for v in self.val if v is not None)

@@ -485,3 +485,35 @@ def test_group_per_row_kernel_matches_row_kernel(f, dtype, n_ops):
             got = ops.spmm(p, xs, ops_ids, variant=variant, **kw)
             for a, b in zip(got, ref):
                 assert_close_rel(a.float(), b.float(), tol, f"variant {variant:#x} {list(kw)}")
+
+
+def test_hub_rows_power_law_graph():
+    """Rows far above PGSD_HUB_ROW_THRESHOLD (4096): their entries are aggregated in slices by the
+    hub-row kernel (fp32 atomics); everything else is unchanged."""
+    g = torch.Generator().manual_seed(21)
+    n = 60_000
+    ei = torch.randint(0, n, (2, 200_000), generator=g)
+    ei[1, :50_000] = 7                  # 50k edges into node 7  (=> ~100k stored entries after symmetrisation)
+    ei[0, 50_000:62_000] = 9            # 12k edges out of node 9
+    ew = torch.rand(ei.size(1), generator=g) + 0.5
+    xr, xi = torch.rand(n, 64, generator=g) * 2 - 1, torch.rand(n, 64, generator=g) * 2 - 1
+    conv = nn.MagNetConv(64, 32, K=2, q=0.15, trainable_q=False, cached=True).to(DEV)
+    with torch.no_grad():
+        out_r, out_i = conv(xr.to(DEV), xi.to(DEV), ei.to(DEV), ew.to(DEV))
+    hubs = conv._plan.hub_rows()
+    assert hubs is not None and set(hubs[0].tolist()) >= {7, 9}
+    o_r, o_i = port.magnet_conv(xr, xi, ei, ew, conv.weight.detach().cpu(), conv.bias.detach().cpu(), 0.15, "sym")
+    assert_close_rel(out_r, o_r, 1e-5, "hub graph out_real")
+    assert_close_rel(out_i, o_i, 1e-5, "hub graph out_imag")
+    # both main kernels + mean epilogue with a hub, against the scalar evaluation
+    pos = ei[:, :120_000]
+    c1 = nn.SGCNConv(64, 16, first_aggr=True).to(DEV)
+    with torch.no_grad():
+        z = c1(xr.to(DEV), pos.to(DEV), ei[:, 120_000:].to(DEV))
+    ref = port.sgcn_conv(xr, pos, ei[:, 120_000:], c1.lin_b.weight.detach().cpu(), c1.lin_b.bias.detach().cpu(),
+                         c1.lin_u.weight.detach().cpu(), c1.lin_u.bias.detach().cpu(), True)
+    assert_close_rel(z, ref, 1e-5, "hub graph sgcn")
+    p = conv._plan
+    a = ops.spmm(p, [xr.to(DEV), xi.to(DEV)], (0, 1), variant=0)
+    b = ops.spmm(p, [xr.to(DEV), xi.to(DEV)], (0, 1), variant=0x80)
+    assert_close_rel(a[0], b[0], 1e-5, "group vs row kernel with hubs")
