@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
     tools/dist_check.py > gpurun_out/dist_check_n$N.log 2>&1
 grep -E "DIST_CHECK|FAIL|Error|error" gpurun_out/dist_check_n$N.log | head
-for mode in ring nccl; do
+for mode in ${MODES:-ring nccl}; do
   PGSD_EXCHANGE=$([ $mode = nccl ] && echo nccl || echo pull) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
       --master-port 29534 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n${N}_$mode.json 2> gpurun_out/bench_n${N}_$mode.err
   python - <<PY
