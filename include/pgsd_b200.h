@@ -90,6 +90,15 @@ PGSD_API int pgsd_build_csr_rw_norm(const int64_t* edge_dst, const int64_t* edge
                            int32_t* col, float* val, float* diag, int64_t* nnz_host,
                            void* workspace, size_t workspace_bytes, pgsd_stream_t stream);
 
+/* Symmetrically normalised plan with "remaining" self loops (PyG gcn_norm as called by
+ * nn/directed/DGCNConv.py:75-77): deg = rowsum_dst(A_hat), w' = deg^-1/2[src] * w * deg^-1/2[dst],
+ * diag = loop weight / deg.  Same conventions as pgsd_build_csr_rw_norm. */
+PGSD_API int pgsd_build_csr_sym_norm(const int64_t* edge_dst, const int64_t* edge_src,
+                            const float* edge_weight, int64_t num_edges, int64_t num_nodes,
+                            float fill_value, int add_self_loops, int32_t* row_ptr,
+                            int32_t* col, float* val, float* diag, int64_t* nnz_host,
+                            void* workspace, size_t workspace_bytes, pgsd_stream_t stream);
+
 /* Magnetic (Hermitian) Laplacian plan, scaled for the Chebyshev recurrence:
  *   L~ = 2 L / lambda_max - I,  L = I - D^-1/2 A_s D^-1/2 (.) exp(i 2 pi q Theta)   ('sym')
  *                               L = D - A_s (.) exp(i 2 pi q Theta)                (none)

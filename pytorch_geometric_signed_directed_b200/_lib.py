@@ -65,6 +65,8 @@ _PROTOTYPES = {
                                  C.c_size_t, _vp]),
     "pgsd_build_csr_rw_norm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp, _vp, _vp,
                                          _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
+    "pgsd_build_csr_sym_norm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp, _vp, _vp,
+                                          _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
     "pgsd_build_magnetic_laplacian": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_double, C.c_int,
                                                 _f32, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                                 C.POINTER(_i64), _vp, C.c_size_t, _vp]),

@@ -241,6 +241,41 @@ __global__ void k_rw_scale(const int32_t* __restrict__ row_ptr, const int32_t* _
   }
 }
 
+// gcn_norm (PyG; used by nn/directed/DGCNConv.py:75): deg = rowsum over the DESTINATION of
+// A_hat, dis = deg^-1/2 (inf -> 0), w' = dis[src] * w * dis[dst].  Pass 1 leaves dis in `diag`.
+__global__ void k_sym_deg(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ loop_pos,
+                          const float* __restrict__ weight, float fill, int64_t N, const float* __restrict__ val,
+                          float* __restrict__ dis) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < N;
+       r += (int64_t(gridDim.x) * blockDim.x) >> 5) {
+    float acc = 0.f;
+    for (int k = row_ptr[r] + lane; k < row_ptr[r + 1]; k += 32) acc += val[k];
+    acc = warp_sum(acc);
+    const int lp = loop_pos ? loop_pos[r] : -1;
+    const float lw = loop_pos ? (lp >= 0 ? (weight ? weight[lp] : 1.f) : fill) : 0.f;
+    if (lane == 0) dis[r] = inv_sqrt_or_zero(acc + lw);
+  }
+}
+__global__ void k_sym_scale(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                            const float* __restrict__ dis, int64_t N, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < N;
+       r += (int64_t(gridDim.x) * blockDim.x) >> 5) {
+    const float dr = dis[r];
+    for (int k = row_ptr[r] + lane; k < row_ptr[r + 1]; k += 32) val[k] = (dis[col[k]] * val[k]) * dr;
+  }
+}
+__global__ void k_sym_diag(const int32_t* __restrict__ loop_pos, const float* __restrict__ weight, float fill,
+                           int64_t N, float* __restrict__ diag) {
+  GRID_STRIDE(r, N) {
+    const int lp = loop_pos ? loop_pos[r] : -1;
+    const float lw = loop_pos ? (lp >= 0 ? (weight ? weight[lp] : 1.f) : fill) : 0.f;
+    const float d = diag[r];            // dis[r] from k_sym_deg
+    diag[r] = (d * lw) * d;
+  }
+}
+
 // ---------------------------------------------------------------------------- workspace plan
 struct Carver {
   char* base;
@@ -432,6 +467,37 @@ extern "C" int pgsd_build_csr_rw_norm(const int64_t* edge_dst, const int64_t* ed
                                                            edge_weight, add_self_loops ? fill_value : 0.f,
                                                            num_nodes, val, diag);
     PGSD_LAUNCH_CHECK("k_rw_scale");
+  }
+  return PGSD_OK;
+}
+
+extern "C" int pgsd_build_csr_sym_norm(const int64_t* edge_dst, const int64_t* edge_src,
+                                      const float* edge_weight, int64_t num_edges, int64_t num_nodes,
+                                      float fill_value, int add_self_loops, int32_t* row_ptr, int32_t* col,
+                                      float* val, float* diag, int64_t* nnz_host, void* workspace,
+                                      size_t workspace_bytes, pgsd_stream_t stream) {
+  int rc = check_sizes(num_nodes, num_edges);
+  if (rc != PGSD_OK) return rc;
+  PGSD_REQUIRE(row_ptr && diag && nnz_host && (num_edges == 0 || (edge_src && edge_dst && col && val)),
+               "build_csr_sym_norm: null pointer");
+  PGSD_REQUIRE(workspace != nullptr, "build_csr_sym_norm: null workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DstSpace s = carve_dst(workspace, num_edges, num_nodes);
+  if (s.total > workspace_bytes)
+    return fail(PGSD_ERR_WORKSPACE, "build_csr_sym_norm: workspace %zu < %zu", workspace_bytes, s.total);
+  Counters hc{};
+  rc = build_dst_sorted(edge_dst, edge_src, edge_weight, num_edges, num_nodes, num_nodes,
+                        add_self_loops ? 1 : 0, s, row_ptr, col, val, &hc, st);
+  if (rc != PGSD_OK) return rc;
+  *nnz_host = hc.nnz;
+  if (num_nodes > 0) {
+    const int32_t* lp = add_self_loops ? s.loop_pos : nullptr;
+    k_sym_deg<<<blocks_for(num_nodes * 32), TPB, 0, st>>>(row_ptr, lp, edge_weight, fill_value, num_nodes, val, diag);
+    PGSD_LAUNCH_CHECK("k_sym_deg");
+    k_sym_scale<<<blocks_for(num_nodes * 32), TPB, 0, st>>>(row_ptr, col, diag, num_nodes, val);
+    PGSD_LAUNCH_CHECK("k_sym_scale");
+    k_sym_diag<<<blocks_for(num_nodes), TPB, 0, st>>>(lp, edge_weight, fill_value, num_nodes, diag);
+    PGSD_LAUNCH_CHECK("k_sym_diag");
   }
   return PGSD_OK;
 }

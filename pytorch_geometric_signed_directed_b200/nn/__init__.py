@@ -7,6 +7,7 @@ from .sgcn_conv import SGCNConv
 from .snea_conv import SNEAConv
 from .mixed_path import Conv_Base, DIMPA
 from .complex_relu import complex_relu_layer
+from .dgcn_simpa import DGCNConv, SIMPA
 
 __all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv", "SNEAConv",
-           "Conv_Base", "DIMPA", "complex_relu_layer"]
+           "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA"]

@@ -152,6 +152,28 @@ def build_rw_norm(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, fil
     return CSRPlan(n, n, k, e, row_ptr, col[:k], [val[:k]], [diag[:n]], [0.0])
 
 
+def build_sym_norm(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, fill_value: float,
+                   add_self_loops: bool = True) -> CSRPlan:
+    """gcn_norm + source_to_target aggregation plan (`pgsd_build_csr_sym_norm`): dst = edge_index[1]."""
+    ei, ew = _prep_edges(edge_index, edge_weight)
+    dev, e = ei.device, ei.size(1)
+    with torch.cuda.device(dev):
+        row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        val = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
+        diag = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        ws = _workspace(n, e, dev)
+        nnz = C.c_int64(0)
+        lib = _lib.load()
+        _lib.check(lib.pgsd_build_csr_sym_norm(ei[1].data_ptr(), ei[0].data_ptr(), _ptr(ew), e, n,
+                                               float(fill_value), int(add_self_loops), row_ptr.data_ptr(),
+                                               col.data_ptr(), val.data_ptr(), diag.data_ptr(), C.byref(nnz),
+                                               ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
+                   "pgsd_build_csr_sym_norm")
+    k = nnz.value
+    return CSRPlan(n, n, k, e, row_ptr, col[:k], [val[:k]], [diag[:n]], [0.0])
+
+
 def build_magnetic(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, q: float,
                    normalization: Optional[str], lambda_max: float,
                    signed_mode: int = 0) -> CSRPlan:

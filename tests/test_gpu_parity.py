@@ -517,3 +517,33 @@ def test_hub_rows_power_law_graph():
     a = ops.spmm(p, [xr.to(DEV), xi.to(DEV)], (0, 1), variant=0)
     b = ops.spmm(p, [xr.to(DEV), xi.to(DEV)], (0, 1), variant=0x80)
     assert_close_rel(a[0], b[0], 1e-5, "group vs row kernel with hubs")
+
+
+def test_dgcn_and_simpa_golden():
+    g = load_golden("dgcn_conv", DEV)
+    conv = nn.DGCNConv(cached=True)
+    y = conv(g["x"], g["edge_index"], g["edge_weight"])
+    assert_close_rel(y, g["out"], 1e-5)
+    # cache quirk Q6: a cached layer ignores whatever graph comes next
+    assert torch.equal(conv(g["x"], g["edge_index"][:, :50], None), y)
+    assert_close_rel(nn.DGCNConv(improved=True)(g["x"], g["edge_index"], None), g["out_improved_unweighted"], 1e-5)
+    g = load_golden("simpa", DEV)
+    args = (g["edge_index_p"], g["edge_weight_p"], g["edge_index_n"], g["edge_weight_n"], g["x_p"], g["x_n"])
+    und = nn.SIMPA(hop=2, fill_value=0.5, directed=False).to(DEV)
+    with torch.no_grad():
+        und._w_p.copy_(g["w_p"]); und._w_n.copy_(g["w_n"])
+        assert_close_rel(und(*args), g["out_undirected"], 1e-5)
+    dr = nn.SIMPA(hop=2, fill_value=0.5, directed=True).to(DEV)
+    with torch.no_grad():
+        for nm in ("w_sp", "w_sn", "w_tp", "w_tn"):
+            getattr(dr, "_" + nm).copy_(g[nm])
+        assert_close_rel(dr(*args, g["x_pt"], g["x_nt"]), g["out_directed"], 1e-5)
+    # and with autograd enabled (differentiable path, torch.cat of the parts)
+    und2 = nn.SIMPA(hop=2, fill_value=0.5).to(DEV)
+    with torch.no_grad():
+        und2._w_p.copy_(g["w_p"]); und2._w_n.copy_(g["w_n"])
+    out = und2(*args)
+    assert out.requires_grad
+    assert_close_rel(out, g["out_undirected"], 1e-5)
+    out.sum().backward()
+    assert und2._w_p.grad is not None and torch.isfinite(und2._w_p.grad).all()

@@ -123,3 +123,14 @@ def test_snea_port(name, first):
         h = torch.nn.functional.linear(g["x"], g["lin_b_weight"], g["lin_b_bias"])
         assert_close_rel(g["out"][:134, :6], h[:134], 1e-5)
         assert float(g["out"][134:].abs().max()) == 0.0
+
+
+def test_dgcn_and_simpa_port():
+    g = load_golden("dgcn_conv")
+    assert_close_rel(port.dgcn_conv(g["x"], g["edge_index"], g["edge_weight"]), g["out"], 1e-5)
+    assert_close_rel(port.dgcn_conv(g["x"], g["edge_index"], None, improved=True), g["out_improved_unweighted"], 1e-5)
+    g = load_golden("simpa")
+    args = (g["edge_index_p"], g["edge_weight_p"], g["edge_index_n"], g["edge_weight_n"], g["x_p"], g["x_n"])
+    assert_close_rel(port.simpa(*args, (g["w_p"], g["w_n"]), 2, 0.5), g["out_undirected"], 1e-5)
+    assert_close_rel(port.simpa(*args, (g["w_sp"], g["w_sn"], g["w_tp"], g["w_tn"]), 2, 0.5, g["x_pt"], g["x_nt"]),
+                     g["out_directed"], 1e-5)
