@@ -128,7 +128,8 @@ class SymmetricPullExchange:
         grp = group if group is not None else dist.group.WORLD
         self.send = [symm_mem.empty((rows_max, width), dtype=dtype, device=device) for _ in range(2)]
         self.hdl = [symm_mem.rendezvous(t, grp) for t in self.send]
-        self.copy_stream = torch.cuda.Stream(device=device)
+        # two copy streams: consecutive rounds overlap on different copy engines
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(int(os.environ.get("PGSD_COPY_STREAMS", "2")))]
         self.calls = 0
         self.width, self.dtype = width, dtype
 
@@ -147,14 +148,16 @@ class SymmetricPullExchange:
         ready = torch.cuda.Event()
         ready.record(cur)
         works = []
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(ready)
-            for s in range(1, self.world):
+        for cs in self.copy_streams:
+            cs.wait_event(ready)
+        for s in range(1, self.world):
+            cs = self.copy_streams[(s - 1) % len(self.copy_streams)]
+            with torch.cuda.stream(cs):
                 src = self.source_of_round(s)
                 peer = hdl.get_buffer(src, (recv[src].size(0), self.width), self.dtype)
                 recv[src].copy_(peer, non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
+                ev.record(cs)
                 works.append((src, [_EventWork(ev)]))
         return works
 
