@@ -359,6 +359,24 @@ def run_gpu_arm(args, rank, world):
                                        "copies double-buffered on side streams (serial_ms_per_step = same loop "
                                        "without overlap)"}
 
+    # ---- cold path: cached=False (the reference's constructor default) rebuilds the operator from the
+    # COO edge list inside every forward (symmetrise, 64-bit key sort, coalesce, degree, phase)
+    cold_ms = None
+    if world == 1:
+        conv_cold = nn.MagNetConv(FEAT, FEAT, K=1, q=0.25, trainable_q=False, cached=False).to(dev)
+        conv_cold.load_state_dict(conv.state_dict())
+        for _ in range(2):
+            conv_cold(x_real, x_imag, ei)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            conv_cold(x_real, x_imag, ei)
+        c1.record()
+        torch.cuda.synchronize()
+        cold_ms = c0.elapsed_time(c1) / 5
+        del conv_cold
+
     if rank != 0:
         return
 
@@ -401,6 +419,7 @@ def run_gpu_arm(args, rank, world):
         "data": "synthetic", "config": bench_config(world),
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "edges_total": e_input, "nnz_per_rank": nnz,
+        "cold_ms_per_step": cold_ms,   # cached=False: plan build + forward (reference: ~48 s on CPU)
     }
     emit_json(line)
 

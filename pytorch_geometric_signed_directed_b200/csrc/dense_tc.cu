@@ -54,10 +54,12 @@ struct Params {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Round-to-nearest (ties away) to TF32's 10-bit mantissa: add half a TF32 ulp to the magnitude
+// bits and clear the 13 low bits.  Same result as cvt.rna.tf32.f32, but 2 integer instructions:
+// ptxas expands the cvt into ~5 (FSETP/SEL/LOP3/VIADD/IMAD), and with 32 conversions per thread
+// per 16 KB chunk the split was half of the kernel's instruction count (profiles/README.md).
 __device__ __forceinline__ float to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
