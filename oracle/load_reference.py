@@ -77,4 +77,12 @@ def ref_classes():
     out["DGCNConv"] = load("nn.directed.DGCNConv").DGCNConv
     out["complex_relu_layer"] = load("nn.directed.complex_relu").complex_relu_layer
     out["SNEAConv"] = load("nn.signed.SNEAConv").SNEAConv
+    # SDGNN.py imports losses / feature builders from utils.signed (sklearn, scipy pipelines that the
+    # SDRLayer itself never touches): give the empty package module placeholder attributes
+    us = sys.modules[_PKG + ".utils.signed"]
+    for name in ("create_spectral_features", "Sign_Product_Entropy_Loss", "Sign_Direction_Loss",
+                 "Sign_Triangle_Loss"):
+        if not hasattr(us, name):
+            setattr(us, name, None)
+    out["SDRLayer"] = load("nn.signed.SDGNN").SDRLayer
     return out

@@ -256,6 +256,47 @@ class MessagePassing(torch.nn.Module):
         return self.update(out, **uargs)
 
 
+class GATConv(MessagePassing):
+    """PyG GATConv restated for heads >= 1, concat=True, no edge features, dropout 0:
+    h = lin(x) [N, H, C]; e_ij = leaky_relu(<h_j, att_src> + <h_i, att_dst>, slope);
+    alpha = softmax over the incoming edges of i (self-loops removed, then one added per node);
+    out_i = sum_j alpha_ij h_j, heads concatenated, + bias.  Parameter names follow PyG >= 2.3
+    (`lin`, `att_src`, `att_dst`, `bias`)."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
+                 add_self_loops=True, bias=True, **kwargs):
+        kwargs.setdefault('aggr', 'add')
+        super().__init__(node_dim=0, **kwargs)
+        assert concat and dropout == 0.0
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.negative_slope, self.add_self_loops = negative_slope, add_self_loops
+        self.lin = Linear(in_channels, heads * out_channels, bias=False)
+        self.att_src = torch.nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = torch.nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(heads * out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot(self.lin.weight)
+        glorot(self.att_src)
+        glorot(self.att_dst)
+        zeros(self.bias)
+
+    def forward(self, x, edge_index):
+        H, C = self.heads, self.out_channels
+        h = self.lin(x).view(-1, H, C)
+        a_src = (h * self.att_src).sum(-1)
+        a_dst = (h * self.att_dst).sum(-1)
+        if self.add_self_loops:
+            edge_index, _ = remove_self_loops(edge_index)
+            edge_index, _ = add_self_loops(edge_index, num_nodes=x.size(0))
+        j, i = edge_index[0], edge_index[1]
+        e = torch.nn.functional.leaky_relu(a_src[j] + a_dst[i], self.negative_slope)
+        alpha = softmax(e, i, num_nodes=x.size(0))
+        out = scatter(h[j] * alpha.unsqueeze(-1), i, 0, x.size(0), 'sum').view(-1, H * C)
+        return out if self.bias is None else out + self.bias
+
+
 # --------------------------------------------------------------------------- install
 
 def install(force: bool = False) -> bool:
@@ -301,6 +342,8 @@ def install(force: bool = False) -> bool:
     num_nodes.maybe_num_nodes = maybe_num_nodes
     conv.MessagePassing = MessagePassing
     nn_.MessagePassing = MessagePassing
+    conv.GATConv = GATConv
+    nn_.GATConv = GATConv
     gcn_conv.gcn_norm = gcn_norm
     inits.glorot, inits.zeros = glorot, zeros
     linear.Linear = Linear

@@ -8,6 +8,7 @@ from .snea_conv import SNEAConv
 from .mixed_path import Conv_Base, DIMPA
 from .complex_relu import complex_relu_layer
 from .dgcn_simpa import DGCNConv, SIMPA
+from .sdr_layer import GATConv, SDRLayer
 
 __all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv", "SNEAConv",
-           "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA"]
+           "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA", "GATConv", "SDRLayer"]

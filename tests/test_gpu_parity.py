@@ -547,3 +547,24 @@ def test_dgcn_and_simpa_golden():
     assert_close_rel(out, g["out_undirected"], 1e-5)
     out.sum().backward()
     assert und2._w_p.grad is not None and torch.isfinite(und2._w_p.grad).all()
+
+
+def test_sdr_layer_golden_and_wide():
+    g = load_golden("sdr_layer", DEV)
+    lists = [g[f"edges_{i}"] for i in range(4)]
+    layer = nn.SDRLayer(12, 12, lists).to(DEV)
+    layer.load_state_dict({k.replace("__", "."): v for k, v in g.items()
+                           if k not in ("x", "out") and not k.startswith("edges_")})
+    assert_close_rel(layer(g["x"]), g["out"], 1e-5)
+    # a GATConv on its own against the oracle at a width the vector kernels take
+    gen = torch.Generator().manual_seed(12)
+    n = 4000
+    ei = torch.randint(0, n, (2, 60_000), generator=gen)
+    x = torch.randn(n, 64, generator=gen)
+    conv = nn.GATConv(64, 64).to(DEV)
+    with torch.no_grad():
+        conv.bias.uniform_(-0.2, 0.2)
+    y = conv(x.to(DEV), ei.to(DEV))
+    ref = port.gat_conv(x, ei, conv.lin.weight.detach().cpu(), conv.att_src.detach().cpu(),
+                        conv.att_dst.detach().cpu(), conv.bias.detach().cpu())
+    assert_close_rel(y, ref, 1e-5)

@@ -134,3 +134,17 @@ def test_dgcn_and_simpa_port():
     assert_close_rel(port.simpa(*args, (g["w_p"], g["w_n"]), 2, 0.5), g["out_undirected"], 1e-5)
     assert_close_rel(port.simpa(*args, (g["w_sp"], g["w_sn"], g["w_tp"], g["w_tn"]), 2, 0.5, g["x_pt"], g["x_nt"]),
                      g["out_directed"], 1e-5)
+
+
+def _sdr_params(g):
+    gat = [(g[f"agg_{i}__lin__weight"], g[f"agg_{i}__att_src"], g[f"agg_{i}__att_dst"], g[f"agg_{i}__bias"])
+           for i in range(4)]
+    return [g[f"edges_{i}"] for i in range(4)], gat
+
+
+def test_sdr_layer_port():
+    g = load_golden("sdr_layer")
+    lists, gat = _sdr_params(g)
+    y = port.sdr_layer(g["x"], lists, gat, g["mlp_layer__0__weight"], g["mlp_layer__0__bias"],
+                       g["mlp_layer__2__weight"], g["mlp_layer__2__bias"])
+    assert_close_rel(y, g["out"], 1e-5)
