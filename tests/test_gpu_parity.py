@@ -568,3 +568,24 @@ def test_sdr_layer_golden_and_wide():
     ref = port.gat_conv(x, ei, conv.lin.weight.detach().cpu(), conv.att_src.detach().cpu(),
                         conv.att_dst.detach().cpu(), conv.bias.detach().cpu())
     assert_close_rel(y, ref, 1e-5)
+
+
+def test_magnet_bf16_features():
+    """bf16 storage, fp32 accumulation everywhere (aggregation and tcgen05 kind::f16 transform):
+    compared with the fp32 oracle on the bf16-rounded inputs at 2e-2 * max|ref| (three bf16
+    roundings on the path: T, out, and the inputs' own 2^-9)."""
+    g = torch.Generator().manual_seed(31)
+    n, e, f = 4000, 80_000, 64
+    ei = torch.randint(0, n, (2, e), generator=g)
+    xr = (torch.rand(n, f, generator=g) * 2 - 1).bfloat16()
+    xi = (torch.rand(n, f, generator=g) * 2 - 1).bfloat16()
+    conv = nn.MagNetConv(f, f, K=2, q=0.25, trainable_q=False).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+        conv.bias.uniform_(-0.3, 0.3)
+        out_r, out_i = conv(xr.to(DEV), xi.to(DEV), ei.to(DEV))
+    assert out_r.dtype == torch.bfloat16
+    o_r, o_i = port.magnet_conv(xr.float(), xi.float(), ei, None, conv.weight.detach().cpu(),
+                                conv.bias.detach().cpu(), 0.25, "sym")
+    assert_close_rel(out_r.float(), o_r, 2e-2, "bf16 out_real")
+    assert_close_rel(out_i.float(), o_i, 2e-2, "bf16 out_imag")
