@@ -43,6 +43,7 @@ struct SpmmParams {
   float alpha_op[2];   // alpha * op_scale[k]
   int use_groups;      // host-side switch: group-per-row kernel for short rows
   int long_thr;        // rows longer than this are aggregated by spmm_long_rows_kernel (0 = off)
+  int keep_policy;     // L2 policy of the feature gathers: 0 evict_last (default), 1 normal, 2 evict_first
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
   const int l = lane % LPR;
   const bool lane_active = l < p.lpr_active;
   const int64_t lane_off = int64_t(l) * (W * 4);  // byte offset inside a feature row
-  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_keep = p.keep_policy == 1 ? policy_evict_normal() : (p.keep_policy == 2 ? policy_evict_first() : policy_evict_last());
   const uint64_t pol_stream = policy_evict_first();
 
   const int64_t warps_total = int64_t(gridDim.x) * (THREADS / 32);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
   const int l = lane % LPR;
   const bool lane_active = l < p.lpr_active;
   const int64_t lane_off = int64_t(l) * (W * 4);
-  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_keep = p.keep_policy == 1 ? policy_evict_normal() : (p.keep_policy == 2 ? policy_evict_first() : policy_evict_last());
   const uint64_t pol_stream = policy_evict_first();
 
   const int64_t groups_total = int64_t(gridDim.x) * (THREADS / 32) * G;
@@ -656,6 +657,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   // group-per-row kernel unless the warp-per-row kernel is requested (bit 7); measured faster at
   // every row length tried (2.91 vs 3.18 ms at 40 entries/row, 2-3x at 5 entries/row)
   p.use_groups = (a->variant & 0x80) == 0;
+  p.keep_policy = (a->variant >> 8) & 3;   // experiment knob (bits 8-9), 128-bit gather path only
   const bool can256 = vec32 && row_bytes <= 32 * 32;
   const bool can128 = vec16 && row_bytes <= 32 * 16;
   int W = 0;

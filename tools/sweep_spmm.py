@@ -55,6 +55,9 @@ yr, yi = torch.empty_like(xr), torch.empty_like(xi)
 for variant in (0x80 | 0x10 | 4, 0x80 | 0x20 | 2, 0x10 | 2, 0x10 | 4, 0x20 | 2, 0x20 | 4):
     ms = timeit(lambda: ops.spmm(p, [xr, xi], (0, 1), out=[yr, yi], variant=variant))
     emit(what="spmm2", variant=hex(variant), ms=ms, gbs=b_alg / ms / 1e6, nnz=nnz)
+for variant in (0x100 | 0x10 | 4, 0x200 | 0x10 | 4):
+    ms = timeit(lambda: ops.spmm(p, [xr, xi], (0, 1), out=[yr, yi], variant=variant))
+    emit(what="spmm2_l2policy", variant=hex(variant), policy={1: "evict_normal", 2: "evict_first"}[variant >> 8], ms=ms, gbs=b_alg / ms / 1e6)
 b1 = nnz * (8 + F * 4) + (N + 1) * 4 + N * F * 4
 for variant in (0x80 | 0x20 | 2, 0x80 | 0x20 | 4, 0x10 | 4, 0x20 | 2, 0x20 | 4):
     ms = timeit(lambda: ops.spmm(p, [xr], (0,), out=[yr], variant=variant))
