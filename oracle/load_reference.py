@@ -85,4 +85,5 @@ def ref_classes():
         if not hasattr(us, name):
             setattr(us, name, None)
     out["SDRLayer"] = load("nn.signed.SDGNN").SDRLayer
+    out["MagNet_node_classification"] = load("nn.directed.MagNet_node_classification").MagNet_node_classification
     return out

@@ -9,6 +9,8 @@ from .mixed_path import Conv_Base, DIMPA
 from .complex_relu import complex_relu_layer
 from .dgcn_simpa import DGCNConv, SIMPA
 from .sdr_layer import GATConv, SDRLayer
+from .magnet_model import MagNet_node_classification
 
 __all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv", "SNEAConv",
-           "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA", "GATConv", "SDRLayer"]
+           "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA", "GATConv", "SDRLayer",
+           "MagNet_node_classification"]

@@ -589,3 +589,23 @@ def test_magnet_bf16_features():
                                 conv.bias.detach().cpu(), 0.25, "sym")
     assert_close_rel(out_r.float(), o_r, 2e-2, "bf16 out_real")
     assert_close_rel(out_i.float(), o_i, 2e-2, "bf16 out_imag")
+
+
+def test_magnet_node_classification_model_golden():
+    g = load_golden("magnet_model", DEV)
+    model = nn.MagNet_node_classification(9, hidden=16, q=0.2, K=2, label_dim=5, activation=True, layer=3,
+                                          dropout=0.5, cached=True).to(DEV).eval()
+    model.load_state_dict({k.replace("__", "."): v for k, v in g.items()
+                           if k not in ("x", "out", "edge_index", "edge_weight")})
+    with torch.no_grad():
+        y = model(g["x"], g["x"], g["edge_index"], g["edge_weight"])
+        y2 = model(g["x"], g["x"], g["edge_index"], g["edge_weight"])       # cached branch
+    assert_close_rel(y, g["out"], 1e-5)
+    assert torch.equal(y, y2)
+    assert model.Chebs[1]._plan is model.Chebs[0]._plan                      # one operator for the stack
+    # training mode: gradients reach every layer through the shared plan and the fused ReLU
+    model.train()
+    out = model(g["x"], g["x"], g["edge_index"], g["edge_weight"])
+    F_loss = torch.nn.functional.nll_loss(out, torch.randint(0, 5, (out.size(0),), device=DEV))
+    F_loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())

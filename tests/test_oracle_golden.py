@@ -148,3 +148,11 @@ def test_sdr_layer_port():
     y = port.sdr_layer(g["x"], lists, gat, g["mlp_layer__0__weight"], g["mlp_layer__0__bias"],
                        g["mlp_layer__2__weight"], g["mlp_layer__2__bias"])
     assert_close_rel(y, g["out"], 1e-5)
+
+
+def test_magnet_model_port():
+    g = load_golden("magnet_model")
+    chebs = [(g[f"Chebs__{i}__weight"], g[f"Chebs__{i}__bias"]) for i in range(3)]
+    y = port.magnet_node_classification(g["x"], g["x"], g["edge_index"], g["edge_weight"], chebs,
+                                        g["Conv__weight"], g["Conv__bias"], 0.2)
+    assert_close_rel(y, g["out"], 1e-5)

@@ -71,6 +71,23 @@ with torch.no_grad():
     del pos, neg, x, z1
     torch.cuda.empty_cache()
 
+    # ---- C2 as a whole model: MagNet_node_classification, 2 layers, 1M nodes / 20M edges / 64 hidden
+    n, f, lab = 1_000_000, 64, 10
+    ei, _ = synthetic.dsbm_edges(n, 3, num_edges=20_000_000, seed=0, device=dev)
+    x = torch.rand(n, f, device=dev) * 2 - 1
+    model = nn.MagNet_node_classification(f, hidden=f, q=0.25, K=1, label_dim=lab, activation=True, layer=2,
+                                          cached=True).to(dev).eval()
+    model(x, x, ei)
+    p0 = model.Chebs[0]._plan
+    nnz = int(p0.nnz)
+    layer = nnz * (4 + 8 + 2 * f * 4) + (n + 1) * 4 + 4 * n * f * 4      # SURVEY 8d per layer, as bench.py
+    b = 2 * layer + n * 2 * f * 4 + n * lab * 4 * 3
+    ms = timeit(lambda: model(x, x, ei))
+    emit(config="C2 MagNet_node_classification 2 layers 1M/20M/64 fp32 (inference)", ms=ms,
+         edges_per_s=2 * ei.size(1) / ms * 1e3, alg_gb=b / 1e9, alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK)
+    del model, x, ei, p0
+    torch.cuda.empty_cache()
+
     # ---- DIMPA hop=2 on 1M nodes / 20M edges / 64
     n = 1_000_000
     ei, _ = synthetic.dsbm_edges(n, 3, num_edges=20_000_000, seed=0, device=dev)
@@ -82,3 +99,24 @@ with torch.no_grad():
     b = 4 * (ei.size(1) * (8 + 256) + (n + 1) * 4 + n * 256 * 2) + 4 * n * 256 * 3
     emit(config="DIMPA hop=2 1M/20M/64 fp32", ms=ms, edges_per_s=4 * ei.size(1) / ms * 1e3, alg_gb=b / 1e9,
          alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK)
+
+# ---- C2 training step (forward + nll loss + backward through the same kernels), same model
+n, f, lab = 1_000_000, 64, 10
+ei, _ = synthetic.dsbm_edges(n, 3, num_edges=20_000_000, seed=0, device=dev)
+x = torch.rand(n, f, device=dev) * 2 - 1
+yl = torch.randint(0, lab, (n,), device=dev)
+model = nn.MagNet_node_classification(f, hidden=f, q=0.25, K=1, label_dim=lab, activation=True, layer=2,
+                                      cached=True).to(dev).train()
+opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+
+def train_step():
+    opt.zero_grad(set_to_none=True)
+    loss = torch.nn.functional.nll_loss(model(x, x, ei), yl)
+    loss.backward()
+    opt.step()
+
+
+ms = timeit(train_step)
+emit(config="C2 MagNet_node_classification 2 layers 1M/20M/64 fp32 (training step, Adam)", ms=ms,
+     edges_per_s=2 * ei.size(1) / ms * 1e3)
