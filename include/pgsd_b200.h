@@ -122,6 +122,18 @@ PGSD_API int pgsd_build_magnetic_laplacian(const int64_t* edge_row, const int64_
                                   void* workspace, size_t workspace_bytes,
                                   pgsd_stream_t stream);
 
+/* Same plan, additionally keeping theta[u] = the coalesced antisymmetric weight Theta of every
+ * stored entry (plan orientation: val_real = -m cos(2 pi q theta), val_imag = m sin(2 pi q theta)),
+ * which pgsd_magnetic_q_grad needs when q is trainable (MagNetConv.py:58-59,141-142). */
+PGSD_API int pgsd_build_magnetic_laplacian_theta(const int64_t* edge_row, const int64_t* edge_col,
+                                  const float* edge_weight, int64_t num_edges,
+                                  int64_t num_nodes, double q, int normalization,
+                                  float lambda_max, int signed_mode,
+                                  int32_t* row_ptr, int32_t* col, float* val_real,
+                                  float* val_imag, float* diag_real, float* theta,
+                                  int64_t* nnz_host, void* workspace, size_t workspace_bytes,
+                                  pgsd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Sparse aggregation (the hot loop): for every destination row r and operator k < n_ops
  *   agg_k[r] = diag_k[r] * x_k[r] + sum_{e in row r} val_k[e] * x_k[col[e]]
@@ -257,6 +269,20 @@ PGSD_API int pgsd_edge_softmax(const pgsd_attn_args* args, pgsd_stream_t stream)
 PGSD_API int pgsd_xtg_accumulate(const void* x, int64_t ldx, const void* g, int64_t ldg, int64_t n_rows,
                                  int32_t k, int32_t n, int32_t dtype, float* dw, int64_t lddw, float* db,
                                  pgsd_stream_t stream);
+
+/* Gradient of the loss w.r.t. a trainable magnetic charge q through ONE aggregation
+ *   y_real = alpha * L~_r^T x_real,  y_imag = alpha * L~_i^T x_imag   (pgsd_spmm_csr, n_ops = 2):
+ *   *dq += scale * sum_e theta[e] * ( val_imag[e] * <gy_real[row(e)], x_real[col[e]]>
+ *                                   - val_real[e] * <gy_imag[row(e)], x_imag[col[e]]> ),
+ * scale = 2 pi alpha  (d val_real/dq = 2 pi theta val_imag, d val_imag/dq = -2 pi theta val_real).
+ * A sampled dense-dense product (SDDMM) reduced to a scalar; fp32 features, double accumulator the
+ * caller zero-initialises.  Replaces autograd through torch.exp(1j*2*pi*q*theta)
+ * (utils/directed/get_magnetic_Laplacian.py:68) + the four propagates of MagNetConv.py:196-236. */
+PGSD_API int pgsd_magnetic_q_grad(const int32_t* row_ptr, const int32_t* col, const float* val_real,
+                                  const float* val_imag, const float* theta, int64_t n_rows, int32_t feat,
+                                  const float* gy_real, int64_t ldgr, const float* gy_imag, int64_t ldgi,
+                                  const float* x_real, int64_t ldxr, const float* x_imag, int64_t ldxi,
+                                  double scale, double* dq, pgsd_stream_t stream);
 
 /* Halo pack for the node-range sharded path (no reference counterpart: the reference is
  * single-device): out[i, :] = x[index[i], :]  -- rows another rank asked for. */

@@ -11,7 +11,9 @@ expressed with the forward kernels themselves:
 M^T comes for free for the magnetic plans (real part symmetric, imaginary part antisymmetric:
 same plan, `op_scale = (1, -1)`); other plans get a transposed CSR built once and cached on the
 plan.  `spmm` / `dense` fall through to the raw kernels when no gradient is required, so the
-inference path is unchanged.  Not differentiated: edge weights and MagNetConv's trainable q.
+inference path is unchanged.  A trainable magnetic charge q (MagNetConv.py:58-59) gets its gradient
+from `pgsd_magnetic_q_grad` (d val/dq is a rotation of the stored values, so only an SDDMM reduced
+to a scalar is needed).  Not differentiated: edge weights.
 """
 from __future__ import annotations
 
@@ -59,13 +61,17 @@ def transposed(plan: CSRPlan) -> Tuple[CSRPlan, Tuple[float, float]]:
 
 class _SpmmFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, op_ids, mean, alpha, beta, n_x, has_z, has_bias, *tensors):
+    def forward(ctx, plan, op_ids, mean, alpha, beta, n_x, has_z, has_bias, q, *tensors):
         xs = list(tensors[:n_x])
         zs = list(tensors[n_x:2 * n_x]) if has_z else None
         bias = tensors[-1] if has_bias else None
         outs = ops.spmm(plan, xs, op_ids, mean=mean, alpha=alpha, beta=beta, zs=zs, bias=bias)
         ctx.plan, ctx.op_ids, ctx.mean, ctx.alpha, ctx.beta = plan, op_ids, mean, alpha, beta
         ctx.n_x, ctx.has_z, ctx.has_bias = n_x, has_z, has_bias
+        ctx.q_shape = None
+        if q is not None and q.requires_grad:
+            ctx.q_shape = (tuple(q.shape), q.dtype)
+            ctx.save_for_backward(*xs)
         return tuple(outs)
 
     @staticmethod
@@ -77,7 +83,11 @@ class _SpmmFn(torch.autograd.Function):
         if ctx.mean:
             inv = 1.0 / (plan.row_ptr[1:] - plan.row_ptr[:-1]).clamp(min=1).to(gys[0].dtype)
             gin = [g * inv.view(-1, 1) for g in gys]
-        need_x = any(ctx.needs_input_grad[8 + k] for k in range(ctx.n_x))
+        gq = None
+        if ctx.q_shape is not None and ctx.needs_input_grad[8]:
+            gq = ops.magnetic_q_grad(plan, gin, ctx.saved_tensors, ctx.alpha)
+            gq = gq.to(ctx.q_shape[1]).reshape(ctx.q_shape[0])
+        need_x = any(ctx.needs_input_grad[9 + k] for k in range(ctx.n_x))
         gxs = [None] * ctx.n_x
         if need_x:
             if len(op_ids) == 2:
@@ -93,19 +103,21 @@ class _SpmmFn(torch.autograd.Function):
             for g in gys[1:]:
                 gb = gb + g.float().sum(0)
             grads.append(gb)
-        return (None,) * 8 + tuple(grads)
+        return (None,) * 8 + (gq,) + tuple(grads)
 
 
 def spmm(plan: CSRPlan, xs: Sequence[Tensor], op_ids: Sequence[int] = (0,), *, mean: bool = False,
          alpha: float = 1.0, beta: float = 0.0, zs: Optional[Sequence[Tensor]] = None,
-         bias: Optional[Tensor] = None, out=None) -> List[Tensor]:
+         bias: Optional[Tensor] = None, out=None, q: Optional[Tensor] = None) -> List[Tensor]:
+    """`q`: the trainable magnetic charge the plan's values were computed from (plan built with
+    `keep_theta`); it then receives d loss / d q."""
     op_ids = tuple(op_ids)
     track = list(xs) + (list(zs) if zs is not None else []) + ([bias] if bias is not None else [])
-    if not _needs_grad(track):
+    if not _needs_grad(track + [q]):
         return ops.spmm(plan, xs, op_ids, mean=mean, alpha=alpha, beta=beta, zs=zs, bias=bias, out=out)
     tensors = list(xs) + (list(zs) if zs is not None else []) + ([bias] if bias is not None else [])
     outs = list(_SpmmFn.apply(plan, op_ids, mean, alpha, beta, len(xs), zs is not None,
-                              bias is not None, *tensors))
+                              bias is not None, q, *tensors))
     if out is not None:
         raise RuntimeError("spmm: preallocated outputs are not supported on the autograd path")
     return outs

@@ -111,3 +111,126 @@ extern "C" int pgsd_xtg_accumulate(const void* x, int64_t ldx, const void* g, in
   PGSD_LAUNCH_CHECK("xtg_kernel");
   return PGSD_OK;
 }
+
+// ---- dL/dq of a trainable magnetic charge (SDDMM reduced to a scalar) ------------------------
+// A group of LPR lanes owns a row: it keeps its slice of the two output-gradient rows in
+// registers and walks the row's entries, gathering the matching slices of x_real / x_imag.
+// No per-entry reduction is needed (the result is one scalar): every lane accumulates
+// theta * (val_i * g_r.x_r - val_r * g_i.x_i) for its slice, lanes are summed once at the end.
+namespace pgsd {
+
+template <int VEC>
+struct FVec;
+template <>
+struct FVec<4> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ float dot(const FVec& o) const {
+    return fmaf(v.x, o.v.x, fmaf(v.y, o.v.y, fmaf(v.z, o.v.z, v.w * o.v.w)));
+  }
+};
+template <>
+struct FVec<1> {
+  float v;
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+  __device__ __forceinline__ float dot(const FVec& o) const { return v * o.v; }
+};
+
+constexpr int QG_THREADS = 256;
+
+template <int VEC>
+__global__ void __launch_bounds__(QG_THREADS) magnetic_q_grad_kernel(
+    const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const float* __restrict__ vr,
+    const float* __restrict__ vi, const float* __restrict__ th, int64_t n_rows, int feat,
+    const float* __restrict__ gr, int64_t ldgr, const float* __restrict__ gi, int64_t ldgi,
+    const float* __restrict__ xr, int64_t ldxr, const float* __restrict__ xi, int64_t ldxi, int lpr,
+    double scale, double* __restrict__ dq) {
+  const int lane = threadIdx.x & 31, sub = lane & (lpr - 1), rows_per_warp = 32 / lpr;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float acc = 0.f;
+  for (int64_t r0 = warp * rows_per_warp; r0 < n_rows; r0 += n_warps * rows_per_warp) {
+    const int64_t r = r0 + lane / lpr;
+    if (r >= n_rows) continue;
+    const int beg = row_ptr[r], end = row_ptr[r + 1];
+    for (int c = sub * VEC; c < feat; c += lpr * VEC) {
+      FVec<VEC> g_r, g_i;
+      g_r.load(gr + r * ldgr + c);
+      g_i.load(gi + r * ldgi + c);
+      int e = beg;
+      for (; e + 4 <= end; e += 4) {
+        int cc[4];
+        float a[4], b[4];
+        FVec<VEC> u[4], w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cc[j] = __ldg(col + e + j);
+          const float t = __ldg(th + e + j);
+          a[j] = t * __ldg(vi + e + j);
+          b[j] = t * __ldg(vr + e + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          u[j].load(xr + int64_t(cc[j]) * ldxr + c);
+          w[j].load(xi + int64_t(cc[j]) * ldxi + c);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += a[j] * g_r.dot(u[j]) - b[j] * g_i.dot(w[j]);
+      }
+      for (; e < end; ++e) {
+        const int cj = __ldg(col + e);
+        const float t = __ldg(th + e);
+        FVec<VEC> u, w;
+        u.load(xr + int64_t(cj) * ldxr + c);
+        w.load(xi + int64_t(cj) * ldxi + c);
+        acc += t * __ldg(vi + e) * g_r.dot(u) - t * __ldg(vr + e) * g_i.dot(w);
+      }
+    }
+  }
+  __shared__ double part[QG_THREADS / 32];
+  double d = double(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if (lane == 0) part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < QG_THREADS / 32; ++k) s += part[k];
+    atomicAdd(dq, s * scale);
+  }
+}
+
+}  // namespace pgsd
+
+extern "C" int pgsd_magnetic_q_grad(const int32_t* row_ptr, const int32_t* col, const float* val_real,
+                                    const float* val_imag, const float* theta, int64_t n_rows, int32_t feat,
+                                    const float* gy_real, int64_t ldgr, const float* gy_imag, int64_t ldgi,
+                                    const float* x_real, int64_t ldxr, const float* x_imag, int64_t ldxi,
+                                    double scale, double* dq, pgsd_stream_t stream) {
+  PGSD_REQUIRE(n_rows >= 0 && feat >= 0, "magnetic_q_grad: negative size");
+  PGSD_REQUIRE(dq != nullptr, "magnetic_q_grad: null dq");
+  if (n_rows == 0 || feat == 0) return PGSD_OK;
+  PGSD_REQUIRE(row_ptr && gy_real && gy_imag && x_real && x_imag, "magnetic_q_grad: null pointer");
+  const bool vec4 = feat % 4 == 0 && ldgr % 4 == 0 && ldgi % 4 == 0 && ldxr % 4 == 0 && ldxi % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(gy_real) | reinterpret_cast<uintptr_t>(gy_imag) |
+                      reinterpret_cast<uintptr_t>(x_real) | reinterpret_cast<uintptr_t>(x_imag)) & 15) == 0;
+  const int chunks = vec4 ? feat / 4 : feat;
+  int lpr = 1;
+  while (lpr < 32 && lpr < chunks) lpr <<= 1;
+  const int64_t rows_per_block = int64_t(QG_THREADS / 32) * (32 / lpr);
+  int64_t grid = ceil_div<int64_t>(n_rows, rows_per_block);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec4)
+    magnetic_q_grad_kernel<4><<<unsigned(grid), QG_THREADS, 0, st>>>(
+        row_ptr, col, val_real, val_imag, theta, n_rows, feat, gy_real, ldgr, gy_imag, ldgi, x_real, ldxr,
+        x_imag, ldxi, lpr, scale, dq);
+  else
+    magnetic_q_grad_kernel<1><<<unsigned(grid), QG_THREADS, 0, st>>>(
+        row_ptr, col, val_real, val_imag, theta, n_rows, feat, gy_real, ldgr, gy_imag, ldgi, x_real, ldxr,
+        x_imag, ldxi, lpr, scale, dq);
+  PGSD_LAUNCH_CHECK("magnetic_q_grad_kernel");
+  return PGSD_OK;
+}

@@ -160,10 +160,12 @@ __global__ void k_magnetic_values(const int32_t* __restrict__ urow, const int32_
                                   const float* __restrict__ usym, const float* __restrict__ utheta,
                                   const float* __restrict__ deg, const int* n_ptr, float two_pi_q,
                                   int normalization, float lambda_max,
-                                  float* __restrict__ val_real, float* __restrict__ val_imag) {
+                                  float* __restrict__ val_real, float* __restrict__ val_imag,
+                                  float* __restrict__ theta_out) {
   const int64_t n = *n_ptr;
   GRID_STRIDE(u, n) {
     const int a = urow[u], b = ucol[u];
+    if (theta_out) theta_out[u] = utheta[u];
     const float s = usym[u] / 2;
     float sn, cs;
     sincosf(two_pi_q * utheta[u], &sn, &cs);
@@ -502,10 +504,10 @@ extern "C" int pgsd_build_csr_sym_norm(const int64_t* edge_dst, const int64_t* e
   return PGSD_OK;
 }
 
-extern "C" int pgsd_build_magnetic_laplacian(
+static int build_magnetic_impl(
     const int64_t* edge_row, const int64_t* edge_col, const float* edge_weight, int64_t num_edges,
     int64_t num_nodes, double q, int normalization, float lambda_max, int signed_mode,
-    int32_t* row_ptr, int32_t* col, float* val_real, float* val_imag, float* diag_real,
+    int32_t* row_ptr, int32_t* col, float* val_real, float* val_imag, float* diag_real, float* theta,
     int64_t* nnz_host, void* workspace, size_t workspace_bytes, pgsd_stream_t stream) {
   int rc = check_sizes(num_nodes, num_edges);
   if (rc != PGSD_OK) return rc;
@@ -567,8 +569,29 @@ extern "C" int pgsd_build_magnetic_laplacian(
     const float two_pi_q = float(2.0 * 3.14159265358979323846 * q);
     k_magnetic_values<<<blocks_for(hc.nnz), TPB, 0, st>>>(s.urow, col, s.usym, s.utheta, s.deg,
                                                           &s.cnt->nnz, two_pi_q, normalization,
-                                                          lambda_max, val_real, val_imag);
+                                                          lambda_max, val_real, val_imag, theta);
     PGSD_LAUNCH_CHECK("k_magnetic_values");
   }
   return PGSD_OK;
+}
+
+extern "C" int pgsd_build_magnetic_laplacian(
+    const int64_t* edge_row, const int64_t* edge_col, const float* edge_weight, int64_t num_edges,
+    int64_t num_nodes, double q, int normalization, float lambda_max, int signed_mode,
+    int32_t* row_ptr, int32_t* col, float* val_real, float* val_imag, float* diag_real,
+    int64_t* nnz_host, void* workspace, size_t workspace_bytes, pgsd_stream_t stream) {
+  return build_magnetic_impl(edge_row, edge_col, edge_weight, num_edges, num_nodes, q, normalization,
+                             lambda_max, signed_mode, row_ptr, col, val_real, val_imag, diag_real,
+                             nullptr, nnz_host, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pgsd_build_magnetic_laplacian_theta(
+    const int64_t* edge_row, const int64_t* edge_col, const float* edge_weight, int64_t num_edges,
+    int64_t num_nodes, double q, int normalization, float lambda_max, int signed_mode,
+    int32_t* row_ptr, int32_t* col, float* val_real, float* val_imag, float* diag_real, float* theta,
+    int64_t* nnz_host, void* workspace, size_t workspace_bytes, pgsd_stream_t stream) {
+  PGSD_REQUIRE(num_edges == 0 || theta, "build_magnetic_laplacian_theta: null theta");
+  return build_magnetic_impl(edge_row, edge_col, edge_weight, num_edges, num_nodes, q, normalization,
+                             lambda_max, signed_mode, row_ptr, col, val_real, val_imag, diag_real,
+                             theta, nnz_host, workspace, workspace_bytes, stream);
 }

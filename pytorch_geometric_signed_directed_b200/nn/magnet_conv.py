@@ -15,8 +15,8 @@ The reference's quirks are reproduced on purpose: aggregation is source_to_targe
 collapse to A and B (two are duplicates).
 
 Autograd: x_real / x_imag / weight / bias are differentiable through `autograd.py` (the
-backward aggregation reuses the same plan: L~_r is symmetric, L~_i antisymmetric); edge weights
-and a trainable q receive no gradient.
+backward aggregation reuses the same plan: L~_r is symmetric, L~_i antisymmetric); a trainable q
+gets its gradient from `pgsd_magnetic_q_grad`; edge weights receive no gradient.
 """
 from __future__ import annotations
 
@@ -160,7 +160,8 @@ class _MagneticChebConv(torch.nn.Module):
             if isinstance(lambda_max, Tensor):
                 lambda_max = float(lambda_max.detach().to(torch.float32).item())
             self._plan = _plan.build_magnetic(edge_index, edge_weight, n, qv, self.normalization,
-                                              float(lambda_max), self._signed_mode())
+                                              float(lambda_max), self._signed_mode(),
+                                              keep_theta=bool(self.trainable_q))
             self._cached_result = None
 
         return self._cheb_forward(x_real, x_imag)
@@ -177,11 +178,13 @@ class _MagneticChebConv(torch.nn.Module):
             raise TypeError(f"MagNetConv kernels take float32 or bfloat16 features, got {dt}")
         t0 = [x_real, x_imag.to(dt)]
         terms = [(t0[0], w[0], 0), (t0[1], w[0], 1)]
+        # a trainable q is a leaf the operator values were computed from (MagNetConv.py:141-142)
+        q = self.q if (self.trainable_q and "theta" in p.meta) else None
         if k1 > 1:
-            t1 = ag.spmm(p, t0, (0, 1))
+            t1 = ag.spmm(p, t0, (0, 1), q=q)
             terms += [(t1[0], w[1], 0), (t1[1], w[1], 1)]
             for k in range(2, k1):
-                t2 = ag.spmm(p, t1, (0, 1), alpha=2.0, beta=-1.0, zs=t0)  # MagNetConv.py:214-216
+                t2 = ag.spmm(p, t1, (0, 1), alpha=2.0, beta=-1.0, zs=t0, q=q)  # MagNetConv.py:214-216
                 terms += [(t2[0], w[k], 0), (t2[1], w[k], 1)]
                 t0, t1 = t1, t2
         out_real, out_imag = ag.dense(terms, self.out_channels, bias=self.bias, combine=True,

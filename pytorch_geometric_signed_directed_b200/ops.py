@@ -5,6 +5,7 @@ PyTorch supplies device memory and the current stream; all arithmetic is in libp
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import List, Optional, Sequence, Tuple
 
@@ -267,3 +268,32 @@ def xtg_accumulate(x: Tensor, g: Tensor, dw: Tensor, db: Optional[Tensor] = None
                                            torch.cuda.current_stream(x.device).cuda_stream),
                    "pgsd_xtg_accumulate")
     LAUNCHES += 1
+
+
+def magnetic_q_grad(plan: CSRPlan, gys: Sequence[Tensor], xs: Sequence[Tensor], alpha: float = 1.0) -> Tensor:
+    """dL/dq through one two-operator aggregation of a magnetic plan built with `keep_theta`
+    (`pgsd_magnetic_q_grad`); returns a float64 scalar tensor."""
+    global LAUNCHES
+    theta = plan.meta.get("theta")
+    if theta is None:
+        raise _lib.PgsdError("magnetic_q_grad: the plan was built without theta (keep_theta=False)")
+    gr, gi = (_rows2d(g.detach(), "gy") for g in gys)
+    xr, xi = (_rows2d(x.detach(), "x") for x in xs)
+    for t in (gr, gi, xr, xi):
+        if t.dtype != torch.float32:
+            raise TypeError("magnetic_q_grad: fp32 features only")
+    if not (gr.size(0) == gi.size(0) == plan.n_dst and xr.size(0) == xi.size(0) == plan.n_src
+            and gr.size(1) == gi.size(1) == xr.size(1) == xi.size(1)):
+        raise ValueError("magnetic_q_grad: shape mismatch")
+    dq = torch.zeros((), dtype=torch.float64, device=gr.device)
+    if plan.nnz == 0:
+        return dq
+    lib = _lib.load()
+    with torch.cuda.device(gr.device), _Timed("q_grad", gr.device):
+        _lib.check(lib.pgsd_magnetic_q_grad(
+            plan.row_ptr.data_ptr(), plan.col.data_ptr(), plan.val[0].data_ptr(), plan.val[1].data_ptr(),
+            theta.data_ptr(), plan.n_dst, gr.size(1), gr.data_ptr(), gr.stride(0), gi.data_ptr(), gi.stride(0),
+            xr.data_ptr(), xr.stride(0), xi.data_ptr(), xi.stride(0), 2.0 * math.pi * float(alpha),
+            dq.data_ptr(), torch.cuda.current_stream(gr.device).cuda_stream), "pgsd_magnetic_q_grad")
+    LAUNCHES += 1
+    return dq

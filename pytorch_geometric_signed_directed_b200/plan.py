@@ -176,7 +176,7 @@ def build_sym_norm(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, fi
 
 def build_magnetic(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, q: float,
                    normalization: Optional[str], lambda_max: float,
-                   signed_mode: int = 0) -> CSRPlan:
+                   signed_mode: int = 0, keep_theta: bool = False) -> CSRPlan:
     """Scaled magnetic (signed) Laplacian plan (`pgsd_build_magnetic_laplacian`):
     val[0]/val[1] = real/imag off-diagonals of L~ = 2L/lambda_max - I stored for
     source_to_target aggregation, diag[0] = its real diagonal (imag diagonal is 0)."""
@@ -192,15 +192,22 @@ def build_magnetic(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, q:
         ws = _workspace(n, e, dev)
         nnz = C.c_int64(0)
         lib = _lib.load()
-        _lib.check(lib.pgsd_build_magnetic_laplacian(
-            ei[0].data_ptr(), ei[1].data_ptr(), _ptr(ew), e, n, float(q),
-            1 if normalization == "sym" else 0, float(lambda_max), int(signed_mode),
-            row_ptr.data_ptr(), col.data_ptr(), vr.data_ptr(), vi.data_ptr(), diag.data_ptr(),
-            C.byref(nnz), ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
-            "pgsd_build_magnetic_laplacian")
+        head = (ei[0].data_ptr(), ei[1].data_ptr(), _ptr(ew), e, n, float(q),
+                1 if normalization == "sym" else 0, float(lambda_max), int(signed_mode),
+                row_ptr.data_ptr(), col.data_ptr(), vr.data_ptr(), vi.data_ptr(), diag.data_ptr())
+        tail = (C.byref(nnz), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        theta = None
+        if keep_theta:   # trainable q: the phase weights stay with the plan for pgsd_magnetic_q_grad
+            theta = torch.empty(cap, dtype=torch.float32, device=dev)
+            _lib.check(lib.pgsd_build_magnetic_laplacian_theta(*head, theta.data_ptr(), *tail),
+                       "pgsd_build_magnetic_laplacian_theta")
+        else:
+            _lib.check(lib.pgsd_build_magnetic_laplacian(*head, *tail), "pgsd_build_magnetic_laplacian")
     k = nnz.value
     meta = {"q": q, "normalization": normalization, "lambda_max": float(lambda_max), "diag_real": diag[:n],
             "hermitian": True}   # real part symmetric, imaginary part antisymmetric: M^T = (M_r, -M_i)
+    if theta is not None:
+        meta["theta"] = theta[:k]
     if normalization == "sym":
         # diag(L) = 1 for every node, so the real diagonal of L~ is the constant 2/lambda_max - 1
         # (exactly 0 for the default lambda_max = 2: the reference's 2N cancelling self-loop

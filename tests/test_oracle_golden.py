@@ -156,3 +156,17 @@ def test_magnet_model_port():
     y = port.magnet_node_classification(g["x"], g["x"], g["edge_index"], g["edge_weight"], chebs,
                                         g["Conv__weight"], g["Conv__bias"], 0.2)
     assert_close_rel(y, g["out"], 1e-5)
+
+
+@pytest.mark.parametrize("name,signed,norm", [("qgrad_magnet_k2", False, "sym"), ("qgrad_magnet_k1_none", False, None),
+                                              ("qgrad_msconv_k3", True, "sym"), ("qgrad_magnet_clamped", False, "sym")])
+def test_trainable_q_gradient_port(name, signed, norm):
+    """autograd of the port w.r.t. a trainable q == autograd of the reference (golden d_q)."""
+    g = load_golden(name)
+    q = g["q"].clone().requires_grad_(True)
+    lam = float(g["lambda_max"])
+    o_r, o_i = port.magnet_conv(g["x_real"], g["x_imag"], g["edge_index"], g["edge_weight"], g["weight"], g["bias"],
+                                q, norm, lambda_max=None if lam < 0 else lam, signed=signed)
+    ((o_r * g["r1"]).sum() + (o_i * g["r2"]).sum()).backward()
+    assert_close_rel(o_r, g["out_real"], 1e-5)
+    assert_close_rel(q.grad, g["d_q"], 1e-4)
