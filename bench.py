@@ -78,10 +78,10 @@ def measured_peak_gbs():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def recorded_traffic():
+def recorded_traffic(name="spmm_dram_traffic.json"):
     """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture."""
     try:
-        with open(os.path.join(ROOT, "profiles", "spmm_dram_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
             return float(json.load(fh)["dram_bytes_per_launch"])
     except Exception:
         return None
@@ -240,7 +240,9 @@ def run_gpu_arm(args, rank, world):
         x_imag = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
         conv(x_real, x_imag, ei)                       # builds & caches the plan
         plan = conv._plan
-        step = lambda: conv(x_real, x_imag, ei)
+        def step():
+            with torch.no_grad():          # forward-only metric: the inference path of the layer
+                return conv(x_real, x_imag, ei)
         nnz, n_rows = plan.nnz, n_local
     else:
         from pytorch_geometric_signed_directed_b200 import distributed as pgd
@@ -249,7 +251,9 @@ def run_gpu_arm(args, rank, world):
         n_local = sharded.n_local
         x_real = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
         x_imag = torch.rand(n_local, FEAT, generator=gen, device=dev) * 2 - 1
-        step = lambda: sharded(x_real, x_imag)
+        def step():
+            with torch.no_grad():
+                return sharded(x_real, x_imag)
         nnz, n_rows = sharded.local_nnz, n_local
     if world > 1:
         del ei
@@ -261,12 +265,13 @@ def run_gpu_arm(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    # ---- device-resident timing (clock sampler spans warm-up + timed region: the timed region alone
+    # is shorter than one 200 ms nvidia-smi period)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ops.TIMING = []
     launches0 = ops.LAUNCHES
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,6 +301,7 @@ def run_gpu_arm(args, rank, world):
         ho_i = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
         dx_r, dx_i = torch.empty_like(x_real), torch.empty_like(x_imag)
 
+        @torch.no_grad()
         def e2e_step():
             dx_r.copy_(hx_r, non_blocking=True)
             dx_i.copy_(hx_i, non_blocking=True)
@@ -324,6 +330,7 @@ def run_gpu_arm(args, rank, world):
         ev_cmp = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
 
+        @torch.no_grad()
         def pipelined(n):
             for i in range(n):
                 b = i % 2
@@ -365,14 +372,15 @@ def run_gpu_arm(args, rank, world):
     if world == 1:
         conv_cold = nn.MagNetConv(FEAT, FEAT, K=1, q=0.25, trainable_q=False, cached=False).to(dev)
         conv_cold.load_state_dict(conv.state_dict())
-        for _ in range(2):
-            conv_cold(x_real, x_imag, ei)
-        torch.cuda.synchronize()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(5):
-            conv_cold(x_real, x_imag, ei)
-        c1.record()
+        with torch.no_grad():
+            for _ in range(2):
+                conv_cold(x_real, x_imag, ei)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(5):
+                conv_cold(x_real, x_imag, ei)
+            c1.record()
         torch.cuda.synchronize()
         cold_ms = c0.elapsed_time(c1) / 5
         del conv_cold
@@ -392,18 +400,30 @@ def run_gpu_arm(args, rank, world):
     b_spmm = nnz * (4 + 8 + 2 * FEAT * 4) + (n_rows + 1) * 4 + 2 * n_rows * FEAT * 4
     # whole layer: + dense reads of x_r, x_i and writes of out_r, out_i
     b_layer = nnz * (4 + 8 + 2 * FEAT * 4) + (n_rows + 1) * 4 + 4 * n_rows * FEAT * 4
-    roof = {"bound": "hbm", "kernel": "spmm_rows_kernel (pgsd_spmm_csr, n_ops=2)", "unit": "GB/s",
-            "peak": peak, "peak_source": peak_src, "algorithmic_bytes": b_spmm,
-            "traffic": recorded_traffic()}
-    if spmm_ms:
-        roof["achieved"] = b_spmm / (spmm_ms * 1e-3) / 1e9
+    fused_ms = sum(kern["magnet_fused"]) / args.steps if kern.get("magnet_fused") else None
+    if fused_ms:
+        # the whole layer is ONE kernel (pgsd_magnet_layer_fused): its algorithmic bytes are the layer's
+        roof = {"bound": "hbm", "kernel": "magnet_layer_fused_kernel (pgsd_magnet_layer_fused: aggregation + "
+                                          "tcgen05 transform in one launch)", "unit": "GB/s",
+                "peak": peak, "peak_source": peak_src, "algorithmic_bytes": b_layer,
+                "traffic": recorded_traffic("fused_dram_traffic.json"),
+                "achieved": b_layer / (fused_ms * 1e-3) / 1e9, "kernel_ms": fused_ms,
+                "launches_per_step": len(kern["magnet_fused"]) / args.steps,
+                "share_of_step": fused_ms / ms_per_step}
         roof["frac"] = roof["achieved"] / peak
-        roof["kernel_ms"] = spmm_ms
-        roof["launches_per_step"] = len(kern["spmm"]) / args.steps
-        roof["share_of_step"] = spmm_ms / ms_per_step
-        if world > 1:
-            roof["note"] = ("rank 0 of the sharded run: kernel_ms sums the per-shard column-block launches of "
-                            "one step; the step is bounded by the NVLink exchange, see DESIGN.md §7")
+    else:
+        roof = {"bound": "hbm", "kernel": "spmm_groups_kernel (pgsd_spmm_csr, n_ops=2)", "unit": "GB/s",
+                "peak": peak, "peak_source": peak_src, "algorithmic_bytes": b_spmm,
+                "traffic": recorded_traffic()}
+        if spmm_ms:
+            roof["achieved"] = b_spmm / (spmm_ms * 1e-3) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+            roof["kernel_ms"] = spmm_ms
+            roof["launches_per_step"] = len(kern["spmm"]) / args.steps
+            roof["share_of_step"] = spmm_ms / ms_per_step
+            if world > 1:
+                roof["note"] = ("rank 0 of the sharded run: kernel_ms sums the per-shard column-block launches of "
+                                "one step; the step is bounded by the NVLink exchange, see DESIGN.md §7")
     roof["layer"] = {"algorithmic_bytes": b_layer, "achieved": b_layer / (ms_per_step * 1e-3) / 1e9,
                      "frac": b_layer / (ms_per_step * 1e-3) / 1e9 / peak, "dense_ms": dense_ms}
 

@@ -230,6 +230,44 @@ typedef struct pgsd_dense_args {
 PGSD_API int pgsd_dense_transform(const pgsd_dense_args* args, pgsd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * One MagNetConv / MSConv layer of Chebyshev order K = 1 in ONE launch (SURVEY 8b
+ * "magnet_layer_fused_f32"): aggregation and transform fused, so T = L~ x never goes to HBM.
+ *   T_k[r]   = diag_k[r] * x_k[r] + sum_{e in row r} val_k[e] * x_k[col[e]]     k = real, imag
+ *   A        = x_real W0 + T_real W1,   B = x_imag W0 + T_imag W1
+ *   out_real = A - B + bias,  out_imag = A + B + bias       (+ complex ReLU mask when relu_mode = 1)
+ * Replaces the whole body of MagNetConv.forward for weight [2, F_in, F_out]
+ * (nn/directed/MagNetConv.py:185-249: four propagates, eight matmuls, the real/imag mix and the
+ * bias add; nn/general/MSConv.py:181-246 likewise).  Persistent CTAs: lane groups aggregate
+ * rows into a shared-memory ring, a consumer warpgroup splits finished 128-row tiles into TF32
+ * hi/lo operands and runs 3xTF32 tcgen05.mma against the resident weights, epilogue from TMEM.
+ * fp32 only; feat_in = 64, feat_out = 64; plans without hub rows (see pgsd_spmm_args).
+ * pgsd_magnet_fused_supported() returns 1 when the shape is inside that envelope.
+ * ---------------------------------------------------------------------------------- */
+typedef struct pgsd_magnet_fused_args {
+  int64_t n_rows;            /* N (square operator: destination rows == source rows)   */
+  int32_t feat_in, feat_out;
+  const int32_t* row_ptr;    /* [N + 1]                                                */
+  const int32_t* col;        /* [nnz]                                                  */
+  const float* val[2];       /* real / imaginary operator values                       */
+  const float* diag[2];      /* [N] or NULL (use diag_const)                           */
+  float diag_const[2];
+  const float* x[2];         /* x_real, x_imag [N, ldx]                                */
+  int64_t ldx[2];
+  const float* w[2];         /* W0, W1: element (k, n) at w[i][k * ldw_k[i] + n * ldw_n[i]] */
+  int64_t ldw_k[2], ldw_n[2];
+  const float* bias;         /* [feat_out] or NULL                                     */
+  float* y[2];               /* out_real, out_imag [N, ldy]                            */
+  int64_t ldy[2];
+  int32_t relu_mode;         /* as pgsd_dense_args                                     */
+  int32_t variant;           /* 0 = default; 1 = 24 producer warps instead of 20       */
+} pgsd_magnet_fused_args;
+
+PGSD_API int pgsd_magnet_fused_supported(int32_t feat_in, int32_t feat_out, int32_t dtype);
+/* sizeof(pgsd_magnet_fused_args) as compiled (struct-mirror check of foreign bindings). */
+PGSD_API size_t pgsd_sizeof_magnet_fused_args(void);
+PGSD_API int pgsd_magnet_layer_fused(const pgsd_magnet_fused_args* args, pgsd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Segment-softmax attention over CSR-by-destination plans.
  *   t_e     = act(s_src[p][j] + s_dst[p][i])        edge e = (j -> i) of type p (one plan per type)
  *   alpha_e = exp(t_e - max_i) / (sum over ALL entries of row i, both types, + 1e-16)

@@ -47,6 +47,18 @@ class DenseArgs(C.Structure):
     ]
 
 
+class MagnetFusedArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", _i64), ("feat_in", _i32), ("feat_out", _i32),
+        ("row_ptr", _vp), ("col", _vp),
+        ("val", _vp * 2), ("diag", _vp * 2), ("diag_const", _f32 * 2),
+        ("x", _vp * 2), ("ldx", _i64 * 2),
+        ("w", _vp * 2), ("ldw_k", _i64 * 2), ("ldw_n", _i64 * 2),
+        ("bias", _vp), ("y", _vp * 2), ("ldy", _i64 * 2),
+        ("relu_mode", _i32), ("variant", _i32),
+    ]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("n_rows", _i64), ("feat", _i32), ("n_types", _i32), ("act", _i32), ("slope", _f32),
@@ -77,6 +89,9 @@ _PROTOTYPES = {
                                        _vp, _i64, _vp, _i64, C.c_double, _vp, _vp]),
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),
     "pgsd_dense_transform": (C.c_int, [C.POINTER(DenseArgs), _vp]),
+    "pgsd_magnet_fused_supported": (C.c_int, [_i32, _i32, _i32]),
+    "pgsd_sizeof_magnet_fused_args": (C.c_size_t, []),
+    "pgsd_magnet_layer_fused": (C.c_int, [C.POINTER(MagnetFusedArgs), _vp]),
     "pgsd_edge_softmax": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pgsd_xtg_accumulate": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
@@ -109,6 +124,8 @@ def load() -> C.CDLL:
         lib.pgsd_sizeof_args(C.byref(a), C.byref(b))
         if (a.value, b.value) != (C.sizeof(SpmmArgs), C.sizeof(DenseArgs)):
             raise PgsdError("ctypes struct mirror out of sync with include/pgsd_b200.h; rebuild")
+        if lib.pgsd_sizeof_magnet_fused_args() != C.sizeof(MagnetFusedArgs):
+            raise PgsdError("ctypes mirror of pgsd_magnet_fused_args out of sync with include/pgsd_b200.h; rebuild")
         _lib = lib
     return _lib
 

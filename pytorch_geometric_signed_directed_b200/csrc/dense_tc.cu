@@ -19,7 +19,7 @@
 //     real/imag mix + bias (+ complex ReLU mask), 128-bit streaming stores.
 // The tensor work is ~1.6 us per tile against ~3 us of HBM time: the kernel is a streaming
 // kernel whose math rides on the tensor pipe for free ("never the bound").
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pgsd {
 namespace tc {
@@ -49,133 +49,6 @@ struct Params {
   char* y[2];
   int64_t ldy_bytes[2];
 };
-
-// ------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-// Round-to-nearest (ties away) to TF32's 10-bit mantissa: add half a TF32 ulp to the magnitude
-// bits and clear the 13 low bits.  Same result as cvt.rna.tf32.f32, but 2 integer instructions:
-// ptxas expands the cvt into ~5 (FSETP/SEL/LOP3/VIADD/IMAD), and with 32 conversions per thread
-// per 16 KB chunk the split was half of the kernel's instruction count (profiles/README.md).
-__device__ __forceinline__ float to_tf32(float v) {
-  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a descriptor / barrier bug must surface as a trapped kernel (launch error),
-// never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) = 1024 B
-// between 8-row groups, version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
-         (uint64_t(1) << 46) | (uint64_t(2) << 61);
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, M=128 (cute::UMMA::InstrDescriptor in idesc)
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-template <int CPW>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[CPW]);
-template <>
-__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, float (&v)[4]) {
-  uint32_t r[4];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-                 "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) {
-  float a[16], b[16];
-  tmem_ld<16>(taddr, a);
-  tmem_ld<16>(taddr + 16, b);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = a[i], v[16 + i] = b[i];
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 operands, fp32 accumulate)
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 // ------------------------------------------------------------------------------------ kernel
 // BF16 = false: fp32 operands, 3xTF32 (hi/lo split), 32 k per 128-byte chunk row.
@@ -403,9 +276,6 @@ constexpr int WS_LOADER_WARPS = 16;
 constexpr int WS_THREADS = (WS_LOADER_WARPS + 1) * 32;
 constexpr int WS_MAX_STAGES = 4;
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 template <int N_OUT, int GROUPS, bool BF16>
 __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const __grid_constant__ Params p) {

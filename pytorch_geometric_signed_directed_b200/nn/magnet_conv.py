@@ -27,7 +27,7 @@ import torch
 from torch import Tensor
 from torch.nn import Parameter
 
-from .. import autograd as ag, plan as _plan
+from .. import autograd as ag, ops as _ops, plan as _plan
 from .._lib import DENSE_MAX_TERMS
 
 
@@ -177,6 +177,13 @@ class _MagneticChebConv(torch.nn.Module):
         if dt not in (torch.float32, torch.bfloat16):
             raise TypeError(f"MagNetConv kernels take float32 or bfloat16 features, got {dt}")
         t0 = [x_real, x_imag.to(dt)]
+        # K = 1 inside the fused kernel's envelope and nothing to differentiate: one launch
+        # (aggregation -> shared memory -> tcgen05 transform), T = L~ x never touches HBM
+        if (_ops.FUSED_LAYER and k1 == 2 and not ag._needs_grad([x_real, x_imag, w, self.bias, self.q
+                                                                  if isinstance(self.q, Tensor) else None])
+                and _ops.magnet_fused_supported(p, t0[0], t0[1], w)):
+            return _ops.magnet_layer_fused(p, t0[0], t0[1], w, self.bias,
+                                           relu_mode=1 if self.fused_complex_relu else 0)
         terms = [(t0[0], w[0], 0), (t0[1], w[0], 1)]
         # a trainable q is a leaf the operator values were computed from (MagNetConv.py:141-142)
         q = self.q if (self.trainable_q and "theta" in p.meta) else None

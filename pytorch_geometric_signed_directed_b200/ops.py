@@ -297,3 +297,63 @@ def magnetic_q_grad(plan: CSRPlan, gys: Sequence[Tensor], xs: Sequence[Tensor], 
             dq.data_ptr(), torch.cuda.current_stream(gr.device).cuda_stream), "pgsd_magnetic_q_grad")
     LAUNCHES += 1
     return dq
+
+
+# 1: MagNetConv / MSConv layers of order K = 1 inside the fused kernel's envelope run as ONE launch
+# (pgsd_magnet_layer_fused); 0: aggregation launch + transform launch
+FUSED_LAYER = int(os.environ.get("PGSD_FUSED_LAYER", "0"))
+FUSED_VARIANT = int(os.environ.get("PGSD_FUSED_VARIANT", "0"))
+
+
+def magnet_fused_supported(plan: CSRPlan, x_real: Tensor, x_imag: Tensor, weight: Tensor) -> bool:
+    """True when `magnet_layer_fused` can run this layer: fp32, K = 1, the kernel's feature widths,
+    square plan with two value arrays and no hub rows."""
+    if weight.dim() != 3 or weight.size(0) != 2 or x_real.dtype != torch.float32 or x_imag.dtype != torch.float32:
+        return False
+    if not (x_real.is_cuda and x_real.dim() == 2 and x_real.shape == x_imag.shape):
+        return False
+    if len(plan.val) != 2 or plan.val[0] is None or plan.val[1] is None or plan.n_dst != plan.n_src:
+        return False
+    if plan.meta.get("diag_row_offset", 0) != 0 or plan.hub_rows() is not None:
+        return False
+    if x_real.size(1) != weight.size(1) or x_real.size(0) != plan.n_dst:
+        return False
+    return bool(_lib.load().pgsd_magnet_fused_supported(weight.size(1), weight.size(2), _lib.PGSD_F32))
+
+
+def magnet_layer_fused(plan: CSRPlan, x_real: Tensor, x_imag: Tensor, weight: Tensor,
+                       bias: Optional[Tensor] = None, relu_mode: int = 0,
+                       variant: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+    """(out_real, out_imag) of a K = 1 MagNetConv layer in one launch (`pgsd_magnet_layer_fused`):
+    A = x_r W0 + (L_r x_r) W1, B = x_i W0 + (L_i x_i) W1, out_real = A - B + b, out_imag = A + B + b."""
+    global LAUNCHES
+    if not magnet_fused_supported(plan, x_real, x_imag, weight):
+        raise _lib.PgsdError("magnet_layer_fused: layer is outside the fused kernel's envelope")
+    xr, xi = _rows2d(x_real.detach(), "x_real"), _rows2d(x_imag.detach(), "x_imag")
+    w = weight.detach()
+    dev, n, f_out = xr.device, plan.n_dst, w.size(2)
+    a = _lib.MagnetFusedArgs()
+    a.n_rows, a.feat_in, a.feat_out = n, w.size(1), f_out
+    a.row_ptr, a.col = plan.row_ptr.data_ptr(), plan.col.data_ptr()
+    for k in range(2):
+        a.val[k] = plan.val[k].data_ptr()
+        a.diag[k] = None if plan.diag[k] is None else plan.diag[k].data_ptr()
+        a.diag_const[k] = plan.diag_const[k]
+        a.w[k], a.ldw_k[k], a.ldw_n[k] = w[k].data_ptr(), w.stride(1), w.stride(2)
+    a.x[0], a.ldx[0], a.x[1], a.ldx[1] = xr.data_ptr(), xr.stride(0), xi.data_ptr(), xi.stride(0)
+    keep = [xr, xi, w]
+    if bias is not None:
+        b = bias.detach().float().contiguous()
+        keep.append(b)
+        a.bias = b.data_ptr()
+    outs = [torch.empty((n, f_out), dtype=torch.float32, device=dev) for _ in range(2)]
+    for k in range(2):
+        a.y[k], a.ldy[k] = outs[k].data_ptr(), outs[k].stride(0)
+    a.relu_mode = relu_mode
+    a.variant = FUSED_VARIANT if variant is None else variant
+    lib = _lib.load()
+    with torch.cuda.device(dev), _Timed("magnet_fused", dev):
+        _lib.check(lib.pgsd_magnet_layer_fused(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                   "pgsd_magnet_layer_fused")
+    LAUNCHES += 1
+    return outs[0], outs[1]

@@ -35,6 +35,19 @@ def timeit(fn, iters=10, warm=3):
     return a.elapsed_time(b) / iters
 
 
+def breakdown(fn, iters=3):
+    """Per-kernel-family device time of one call (CUDA events around every launch, ops.TIMING)."""
+    ops.TIMING = []
+    for _ in range(iters):
+        fn()
+    torch.cuda.synchronize()
+    t, ops.TIMING = ops.TIMING, None
+    out = {}
+    for name, a, b in t:
+        out[name] = out.get(name, 0.0) + a.elapsed_time(b) / iters
+    return {k: round(v, 4) for k, v in out.items()}
+
+
 with torch.no_grad():
     # ---- C3: DiGCN_InceptionBlock, 500k nodes, two 10M-nnz operators, 128 features, bf16
     n, e, f = 500_000, 10_000_000, 128
@@ -48,7 +61,8 @@ with torch.no_grad():
     b_alg = nnz * 8 + 2 * (n + 1) * 4 + nnz * f * 2 + n * f * 2 * (1 + 3 + 2 + 2)   # x, buf(3), 2 gathers src, x1, x2
     ms = timeit(lambda: blk(x, ei1, w1, ei2, w2))
     emit(config="C3 DiGCN_InceptionBlock 500k/2x10M/128 bf16", ms=ms, edges_per_s=nnz / ms * 1e3,
-         alg_gb=b_alg / 1e9, alg_gbs=b_alg / ms / 1e6, frac=b_alg / ms / 1e6 / PEAK)
+         alg_gb=b_alg / 1e9, alg_gbs=b_alg / ms / 1e6, frac=b_alg / ms / 1e6 / PEAK,
+         kernels_ms=breakdown(lambda: blk(x, ei1, w1, ei2, w2)))
     del ei1, ei2, w1, w2, x, blk
     torch.cuda.empty_cache()
 
@@ -65,9 +79,9 @@ with torch.no_grad():
     ms1 = timeit(lambda: c1(x, pos, neg))
     ms2 = timeit(lambda: c2(z1, pos, neg))
     emit(config="C4 SGCNConv layer 1 2M/40M/64 fp32", ms=ms1, edges_per_s=nnz / ms1 * 1e3, alg_gb=b1 / 1e9,
-         alg_gbs=b1 / ms1 / 1e6, frac=b1 / ms1 / 1e6 / PEAK)
+         alg_gbs=b1 / ms1 / 1e6, frac=b1 / ms1 / 1e6 / PEAK, kernels_ms=breakdown(lambda: c1(x, pos, neg)))
     emit(config="C4 SGCNConv layer 2 2M/40M/(32|32) fp32", ms=ms2, edges_per_s=nnz / ms2 * 1e3, alg_gb=b1 / 1e9,
-         alg_gbs=b1 / ms2 / 1e6, frac=b1 / ms2 / 1e6 / PEAK)
+         alg_gbs=b1 / ms2 / 1e6, frac=b1 / ms2 / 1e6 / PEAK, kernels_ms=breakdown(lambda: c2(z1, pos, neg)))
     del pos, neg, x, z1
     torch.cuda.empty_cache()
 
@@ -84,7 +98,8 @@ with torch.no_grad():
     b = 2 * layer + n * 2 * f * 4 + n * lab * 4 * 3
     ms = timeit(lambda: model(x, x, ei))
     emit(config="C2 MagNet_node_classification 2 layers 1M/20M/64 fp32 (inference)", ms=ms,
-         edges_per_s=2 * ei.size(1) / ms * 1e3, alg_gb=b / 1e9, alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK)
+         edges_per_s=2 * ei.size(1) / ms * 1e3, alg_gb=b / 1e9, alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK,
+         fused_layer=ops.FUSED_LAYER, kernels_ms=breakdown(lambda: model(x, x, ei)))
     del model, x, ei, p0
     torch.cuda.empty_cache()
 
@@ -98,7 +113,7 @@ with torch.no_grad():
     ms = timeit(lambda: dm(xs, xt, ei, ew))
     b = 4 * (ei.size(1) * (8 + 256) + (n + 1) * 4 + n * 256 * 2) + 4 * n * 256 * 3
     emit(config="DIMPA hop=2 1M/20M/64 fp32", ms=ms, edges_per_s=4 * ei.size(1) / ms * 1e3, alg_gb=b / 1e9,
-         alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK)
+         alg_gbs=b / ms / 1e6, frac=b / ms / 1e6 / PEAK, kernels_ms=breakdown(lambda: dm(xs, xt, ei, ew)))
 
 # ---- C2 training step (forward + nll loss + backward through the same kernels), same model
 n, f, lab = 1_000_000, 64, 10
