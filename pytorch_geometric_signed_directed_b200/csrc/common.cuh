@@ -119,6 +119,48 @@ __device__ __forceinline__ float8 ld_gather_v8(const void* p) {
       : "l"(p));
   return r;
 }
+// Gathers of a batch are issued UNCONDITIONALLY: lanes without an entry read a zero row instead of
+// being predicated off.  "ok ? load : 0" -- in C++ or as a predicated PTX load over zero-initialised
+// registers -- makes ptxas load into temporaries and select with MOVs that wait on the data in the
+// middle of the gather sequence, which delays the later loads of the batch (ncu source page,
+// profiles/README.md session 13).  With an address select the data lands in its final registers
+// and the U * n_ops loads go out back to back.  The zero row (not x[0]: 0 * inf would poison the sum
+// if a feature row held non-finite values) lives in device memory and stays L2-resident.
+__device__ __align__(128) const float g_zero_row[256] = {0.f};
+__device__ __forceinline__ const char* zero_row_ptr() { return reinterpret_cast<const char*>(g_zero_row); }
+
+__device__ __forceinline__ void ld_gather_v4_to(const void* p, uint64_t pol, float (&w)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
+               : "l"(p), "l"(pol));
+}
+// no L2 policy operand (the immediate .L2::evict_* qualifiers are accepted only on 256-bit loads;
+// the policy of the gathers measured as a no-op, profiles/r01_sweep_l2policy.jsonl)
+__device__ __forceinline__ void ld_gather_v4_plain_to(const void* p, float (&w)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])
+               : "l"(p));
+}
+__device__ __forceinline__ void ld_gather_v8_to(const void* p, float (&w)[8]) {
+  asm volatile(
+      "ld.global.nc.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]), "=f"(w[4]), "=f"(w[5]), "=f"(w[6]), "=f"(w[7])
+      : "l"(p));
+}
+__device__ __forceinline__ int ld_once_i32(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_once_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+// base + index * stride with ONE IMAD.WIDE.U32 (row strides are < 4 GiB)
+__device__ __forceinline__ const char* row_addr(const char* base, int index, uint32_t stride_bytes) {
+  return base + uint64_t(uint32_t(index)) * stride_bytes;
+}
 __device__ __forceinline__ void st_stream_v4(void* p, float4 v, uint64_t pol) {
   asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p),
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)

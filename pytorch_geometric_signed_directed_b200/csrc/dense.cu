@@ -204,7 +204,7 @@ extern "C" int pgsd_dense_transform(const pgsd_dense_args* a, pgsd_stream_t stre
     int rc = dense_tc_try(a, st, &handled);
     if (rc != PGSD_OK) return rc;
     if (handled) return PGSD_OK;
-    if (a->variant == 2 || a->variant == 4) return fail(PGSD_ERR_INVALID, "dense: shape outside the tcgen05 path's envelope");
+    if (a->variant == 2 || a->variant == 4 || a->variant == 8) return fail(PGSD_ERR_INVALID, "dense: shape outside the tcgen05 path's envelope");
   }
   dim3 grid((unsigned)ceil_div<int64_t>(a->n_rows, BM), (unsigned)ceil_div<int>(a->n_out, BN));
   if (a->dtype == PGSD_BF16) {

@@ -54,7 +54,7 @@ struct Params {
 // BF16 = false: fp32 operands, 3xTF32 (hi/lo split), 32 k per 128-byte chunk row.
 // BF16 = true : bf16 operands fed to kind::f16 directly, 64 k per 128-byte chunk row, bf16 output.
 // grid.y tiles the output width in N_OUT-column tiles (weights / bias / outputs offset by n0).
-template <int N_OUT, int GROUPS, bool BF16>
+template <int N_OUT, int GROUPS, bool BF16, int PFK>
 __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_constant__ Params p) {
   constexpr int CPW = N_OUT / 4;                 // output columns per epilogue warp
   constexpr int ES = BF16 ? 2 : 4;               // operand element size
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
   const uint32_t st_off1 = st_off0 + 64 * 128;   // (r0 + 64) & 7 == r0 & 7
 
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
-  float4 buf[PF][2];
+  float4 buf[PFK][2];
   auto issue = [&](int slot, int64_t tile, int c) {
     const bool kin = (c16 * EPC) < p.kvalid[c];
     const char* base = p.x[c] + c16 * 16;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
                        : make_float4(0.f, 0.f, 0.f, 0.f);
   };
 #pragma unroll
-  for (int u = 0; u < PF; ++u) {
+  for (int u = 0; u < PFK; ++u) {
     buf[u][0] = buf[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (u < p.n_chunks) issue(u, blockIdx.x, u);
   }
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
   uint32_t uses = 0;   // chunks staged so far (CTA-uniform)
   uint32_t tiles_done = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    for (int cb = 0; cb < p.n_chunks; cb += PF) {
+    for (int cb = 0; cb < p.n_chunks; cb += PFK) {
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
+      for (int u = 0; u < PFK; ++u) {
         const int c = cb + u;
         if (c < p.n_chunks) {
           const uint32_t stage = uses % STAGES;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
           }
           // refill this register slot with the next chunk that maps to it
           {
-            int nc = c + PF;
+            int nc = c + PFK;
             int64_t nt = tile;
             if (nc >= p.n_chunks) nc = u, nt = tile + gridDim.x;
             issue(u, nt, nc);
@@ -528,10 +528,10 @@ static size_t smem_bytes(int n_slabs, int n_tile, bool bf16) {
   return 1024 + STAGES * STAGE_BYTES + size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (STAGES + 1) + 16;
 }
 
-template <int N_OUT, int GROUPS, bool BF16>
+template <int N_OUT, int GROUPS, bool BF16, int PFK = PF>
 static int launch(const Params& p, cudaStream_t st) {
   const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16);
-  auto kern = dense_tc_kernel<N_OUT, GROUPS, BF16>;
+  auto kern = dense_tc_kernel<N_OUT, GROUPS, BF16, PFK>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
   const int n_col_tiles = (p.n_total + N_OUT - 1) / N_OUT;
@@ -604,8 +604,12 @@ int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   // synchronous one at 1M x (4 x 64) -> 64: both are instruction-issue bound on the hi/lo split and
   // address arithmetic, see profiles/README.md), so the synchronous kernel stays the default
   const bool sync_kernel = a->variant != 4;
+  const bool deep = a->variant == 8;     // experiment: 8 chunks (128 KB per SM) of loads in flight instead of 4
 #define PGSD_TC(N_)                                                                                   \
-  if (sync_kernel) {                                                                                  \
+  if (deep) {                                                                                         \
+    if (bf16) rc = groups == 2 ? launch<N_, 2, true, 8>(p, st) : launch<N_, 1, true, 8>(p, st);       \
+    else rc = groups == 2 ? launch<N_, 2, false, 8>(p, st) : launch<N_, 1, false, 8>(p, st);          \
+  } else if (sync_kernel) {                                                                           \
     if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st) : launch<N_, 1, true>(p, st);             \
     else rc = groups == 2 ? launch<N_, 2, false>(p, st) : launch<N_, 1, false>(p, st);                \
   } else {                                                                                            \

@@ -90,7 +90,6 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
   uint8_t* ring = w_smem + N_SLABS * SLAB_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + RING_SLOTS * RING_SLOT_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-  int* cursor = reinterpret_cast<int*>(bars + 5) + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 16, bar_mma = bar_full + 32;
@@ -107,7 +106,6 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_mma, 1);
-    *cursor = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // weights -> K-major SW128 hi/lo images (element (n, k) in 16-byte unit (k/4) ^ (n&7) of row n)
@@ -230,17 +228,16 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
     // ====================================================================== producer warps
     const int g = lane >> 4, l = lane & 15;
     const unsigned gmask = 0xffffu << (16 * g);
-    const int lane_off = l * 16;
-    const uint64_t pol_keep = policy_evict_last();
-    const uint64_t pol_stream = policy_evict_first();
+    const char* xb[NOPS];
+    uint32_t ldx32[NOPS];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + l * 16, ldx32[k] = uint32_t(p.ldx_bytes[k]);
+    const char* zrow = zero_row_ptr() + l * 16;      // what lanes without an entry gather
 
-    // ticket t -> row (t & 127) of this CTA's (t >> 7)-th tile; row = -1: no tile left
-    auto grab = [&](int& t, int& trow) {
-      t = 0;
-      if (l == 0) t = atomicAdd(cursor, 1);
-      t = __shfl_sync(gmask, t, 0, LPR);
+    // ticket t -> row (t & 127) of this CTA's (t >> 7)-th tile; row_of() < 0: no tile left
+    auto row_of = [&](int t) -> int {
       const int64_t tile = int64_t(blockIdx.x) + int64_t(t >> 7) * gridDim.x;
-      trow = tile < p.n_tiles ? int(tile * TILE_M + (t & (TILE_M - 1))) : -1;
+      return tile < p.n_tiles ? int(tile * TILE_M + (t & (TILE_M - 1))) : -1;
     };
     auto load_ptrs = [&](int r, int& s, int& e) {
       s = e = 0;
@@ -249,23 +246,26 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
     auto load_batch = [&](int base, int end, int& c, float (&v)[NOPS]) {
       c = 0;
 #pragma unroll
-      for (int k = 0; k < NOPS; ++k) v[k] = 0.f;
+      for (int k = 0; k < NOPS; ++k) v[k] = 0.f;      // zero values keep lanes past the row end inert
       const int e = base + l;
       if (e < end) {
-        c = ld_stream_i32(p.col + e, pol_stream);
+        c = ld_once_i32(p.col + e);
 #pragma unroll
-        for (int k = 0; k < NOPS; ++k) v[k] = ld_stream_f32(p.val[k] + e, pol_stream);
+        for (int k = 0; k < NOPS; ++k) v[k] = ld_once_f32(p.val[k] + e);
       }
     };
 
-    int ct, crow, nt, nrow;            // current / next ticket and row
+    // Rows are dealt round-robin: group gi takes tickets gi, gi + NG, gi + 2 NG, ... of the CTA's row
+    // sequence (like the grid-stride assignment of spmm_groups_kernel: equal row counts, row-length
+    // variance averages out over the ~170 rows a group sees at the north-star size).
+    constexpr int NG = PW * 2;
+    int ct = (warp - CW) * 2 + g;      // current ticket; the next one is ct + NG
     int base, end, nstart, nend, c;
     float v[NOPS];
-    grab(ct, crow);
-    load_ptrs(crow, base, end);
+    bool live = row_of(ct) >= 0;       // the current ticket maps to a tile of this CTA
+    load_ptrs(row_of(ct), base, end);
     load_batch(base, end, c, v);
-    grab(nt, nrow);
-    load_ptrs(nrow, nstart, nend);
+    load_ptrs(row_of(ct + NG), nstart, nend);
 
     float acc[NOPS][4];
 #pragma unroll
@@ -274,28 +274,22 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
       for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
     bool pending = false;      // row finished, waiting for its ring slot; (c, v) already hold the next row's batch
 
-    while (__any_sync(FULL, crow >= 0)) {
-      const bool active = crow >= 0 && !pending;
+    while (__any_sync(FULL, live)) {
+      const bool active = live && !pending;
       const int cnt = active ? min(LPR, end - base) : 0;
       const bool more = active && (base + LPR < end);
       int nc = 0;
       float nv[NOPS] = {0.f, 0.f};
       bool next_issued = false;
       for (int jj = 0; __any_sync(FULL, jj < cnt); jj += U) {
-        float4 d[NOPS][U];
-        float vv[NOPS][U];
+        float d[NOPS][U][4];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int idx = jj + u;
           const int cc = __shfl_sync(FULL, c, idx & (LPR - 1), LPR);
           const bool ok = idx < cnt;
 #pragma unroll
-          for (int k = 0; k < NOPS; ++k) {
-            const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
-            vv[k][u] = ok ? t : 0.f;
-            d[k][u] = ok ? ld_gather_v4(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int k = 0; k < NOPS; ++k) ld_gather_v4_plain_to(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, d[k][u]);
         }
         if (!next_issued) {
           // next index batch (same row, or the first batch of the group's next row) goes out right
@@ -306,14 +300,14 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
           }
           next_issued = true;
         }
+        // lanes without an entry gathered the zero row: no select needed
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int k = 0; k < NOPS; ++k) {
-            acc[k][0] = fmaf(vv[k][u], d[k][u].x, acc[k][0]);
-            acc[k][1] = fmaf(vv[k][u], d[k][u].y, acc[k][1]);
-            acc[k][2] = fmaf(vv[k][u], d[k][u].z, acc[k][2]);
-            acc[k][3] = fmaf(vv[k][u], d[k][u].w, acc[k][3]);
+            const float t = __shfl_sync(FULL, v[k], (jj + u) & (LPR - 1), LPR);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(t, d[k][u][i], acc[k][i]);
           }
       }
       if (active) {
@@ -335,6 +329,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
           free_ = __shfl_sync(gmask, free_, 0, LPR);
         }
         if (free_) {
+          const int crow = row_of(ct);
           const bool row_ok = crow < p.n_rows;
           uint8_t* dst = ring + slot * RING_SLOT_BYTES + (ct & (TILE_M - 1)) * ROW_BYTES + l * 16;
 #pragma unroll
@@ -342,8 +337,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
             const bool has_diag = p.diag[k] != nullptr;
             const float dg = !row_ok ? 0.f : (has_diag ? __ldg(p.diag[k] + crow) : p.diag_const[k]);
             if (row_ok && (has_diag || dg != 0.f)) {
-              const float4 xr =
-                  __ldg(reinterpret_cast<const float4*>(p.x[k] + int64_t(crow) * p.ldx_bytes[k] + lane_off));
+              const float4 xr = __ldg(reinterpret_cast<const float4*>(row_addr(xb[k], crow, ldx32[k])));
               acc[k][0] = fmaf(dg, xr.x, acc[k][0]);
               acc[k][1] = fmaf(dg, xr.y, acc[k][1]);
               acc[k][2] = fmaf(dg, xr.z, acc[k][2]);
@@ -356,10 +350,10 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
           __syncwarp(gmask);
           if (l == 0) mbar_arrive(bar_full + 8 * slot);
           // advance to the row whose pointers and first batch are already here
-          ct = nt, crow = nrow, base = nstart, end = nend;
+          ct += NG, base = nstart, end = nend;
+          live = row_of(ct) >= 0;
           pending = false;
-          grab(nt, nrow);
-          load_ptrs(nrow, nstart, nend);
+          load_ptrs(row_of(ct + NG), nstart, nend);
         }
       }
       __syncwarp();
@@ -370,7 +364,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(TMEM_COLS)
                  : "memory");
   }
 }
@@ -416,8 +410,10 @@ extern "C" int pgsd_magnet_layer_fused(const pgsd_magnet_fused_args* a, pgsd_str
   p.bias = a->bias;
   p.relu_mode = a->relu_mode;
   for (int k = 0; k < 2; ++k) {
-    PGSD_REQUIRE(a->val[k] && a->x[k] && a->y[k] && a->w[k], "magnet_fused: val/x/y/w[%d] is null", k);
+    // val / col may be null for a plan without entries (their loads are predicated on row_ptr)
+    PGSD_REQUIRE(a->x[k] && a->y[k] && a->w[k], "magnet_fused: x/y/w[%d] is null", k);
     PGSD_REQUIRE(a->ldx[k] >= F_IN && a->ldy[k] >= N_OUT, "magnet_fused: leading dim < feature width");
+    PGSD_REQUIRE(a->ldx[k] * 4 < (int64_t(1) << 32), "magnet_fused: row stride of x must be below 4 GiB");
     PGSD_REQUIRE(al16(a->x[k]) && al16(a->y[k]) && (a->ldx[k] * 4) % 16 == 0 && (a->ldy[k] * 4) % 16 == 0,
                  "magnet_fused: x / y rows must be 16-byte aligned");
     p.val[k] = a->val[k];

@@ -80,6 +80,25 @@ struct RowVec {
     }
     expand(w, d);
   }
+  // predicated gather of the raw words; expansion happens at use (fma_raw) so that no ALU work that
+  // waits on a load sits between the U * n_ops gathers of a batch
+  static __device__ __forceinline__ void gather_raw(const char* p, uint64_t pol, float (&w)[W]) {
+    if constexpr (W == 8) ld_gather_v8_to(p, w);
+    else ld_gather_v4_to(p, pol, w);
+  }
+  static __device__ __forceinline__ void fma_raw(const float (&w)[W], float v, float (&acc)[EPL]) {
+    if constexpr (BF16) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const uint32_t u = __float_as_uint(w[i]);
+        acc[2 * i] = fmaf(v, bf16_lo(u), acc[2 * i]);
+        acc[2 * i + 1] = fmaf(v, bf16_hi(u), acc[2 * i + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; ++i) acc[i] = fmaf(v, w[i], acc[i]);
+    }
+  }
   // plain read of an owned row (diag / z terms)
   static __device__ __forceinline__ void load(const char* p, float (&d)[EPL]) {
     float w[W];
@@ -119,6 +138,11 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
   const int64_t lane_off = int64_t(l) * (W * 4);  // byte offset inside a feature row
   const uint64_t pol_keep = p.keep_policy == 1 ? policy_evict_normal() : (p.keep_policy == 2 ? policy_evict_first() : policy_evict_last());
   const uint64_t pol_stream = policy_evict_first();
+  const char* xb[NOPS];
+  uint32_t ldx32[NOPS];
+#pragma unroll
+  for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + lane_off, ldx32[k] = uint32_t(p.ldx_bytes[k]);
+  const char* zrow = zero_row_ptr() + lane_off;     // what lanes without an entry gather
 
   const int64_t warps_total = int64_t(gridDim.x) * (THREADS / 32);
   int64_t row = int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5);
@@ -146,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
       }
       const int cnt = min(32, end - base);
       for (int j = 0; j < cnt; j += G * U) {
-        float d[NOPS][U][EPL];
+        float d[NOPS][U][W];
         float vv[NOPS][U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -157,18 +181,13 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
           for (int k = 0; k < NOPS; ++k) {
             const float t = __shfl_sync(FULL, v[k], idx & 31);
             vv[k][u] = ok ? t : 0.f;
-            if (ok)
-              RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
-            else
-              RV::zero(d[k][u]);
+            RV::gather_raw(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, pol_keep, d[k][u]);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int k = 0; k < NOPS; ++k)
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
+          for (int k = 0; k < NOPS; ++k) RV::fma_raw(d[k][u], vv[k][u], acc[k]);
       }
     }
 
@@ -231,6 +250,11 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
   const int64_t lane_off = int64_t(l) * (W * 4);
   const uint64_t pol_keep = p.keep_policy == 1 ? policy_evict_normal() : (p.keep_policy == 2 ? policy_evict_first() : policy_evict_last());
   const uint64_t pol_stream = policy_evict_first();
+  const char* xb[NOPS];
+  uint32_t ldx32[NOPS];
+#pragma unroll
+  for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + lane_off, ldx32[k] = uint32_t(p.ldx_bytes[k]);
+  const char* zrow = zero_row_ptr() + lane_off;     // what lanes without an entry gather
 
   const int64_t groups_total = int64_t(gridDim.x) * (THREADS / 32) * G;
   int64_t row = (int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5)) * G + g;
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
     for (int k = 0; k < NOPS; ++k) nv[k] = 0.f;
     bool next_issued = false;
     for (int j = 0; __any_sync(FULL, j < cnt); j += U) {
-      float d[NOPS][U][EPL];
+      float d[NOPS][U][W];
       float vv[NOPS][U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -287,10 +311,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
         for (int k = 0; k < NOPS; ++k) {
           const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
           vv[k][u] = ok ? t : 0.f;
-          if (ok)
-            RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
-          else
-            RV::zero(d[k][u]);
+          RV::gather_raw(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, pol_keep, d[k][u]);
         }
       }
       if (!next_issued) {
@@ -303,9 +324,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int k = 0; k < NOPS; ++k)
-#pragma unroll
-          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
+        for (int k = 0; k < NOPS; ++k) RV::fma_raw(d[k][u], vv[k][u], acc[k]);
     }
     if (!next_issued) {                                     // no group of this warp had entries
       if (more) load_batch(base + LPR, end, nc, nv);
@@ -374,6 +393,11 @@ __global__ void __launch_bounds__(256) spmm_long_rows_kernel(const SpmmParams p,
   const bool lane_active = l < p.lpr_active;
   const int64_t lane_off = int64_t(l) * (W * 4);
   const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+  const char* xb[NOPS];
+  uint32_t ldx32[NOPS];
+#pragma unroll
+  for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + lane_off, ldx32[k] = uint32_t(p.ldx_bytes[k]);
+  const char* zrow = zero_row_ptr() + lane_off;     // what lanes without an entry gather
   const int total = __ldg(chunk_ptr + n_long);
   for (int ck = blockIdx.x * 8 + (threadIdx.x >> 5); ck < total; ck += gridDim.x * 8) {
     int lo = 0, hi = n_long;                       // largest i with chunk_ptr[i] <= ck
@@ -401,7 +425,7 @@ __global__ void __launch_bounds__(256) spmm_long_rows_kernel(const SpmmParams p,
       }
       const int cnt = min(32, end - base);
       for (int j = 0; j < cnt; j += G * 4) {
-        float d[NOPS][4][EPL], vv[NOPS][4];
+        float d[NOPS][4][W], vv[NOPS][4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int idx = j + u * G + g;
@@ -411,16 +435,13 @@ __global__ void __launch_bounds__(256) spmm_long_rows_kernel(const SpmmParams p,
           for (int k = 0; k < NOPS; ++k) {
             const float t = __shfl_sync(FULL, v[k], idx & 31);
             vv[k][u] = ok ? t : 0.f;
-            if (ok) RV::gather(p.x[k] + int64_t(cc) * p.ldx_bytes[k] + lane_off, pol_keep, d[k][u]);
-            else RV::zero(d[k][u]);
+            RV::gather_raw(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, pol_keep, d[k][u]);
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int k = 0; k < NOPS; ++k)
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vv[k][u], d[k][u][i], acc[k][i]);
+          for (int k = 0; k < NOPS; ++k) RV::fma_raw(d[k][u], vv[k][u], acc[k]);
       }
     }
 #pragma unroll
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const char* x, int64_t
 template <int W, int LPR, int NOPS, int U, bool BF16>
 static int launch_groups(const SpmmParams& p, cudaStream_t st) {
   constexpr int THREADS = 256;
-  constexpr int MINB = (NOPS * U * (BF16 ? 2 * W : W) >= 64) ? 2 : 3;   // fp32 values held per lane
+  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
   constexpr int G = 32 / LPR;
   auto kern = spmm_groups_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
   int occ = 0;
@@ -538,7 +559,7 @@ static int launch_rows(const SpmmParams& p, cudaStream_t st) {
   if (p.use_groups) return launch_groups<W, LPR, NOPS, (U > 4 ? 4 : U), BF16>(p, st);
   constexpr int THREADS = 256;
   // register budget: keep >= 3 CTAs (24 warps) resident when the tile is small
-  constexpr int MINB = (NOPS * U * (BF16 ? 2 * W : W) >= 64) ? 2 : 3;   // fp32 values held per lane
+  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
   auto kern = spmm_rows_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
   int occ = 0;
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
@@ -630,6 +651,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   for (int k = 0; k < a->n_ops; ++k) {
     PGSD_REQUIRE(a->x[k] && a->y[k], "spmm: x[%d]/y[%d] is null", k, k);
     PGSD_REQUIRE(a->ldx[k] >= a->feat && a->ldy[k] >= a->feat, "spmm: leading dim < feat");
+    PGSD_REQUIRE(a->ldx[k] * es < (int64_t(1) << 32), "spmm: row stride of x must be below 4 GiB");
     p.val[k] = a->val[k];
     p.diag[k] = a->diag[k];
     p.diag_const[k] = a->diag_const[k];
