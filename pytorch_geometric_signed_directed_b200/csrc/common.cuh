@@ -119,16 +119,11 @@ __device__ __forceinline__ float8 ld_gather_v8(const void* p) {
       : "l"(p));
   return r;
 }
-// Gathers of a batch are issued UNCONDITIONALLY: lanes without an entry read a zero row instead of
-// being predicated off.  "ok ? load : 0" -- in C++ or as a predicated PTX load over zero-initialised
-// registers -- makes ptxas load into temporaries and select with MOVs that wait on the data in the
-// middle of the gather sequence, which delays the later loads of the batch (ncu source page,
-// profiles/README.md session 13).  With an address select the data lands in its final registers
-// and the U * n_ops loads go out back to back.  The zero row (not x[0]: 0 * inf would poison the sum
-// if a feature row held non-finite values) lives in device memory and stays L2-resident.
-__device__ __align__(128) const float g_zero_row[256] = {0.f};
-__device__ __forceinline__ const char* zero_row_ptr() { return reinterpret_cast<const char*>(g_zero_row); }
-
+// Gathers into caller-named registers (raw 32-bit words; bf16 pairs are expanded at FMA time so that no
+// ALU work that waits on a load sits between the U * n_ops gathers of a batch).  Lanes without an entry
+// skip the load (`if (ok) load; else zero;` -- ptxas if-converts it to a predicated LDG over zeroed
+// registers).  Do NOT replace the predication by a dummy address: every idle lane of the GPU then hits
+// the same L2 sector and the kernels run 2x slower (profiles/README.md, session 14).
 __device__ __forceinline__ void ld_gather_v4_to(const void* p, uint64_t pol, float (&w)[4]) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3])

@@ -34,7 +34,7 @@ constexpr int F_IN = 64;
 constexpr int N_OUT = 64;
 constexpr int TILE_M = 128;
 constexpr int CW = 4;                                   // consumer warps = warps 0..3
-constexpr int LPR = 16, U = 4, NOPS = 2;
+constexpr int LPR = 16, NOPS = 2;
 constexpr int ROW_BYTES = F_IN * 4;
 constexpr int STAGE_HALF = TILE_M * 128;                // one [128 x 32] fp32 SW128 image
 constexpr int STAGING_BYTES = 2 * STAGE_HALF;           // hi + lo
@@ -78,7 +78,7 @@ __device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int PW>
+template <int PW, int U>
 __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(const __grid_constant__ Params p) {
   constexpr int THREADS = (PW + CW) * 32;
   constexpr unsigned FULL = 0xffffffffu;
@@ -232,7 +232,6 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
     uint32_t ldx32[NOPS];
 #pragma unroll
     for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + l * 16, ldx32[k] = uint32_t(p.ldx_bytes[k]);
-    const char* zrow = zero_row_ptr() + l * 16;      // what lanes without an entry gather
 
     // ticket t -> row (t & 127) of this CTA's (t >> 7)-th tile; row_of() < 0: no tile left
     auto row_of = [&](int t) -> int {
@@ -272,54 +271,58 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
     for (int k = 0; k < NOPS; ++k)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
-    bool pending = false;      // row finished, waiting for its ring slot; (c, v) already hold the next row's batch
+    int pending = 0;           // row finished, waiting for its ring slot; (c, v) already hold the next row's batch
 
+    // Booleans are kept out of the gather section on purpose: with more than ~4 live predicates next
+    // to the U "entry exists" predicates, ptxas recycles a predicate register between the gathers of a
+    // batch, which forces the zero/select of an earlier gather (a wait on its data) in front of the
+    // later loads (ncu source page, session 13).  The section below needs only ok[u] and the loop test.
     while (__any_sync(FULL, live)) {
-      const bool active = live && !pending;
-      const int cnt = active ? min(LPR, end - base) : 0;
-      const bool more = active && (base + LPR < end);
+      const int cnt = (live && !pending) ? min(LPR, end - base) : 0;        // <= 0: nothing to gather
+      // index range to prefetch in this iteration: the row's next batch, else the next row's first one
+      int pf_b = 0, pf_e = 0;
+      if (live && !pending) {
+        if (base + LPR < end) pf_b = base + LPR, pf_e = end;
+        else pf_b = nstart, pf_e = nend;
+      }
       int nc = 0;
       float nv[NOPS] = {0.f, 0.f};
-      bool next_issued = false;
+      const bool ran = __any_sync(FULL, cnt > 0);
+      // Every gather of a pass is issued UNCONDITIONALLY and its FFMAs are predicated instead: a slot
+      // past the end of the batch re-reads the batch's last neighbour row (an L2 hit, a different row
+      // for every group -- not one hot sector), an idle group reads a row of its next batch.  With
+      // predicated loads ptxas zero-fills through MOV/selects that wait on the data in the middle
+      // of the gather sequence, which delayed the last gather and the index prefetch of every pass
+      // by one memory round trip (ncu source page, sessions 13-14).
+      const int last = cnt > 0 ? cnt - 1 : 0;
       for (int jj = 0; __any_sync(FULL, jj < cnt); jj += U) {
         float d[NOPS][U][4];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int idx = jj + u;
-          const int cc = __shfl_sync(FULL, c, idx & (LPR - 1), LPR);
-          const bool ok = idx < cnt;
+          const int cc = __shfl_sync(FULL, c, min(jj + u, last), LPR);
 #pragma unroll
-          for (int k = 0; k < NOPS; ++k) ld_gather_v4_plain_to(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, d[k][u]);
+          for (int k = 0; k < NOPS; ++k) ld_gather_v4_plain_to(row_addr(xb[k], cc, ldx32[k]), d[k][u]);
         }
-        if (!next_issued) {
-          // next index batch (same row, or the first batch of the group's next row) goes out right
-          // behind the first gathers
-          if (active) {
-            if (more) load_batch(base + LPR, end, nc, nv);
-            else load_batch(nstart, nend, nc, nv);
-          }
-          next_issued = true;
-        }
-        // lanes without an entry gathered the zero row: no select needed
+        // the next index batch goes out right behind the gathers
+        if (jj == 0) load_batch(pf_b, pf_e, nc, nv);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int k = 0; k < NOPS; ++k) {
             const float t = __shfl_sync(FULL, v[k], (jj + u) & (LPR - 1), LPR);
+            if (jj + u < cnt) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(t, d[k][u][i], acc[k][i]);
+              for (int i = 0; i < 4; ++i) acc[k][i] = fmaf(t, d[k][u][i], acc[k][i]);
+            }
           }
       }
-      if (active) {
-        if (!next_issued) {
-          if (more) load_batch(base + LPR, end, nc, nv);
-          else load_batch(nstart, nend, nc, nv);
-        }
+      if (!ran) load_batch(pf_b, pf_e, nc, nv);       // no group of this warp had entries
+      if (live && !pending) {
         c = nc;
 #pragma unroll
         for (int k = 0; k < NOPS; ++k) v[k] = nv[k];
-        if (more) base += LPR;
-        else pending = true;
+        if (base + LPR < end) base += LPR;
+        else pending = 1;
       }
       if (pending) {
         const int cj = ct >> 7, slot = cj & 1;
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
           // advance to the row whose pointers and first batch are already here
           ct += NG, base = nstart, end = nend;
           live = row_of(ct) >= 0;
-          pending = false;
+          pending = 0;
           load_ptrs(row_of(ct + NG), nstart, nend);
         }
       }
@@ -369,9 +372,9 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) magnet_layer_fused_kernel(c
   }
 }
 
-template <int PW>
+template <int PW, int U>
 static int launch(const Params& p, cudaStream_t st) {
-  auto kern = magnet_layer_fused_kernel<PW>;
+  auto kern = magnet_layer_fused_kernel<PW, U>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int64_t grid = sm_count();
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -428,5 +431,10 @@ extern "C" int pgsd_magnet_layer_fused(const pgsd_magnet_fused_args* a, pgsd_str
     p.ldy_bytes[k] = a->ldy[k] * 4;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return a->variant == 1 ? launch<24>(p, st) : launch<20>(p, st);
+  switch (a->variant) {
+    case 1: return launch<20, 4>(p, st);
+    case 2: return launch<20, 2>(p, st);
+    case 3: return launch<24, 2>(p, st);
+    default: return launch<16, 4>(p, st);   // 640 threads -> 96 registers: the 8 gathers of a batch get 8 register quads
+  }
 }

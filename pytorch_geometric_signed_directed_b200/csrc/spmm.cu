@@ -86,6 +86,10 @@ struct RowVec {
     if constexpr (W == 8) ld_gather_v8_to(p, w);
     else ld_gather_v4_to(p, pol, w);
   }
+  static __device__ __forceinline__ void zero_raw(float (&w)[W]) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) w[i] = 0.f;
+  }
   static __device__ __forceinline__ void fma_raw(const float (&w)[W], float v, float (&acc)[EPL]) {
     if constexpr (BF16) {
 #pragma unroll
@@ -142,7 +146,6 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
   uint32_t ldx32[NOPS];
 #pragma unroll
   for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + lane_off, ldx32[k] = uint32_t(p.ldx_bytes[k]);
-  const char* zrow = zero_row_ptr() + lane_off;     // what lanes without an entry gather
 
   const int64_t warps_total = int64_t(gridDim.x) * (THREADS / 32);
   int64_t row = int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5);
@@ -181,7 +184,8 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
           for (int k = 0; k < NOPS; ++k) {
             const float t = __shfl_sync(FULL, v[k], idx & 31);
             vv[k][u] = ok ? t : 0.f;
-            RV::gather_raw(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, pol_keep, d[k][u]);
+            if (ok) RV::gather_raw(row_addr(xb[k], cc, ldx32[k]), pol_keep, d[k][u]);
+            else RV::zero_raw(d[k][u]);
           }
         }
 #pragma unroll
@@ -254,7 +258,6 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
   uint32_t ldx32[NOPS];
 #pragma unroll
   for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + lane_off, ldx32[k] = uint32_t(p.ldx_bytes[k]);
-  const char* zrow = zero_row_ptr() + lane_off;     // what lanes without an entry gather
 
   const int64_t groups_total = int64_t(gridDim.x) * (THREADS / 32) * G;
   int64_t row = (int64_t(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5)) * G + g;
@@ -311,7 +314,8 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
         for (int k = 0; k < NOPS; ++k) {
           const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
           vv[k][u] = ok ? t : 0.f;
-          RV::gather_raw(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, pol_keep, d[k][u]);
+          if (ok) RV::gather_raw(row_addr(xb[k], cc, ldx32[k]), pol_keep, d[k][u]);
+            else RV::zero_raw(d[k][u]);
         }
       }
       if (!next_issued) {
@@ -397,7 +401,6 @@ __global__ void __launch_bounds__(256) spmm_long_rows_kernel(const SpmmParams p,
   uint32_t ldx32[NOPS];
 #pragma unroll
   for (int k = 0; k < NOPS; ++k) xb[k] = p.x[k] + lane_off, ldx32[k] = uint32_t(p.ldx_bytes[k]);
-  const char* zrow = zero_row_ptr() + lane_off;     // what lanes without an entry gather
   const int total = __ldg(chunk_ptr + n_long);
   for (int ck = blockIdx.x * 8 + (threadIdx.x >> 5); ck < total; ck += gridDim.x * 8) {
     int lo = 0, hi = n_long;                       // largest i with chunk_ptr[i] <= ck
@@ -435,7 +438,8 @@ __global__ void __launch_bounds__(256) spmm_long_rows_kernel(const SpmmParams p,
           for (int k = 0; k < NOPS; ++k) {
             const float t = __shfl_sync(FULL, v[k], idx & 31);
             vv[k][u] = ok ? t : 0.f;
-            RV::gather_raw(ok ? row_addr(xb[k], cc, ldx32[k]) : zrow, pol_keep, d[k][u]);
+            if (ok) RV::gather_raw(row_addr(xb[k], cc, ldx32[k]), pol_keep, d[k][u]);
+            else RV::zero_raw(d[k][u]);
           }
         }
 #pragma unroll
