@@ -78,21 +78,24 @@ class SGCNConv(torch.nn.Module):
         wb, wu = self.lin_b.weight.t(), self.lin_u.weight.t()          # [mult*in, out] views
         m_pos = ag.spmm(pos, [x_src], (0,), mean=True)[0]
         m_neg = ag.spmm(neg, [x_src], (0,), mean=True)[0]
+        # Both halves of the output in ONE transform launch: lin_b and lin_u become the two column blocks
+        # of block-structured [k, 2*out] weights (zeros where an input does not feed a half), so m_pos,
+        # m_neg and x are each read once and `torch.cat([out_b, out_u])` (SGCNConv.py:121) is the
+        # kernel's output layout.  The zero blocks cost tensor-core flops only (free: HBM-bound).
+        zb = wb.new_zeros((fi, fo))
         if self.first_aggr:
-            terms_b = [(m_pos, wb[:fi], 0), (x_dst, wb[fi:], 0)]
-            terms_u = [(m_neg, wu[:fi], 0), (x_dst, wu[fi:], 0)]
+            terms = [(m_pos, torch.cat([wb[:fi], zb], 1), 0),
+                     (m_neg, torch.cat([zb, wu[:fi]], 1), 0),
+                     (x_dst, torch.cat([wb[fi:], wu[fi:]], 1), 0)]
         else:
             # x = [x_b | x_u]; m_pos = [mean+(x_b) | mean+(x_u)], m_neg = [mean-(x_b) | mean-(x_u)]
-            terms_b = [(m_pos[:, :fi], wb[:fi], 0), (m_neg[:, fi:], wb[fi:2 * fi], 0), (x_dst[:, :fi], wb[2 * fi:], 0)]
-            terms_u = [(m_pos[:, fi:], wu[:fi], 0), (m_neg[:, :fi], wu[fi:2 * fi], 0), (x_dst[:, fi:], wu[2 * fi:], 0)]
-        track = [x_src, x_dst, self.lin_b.weight, self.lin_u.weight, self.lin_b.bias, self.lin_u.bias]
-        if ag._needs_grad(track):
-            out = torch.cat([ag.dense(terms_b, fo, bias=self.lin_b.bias)[0],
-                             ag.dense(terms_u, fo, bias=self.lin_u.bias)[0]], dim=-1)
-        else:   # inference: both halves are written in place into one buffer (no torch.cat)
-            out = torch.empty((n_dst, 2 * fo), dtype=x_src.dtype, device=x_src.device)
-            ops.dense(terms_b, fo, bias=self.lin_b.bias, out=[out[:, :fo]])
-            ops.dense(terms_u, fo, bias=self.lin_u.bias, out=[out[:, fo:]])
+            terms = [(m_pos, torch.cat([torch.cat([wb[:fi], zb], 1), torch.cat([zb, wu[:fi]], 1)], 0), 0),
+                     (m_neg, torch.cat([torch.cat([zb, wu[fi:2 * fi]], 1), torch.cat([wb[fi:2 * fi], zb], 1)], 0), 0),
+                     (x_dst, torch.cat([torch.cat([wb[2 * fi:], zb], 1), torch.cat([zb, wu[2 * fi:]], 1)], 0), 0)]
+        bias = None
+        if self.lin_b.bias is not None:
+            bias = torch.cat([self.lin_b.bias, self.lin_u.bias])
+        out = ag.dense(terms, 2 * fo, bias=bias)[0]
         if self.norm_emb:
             out = F.normalize(out, p=2, dim=-1)
         return out
