@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(DT) dense_ffma_kernel(const DenseParams p) {
 }
 
 int dense_tc_try(const pgsd_dense_args* a, cudaStream_t st, int* handled);  // dense_tc.cu
+int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled); // dense_tma.cu
 
 }  // namespace pgsd
 
@@ -199,6 +200,14 @@ extern "C" int pgsd_dense_transform(const pgsd_dense_args* a, pgsd_stream_t stre
   }
   // variant: 0 = auto (tcgen05 path when the shape fits, else FFMA), 1 = force FFMA,
   // 2 = require the tcgen05 path, 4 = require its warp-specialised kernel
+  // 16 = require the TMA-fed warp-specialised kernel (dense_tma.cu)
+  if (a->variant == 16) {
+    int handled = 0;
+    int rc = dense_tma_try(a, st, &handled);
+    if (rc != PGSD_OK) return rc;
+    if (handled) return PGSD_OK;
+    return fail(PGSD_ERR_INVALID, "dense: shape outside the TMA kernel's envelope");
+  }
   if (a->variant != 1) {
     int handled = 0;
     int rc = dense_tc_try(a, st, &handled);

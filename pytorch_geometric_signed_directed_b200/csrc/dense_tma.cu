@@ -1,0 +1,420 @@
+// TMA-fed, fully warp-specialised tcgen05 kernel of the dense feature transform (same math and
+// envelope as dense_tc.cu: acc_g = sum_t X_t W_t, 3xTF32 for fp32 / kind::f16 for bf16, real/imag mix,
+// bias, optional complex-ReLU mask).
+//
+// Why a second kernel: dense_tc_kernel moves the feature rows global -> registers -> shared memory with
+// every thread playing every role, so the loads of a CTA advance in lock step with its per-chunk
+// barrier, its single MMA-issuing thread and its epilogue (measured 0.52-0.56 ms on 1.54 GB = 2.9 TB/s,
+// profiles/r01_sweep_dense_s14.jsonl).  Here the roles never wait for each other except through
+// mbarriers, and the feature tiles never touch registers or L1 on their way in:
+//   warp 0      : TMA producer -- one thread issues cp.async.bulk.tensor.2d per [128 rows x 128 B] chunk
+//                 (SWIZZLE_128B tensor maps, one per term; rows / k past the end are zero-filled by
+//                 the TMA unit) into an S-stage ring, completion on the stage's `full` mbarrier;
+//   warps 6..13 : converters (fp32 only) -- split the landed chunk in place into TF32 hi (same bytes)
+//                 and lo (second image of the stage), fence.proxy.async, arrive on `conv`;
+//                 bf16 chunks are already MMA operands: no converter warps at all;
+//   warp 1      : MMA issuer -- waits `conv` (fp32) / `full` (bf16), issues the tcgen05.mma chain of the
+//                 chunk, tcgen05.commit -> `empty` (stage back to the producer); the last chunk of a
+//                 tile also commits to `acc_full`;
+//   warps 2..5  : epilogue -- tcgen05.ld of the finished accumulators (TMEM double-buffered, so tile
+//                 t+1 accumulates while tile t is stored), mix/bias/mask, streaming stores.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace pgsd {
+namespace tma {
+using namespace tc;
+
+constexpr int TILE_M = 128;
+constexpr int MAX_TERMS = PGSD_DENSE_MAX_TERMS;
+constexpr int MAX_CHUNKS = 2 * PGSD_DENSE_MAX_TERMS;
+constexpr int MAX_SLABS = 16;
+constexpr int MAX_STAGES = 8;
+constexpr int CHUNK_BYTES = TILE_M * 128;
+constexpr int EPI_WARPS = 4;
+constexpr int CONV_WARPS = 8;
+
+struct alignas(64) Params {
+  CUtensorMap maps[MAX_TERMS];     // one [n_rows, k_t] tensor per term, box = [128 rows, 128 bytes]
+  int64_t n_rows;
+  int32_t n_chunks, n_slabs, relu_mode, n_total, stages, pad;
+  int16_t k0[MAX_CHUNKS];          // first k (elements) of the chunk inside its term
+  int8_t term[MAX_CHUNKS];
+  int8_t group[MAX_CHUNKS];
+  int8_t slab[MAX_CHUNKS];
+  int8_t first[MAX_CHUNKS];        // first chunk of its group inside a tile -> overwrite TMEM
+  const float* w[MAX_SLABS];       // weight base + k0 * ldw_k
+  int64_t ldw_k[MAX_SLABS], ldw_n[MAX_SLABS];
+  int8_t wk[MAX_SLABS];            // valid k rows of the slab
+  const float* bias;
+  char* y[2];
+  int64_t ldy_bytes[2];
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// waits that span a whole pipeline fill (and much more under a profiler): bounded, with back-off
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > 64) __nanosleep(32);
+    if (spins > (1u << 26)) __trap();
+  }
+}
+
+template <int N_OUT, int GROUPS, bool BF16>
+__global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32, 1)
+    dense_tma_kernel(const __grid_constant__ Params p) {
+  constexpr int NCV = BF16 ? 0 : CONV_WARPS;
+  constexpr int THREADS = (2 + EPI_WARPS + NCV) * 32;
+  constexpr int ES = BF16 ? 2 : 4;
+  constexpr int EPC = 16 / ES;
+  constexpr int CK = 128 / ES;
+  constexpr int STAGE_BYTES = BF16 ? CHUNK_BYTES : 2 * CHUNK_BYTES;   // fp32: hi image (in place) + lo image
+  constexpr int HALF = N_OUT * 128;
+  constexpr int SLAB_BYTES = BF16 ? HALF : 2 * HALF;
+  constexpr int UMMA_K_BYTES = 32;
+  constexpr int ACC_COLS = GROUPS * N_OUT;
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64
+                               : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+  constexpr uint32_t FMT = BF16 ? 1u : 2u;
+  constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | (uint32_t(N_OUT >> 3) << 17) |
+                             (uint32_t(TILE_M >> 4) << 24);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint8_t* a_stage = smem;
+  uint8_t* w_smem = smem + S * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.n_slabs * SLAB_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * N_OUT;
+  const uint32_t a_addr = smem_u32(a_stage), w_addr = smem_u32(w_smem);
+  const uint32_t bar_full = smem_u32(bars), bar_conv = bar_full + 8 * MAX_STAGES, bar_empty = bar_conv + 8 * MAX_STAGES;
+  const uint32_t bar_acc_full = bar_empty + 8 * MAX_STAGES, bar_acc_empty = bar_acc_full + 16;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, NCV > 0 ? NCV : 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // weights -> K-major SW128 images (element (n, k) in 16-byte unit (k / EPC) ^ (n & 7) of row n)
+  for (int idx = tid; idx < p.n_slabs * CK * N_OUT; idx += THREADS) {
+    const int s = idx / (CK * N_OUT);
+    const int rem = idx - s * (CK * N_OUT);
+    const int k = rem / N_OUT, n = rem - k * N_OUT;
+    float v = 0.f;
+    if (k < p.wk[s] && n0 + n < p.n_total) v = __ldg(p.w[s] + k * p.ldw_k[s] + (n0 + n) * p.ldw_n[s]);
+    const int off = n * 128 + (((k / EPC) ^ (n & 7)) << 4) + (k % EPC) * ES;
+    if constexpr (BF16) {
+      *reinterpret_cast<__nv_bfloat16*>(w_smem + s * SLAB_BYTES + off) = __float2bfloat16_rn(v);
+    } else {
+      const float hi = to_tf32(v), lo = to_tf32(v - hi);
+      *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + off) = hi;
+      *reinterpret_cast<float*>(w_smem + s * SLAB_BYTES + HALF + off) = lo;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer
+    uint32_t uses = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int c = 0; c < p.n_chunks; ++c, ++uses) {
+        const uint32_t stage = uses % S;
+        if (lane == 0) {
+          if (uses >= uint32_t(S)) mbar_wait_relaxed(bar_empty + 8 * stage, ((uses / S) - 1) & 1);
+          mbar_expect_tx(bar_full + 8 * stage, CHUNK_BYTES);
+          tma_load_2d(a_addr + stage * STAGE_BYTES, &p.maps[p.term[c]], p.k0[c], int(tile * TILE_M),
+                      bar_full + 8 * stage);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ========================================================================== MMA issuer
+    uint32_t uses = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      if (it >= 2) mbar_wait_relaxed(bar_acc_empty + 8 * acc, ((it >> 1) - 1) & 1);   // epilogue drained this buffer
+      for (int c = 0; c < p.n_chunks; ++c, ++uses) {
+        const uint32_t stage = uses % S;
+        mbar_wait_relaxed((BF16 ? bar_full : bar_conv) + 8 * stage, (uses / S) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t d = tmem_base + acc * ACC_COLS + uint32_t(p.group[c]) * N_OUT;
+          const uint32_t a_hi = a_addr + stage * STAGE_BYTES, a_lo = a_hi + CHUNK_BYTES;
+          const uint32_t w_hi = w_addr + uint32_t(p.slab[c]) * SLAB_BYTES, w_lo = w_hi + HALF;
+#pragma unroll
+          for (int j = 0; j < 128 / UMMA_K_BYTES; ++j) {
+            const uint32_t ko = j * UMMA_K_BYTES;
+            const uint32_t acc0 = (p.first[c] && j == 0) ? 0u : 1u;
+            if constexpr (BF16) {
+              mma_bf16(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
+            } else {
+              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
+              mma_tf32(d, make_desc(a_lo + ko), make_desc(w_hi + ko), IDESC, 1u);
+              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_lo + ko), IDESC, 1u);
+            }
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (c == p.n_chunks - 1) tc_commit(bar_acc_full + 8 * acc);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + EPI_WARPS) {
+    // ============================================================================ epilogue
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const uint64_t pol_stream = policy_evict_first();
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait_relaxed(bar_acc_full + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = tile * TILE_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
+#pragma unroll 1
+      for (int cb = 0; cb < N_OUT / 16; ++cb) {
+        float a[16], b[16];
+        tmem_ld<16>(taddr + cb * 16, a);
+        if (GROUPS == 2) tmem_ld<16>(taddr + N_OUT + cb * 16, b);
+        tmem_ld_wait();
+        if (cb == N_OUT / 16 - 1) {              // everything of this buffer is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+        }
+        const int ncol = n0 + cb * 16;
+        if (row < p.n_rows && ncol < p.n_total) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float bs = p.bias ? __ldg(p.bias + ncol + i) : 0.f;
+            if (GROUPS == 2) {
+              const float o0 = (a[i] - b[i]) + bs, o1 = (a[i] + b[i]) + bs;
+              const float m = (p.relu_mode == 1 && !(o0 >= 0.f)) ? 0.f : 1.f;
+              a[i] = p.relu_mode == 1 ? o0 * m : o0;
+              b[i] = p.relu_mode == 1 ? o1 * m : o1;
+            } else {
+              a[i] = a[i] + bs;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < GROUPS; ++g) {
+            const float* o = g ? b : a;
+            char* yp = p.y[g] + row * p.ldy_bytes[g] + int64_t(ncol) * ES;
+            if constexpr (BF16) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 8) {
+                float4 pk;
+                pk.x = __uint_as_float(pack_bf16(o[i], o[i + 1]));
+                pk.y = __uint_as_float(pack_bf16(o[i + 2], o[i + 3]));
+                pk.z = __uint_as_float(pack_bf16(o[i + 4], o[i + 5]));
+                pk.w = __uint_as_float(pack_bf16(o[i + 6], o[i + 7]));
+                st_stream_v4(yp + i * 2, pk, pol_stream);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                st_stream_v4(yp + i * 4, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]), pol_stream);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================ converters (fp32 only)
+    if constexpr (!BF16) {
+      const int ct = tid - (2 + EPI_WARPS) * 32;           // 0 .. NCV*32-1
+      constexpr int UNITS = CHUNK_BYTES / 16 / (NCV * 32);  // 16-byte units per thread and chunk
+      uint32_t uses = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < p.n_chunks; ++c, ++uses) {
+          const uint32_t stage = uses % S;
+          mbar_wait_relaxed(bar_full + 8 * stage, (uses / S) & 1);
+          uint8_t* hi = a_stage + stage * STAGE_BYTES;
+          uint8_t* lo = hi + CHUNK_BYTES;
+          float4 v[UNITS];
+#pragma unroll
+          for (int i = 0; i < UNITS; ++i) v[i] = *reinterpret_cast<const float4*>(hi + (ct + i * NCV * 32) * 16);
+#pragma unroll
+          for (int i = 0; i < UNITS; ++i) {
+            // the split is position-independent: unit q of the landed (swizzled) image stays unit q
+            float4 vh, vl;
+            vh.x = to_tf32(v[i].x), vh.y = to_tf32(v[i].y), vh.z = to_tf32(v[i].z), vh.w = to_tf32(v[i].w);
+            vl.x = to_tf32(v[i].x - vh.x), vl.y = to_tf32(v[i].y - vh.y);
+            vl.z = to_tf32(v[i].z - vh.z), vl.w = to_tf32(v[i].w - vh.w);
+            *reinterpret_cast<float4*>(hi + (ct + i * NCV * 32) * 16) = vh;
+            *reinterpret_cast<float4*>(lo + (ct + i * NCV * 32) * 16) = vl;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_conv + 8 * stage);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages) {
+  return 1024 + size_t(stages) * (bf16 ? 1 : 2) * CHUNK_BYTES + size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 +
+         8 * (3 * MAX_STAGES + 4) + 16;
+}
+
+template <int N_OUT, int GROUPS, bool BF16>
+static int launch(Params& p, cudaStream_t st) {
+  int stages = MAX_STAGES;
+  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages) > 220 * 1024) --stages;
+  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages) > 220 * 1024) return -1;
+  p.stages = stages;
+  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages);
+  auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16>;
+  PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+  const int n_col_tiles = (p.n_total + N_OUT - 1) / N_OUT;
+  int64_t gx = sm_count() / n_col_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > n_tiles) gx = n_tiles;
+  constexpr int THREADS = (2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32;
+  kern<<<dim3(unsigned(gx), unsigned(n_col_tiles)), THREADS, smem, st>>>(p);
+  PGSD_LAUNCH_CHECK("dense_tma_kernel");
+  return PGSD_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no -lcuda at link time
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static inline bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+}  // namespace tma
+
+// Same contract as dense_tc_try: *handled = 1 when this kernel ran.
+int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
+  using namespace tma;
+  *handled = 0;
+  EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr) return PGSD_OK;
+  const bool bf16 = a->dtype == PGSD_BF16;
+  const int es = bf16 ? 2 : 4, ck = 128 / es, kal = 16 / es;
+  const int n = a->n_out;
+  int n_tile = 0;
+  if (n == 16 || n == 32 || n == 64 || n == 128) n_tile = n;
+  else if (n > 128 && n % 128 == 0) n_tile = 128;
+  if (n_tile == 0 || (bf16 && n_tile < 32)) return PGSD_OK;
+  if (a->n_rows <= 0 || a->n_rows >= (int64_t(1) << 31)) return PGSD_OK;
+  const int groups = a->combine ? 2 : 1;
+  static thread_local Params p;                 // 64-byte aligned, ~2.7 KB: keep it off the stack
+  p = Params{};
+  p.n_rows = a->n_rows;
+  p.n_total = n;
+  p.relu_mode = a->relu_mode;
+  p.bias = a->bias;
+  for (int i = 0; i < groups; ++i) {
+    if (!al16(a->y[i]) || ((a->ldy[i] * es) & 15)) return PGSD_OK;
+    p.y[i] = static_cast<char*>(a->y[i]);
+    p.ldy_bytes[i] = a->ldy[i] * es;
+  }
+  bool seen_group[2] = {false, false};
+  for (int t = 0; t < a->n_terms; ++t) {
+    const char* x = static_cast<const char*>(a->x[t]);
+    if (!al16(x) || ((a->ldx[t] * es) & 15) || (a->k[t] % kal) || a->k[t] == 0 || a->k[t] > 32000) return PGSD_OK;
+    const cuuint64_t gdim[2] = {cuuint64_t(a->k[t]), cuuint64_t(a->n_rows)};
+    const cuuint64_t gstride[1] = {cuuint64_t(a->ldx[t]) * es};
+    const cuuint32_t box[2] = {cuuint32_t(ck), cuuint32_t(TILE_M)};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = enc(&p.maps[t], bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<char*>(x), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return PGSD_OK;     // e.g. a stride the TMA unit cannot express -> other kernels
+    for (int k0 = 0; k0 < a->k[t]; k0 += ck) {
+      if (p.n_chunks >= MAX_CHUNKS) return PGSD_OK;
+      const int kv = (a->k[t] - k0) < ck ? (a->k[t] - k0) : ck;
+      const float* wb = a->w[t] + int64_t(k0) * a->ldw_k[t];
+      int s = -1;
+      for (int j = 0; j < p.n_slabs; ++j)
+        if (p.w[j] == wb && p.ldw_k[j] == a->ldw_k[t] && p.ldw_n[j] == a->ldw_n[t] && p.wk[j] == kv) s = j;
+      if (s < 0) {
+        if (p.n_slabs >= MAX_SLABS) return PGSD_OK;
+        s = p.n_slabs++;
+        p.w[s] = wb, p.ldw_k[s] = a->ldw_k[t], p.ldw_n[s] = a->ldw_n[t], p.wk[s] = int8_t(kv);
+      }
+      const int c = p.n_chunks++;
+      p.term[c] = int8_t(t);
+      p.k0[c] = int16_t(k0);
+      p.group[c] = int8_t(a->group[t]);
+      p.slab[c] = int8_t(s);
+      p.first[c] = seen_group[a->group[t]] ? 0 : 1;
+      seen_group[a->group[t]] = true;
+    }
+  }
+  if (groups == 2 && !(seen_group[0] && seen_group[1])) return PGSD_OK;
+  int rc = -1;
+#define PGSD_TMA(N_)                                                                                \
+  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st) : launch<N_, 1, true>(p, st);             \
+  else rc = groups == 2 ? launch<N_, 2, false>(p, st) : launch<N_, 1, false>(p, st);                \
+  break;
+  switch (n_tile) {
+    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st) : launch<16, 1, false>(p, st); break;
+    case 32: PGSD_TMA(32)
+    case 64: PGSD_TMA(64)
+    default: PGSD_TMA(128)
+  }
+#undef PGSD_TMA
+  if (rc == -1) return PGSD_OK;                  // does not fit in shared memory
+  if (rc == PGSD_OK) *handled = 1;
+  return rc;
+}
+
+}  // namespace pgsd

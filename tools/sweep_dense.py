@@ -53,16 +53,20 @@ with torch.no_grad():
     w = torch.rand(2, f, f, device=dev) - 0.5
     b = torch.rand(f, device=dev)
     case("magnet_combine_1M_4x64_64_f32", [(xs[0], w[0], 0), (xs[1], w[0], 1), (xs[2], w[1], 0), (xs[3], w[1], 1)],
-         f, 6 * n * f * 4, (0, 4, 8, 1), bias=b, combine=True)
+         f, 6 * n * f * 4, (0, 16, 1), bias=b, combine=True)
     del xs
     n, f = 500_000, 128
     x = (torch.rand(n, f, device=dev) * 2 - 1).bfloat16()
     w3 = torch.rand(f, 3 * f, device=dev) - 0.5
-    case("inception_500k_128_384_bf16", [(x, w3, 0)], 3 * f, n * f * 2 * 4, (0, 4, 8, 1))
+    case("inception_500k_128_384_bf16", [(x, w3, 0)], 3 * f, n * f * 2 * 4, (0, 16, 1))
     xf = x.float()
-    case("inception_500k_128_384_f32", [(xf, w3, 0)], 3 * f, n * f * 4 * 4, (0, 8, 1))
+    case("inception_500k_128_384_f32", [(xf, w3, 0)], 3 * f, n * f * 4 * 4, (0, 16, 1))
     del x, xf
     n = 2_000_000
     xa, xb = torch.randn(n, 64, device=dev), torch.randn(n, 64, device=dev)
     w2 = torch.rand(128, 32, device=dev) - 0.5
-    case("sgcn_2M_2x64_32_f32", [(xa, w2[:64], 0), (xb, w2[64:], 0)], 32, n * (128 + 32) * 4, (0, 8, 1))
+    case("sgcn_2M_2x64_32_f32", [(xa, w2[:64], 0), (xb, w2[64:], 0)], 32, n * (128 + 32) * 4, (0, 16, 1))
+    xc = torch.randn(n, 64, device=dev)
+    w4 = torch.rand(192, 64, device=dev) - 0.5
+    case("sgcn_merged_2M_3x64_64_f32", [(xa, w4[:64], 0), (xb, w4[64:128], 0), (xc, w4[128:], 0)], 64,
+         n * (192 + 64) * 4, (0, 16, 1), bias=torch.rand(64, device=dev))
