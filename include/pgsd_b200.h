@@ -224,7 +224,10 @@ typedef struct pgsd_dense_args {
   int64_t ldy[2];
   int32_t relu_mode;         /* 0 none; 1 complex ReLU (mask = y0 >= 0 applied to y0, y1):
                                 nn/directed/complex_relu.py:17-34 (combine == 1 only)   */
-  int32_t variant;
+  int32_t variant;           /* 0 = auto: TMA-fed warp-specialised tcgen05 kernel, else the
+                                register-staged tcgen05 kernel, else FFMA; 1 = FFMA; 2 / 4 / 8 =
+                                register-staged tcgen05 (synchronous / warp-specialised / deep
+                                prefetch); 16 = require the TMA-fed kernel                  */
 } pgsd_dense_args;
 
 PGSD_API int pgsd_dense_transform(const pgsd_dense_args* args, pgsd_stream_t stream);
@@ -259,7 +262,7 @@ typedef struct pgsd_magnet_fused_args {
   float* y[2];               /* out_real, out_imag [N, ldy]                            */
   int64_t ldy[2];
   int32_t relu_mode;         /* as pgsd_dense_args                                     */
-  int32_t variant;           /* 0 = default; 1 = 24 producer warps instead of 20       */
+  int32_t variant;           /* producer warps x gathers in flight: 0 = 16x4, 1 = 20x4, 2 = 20x2, 3 = 24x2 */
 } pgsd_magnet_fused_args;
 
 PGSD_API int pgsd_magnet_fused_supported(int32_t feat_in, int32_t feat_out, int32_t dtype);

@@ -20,7 +20,8 @@ _DT = {torch.float32: _lib.PGSD_F32, torch.bfloat16: _lib.PGSD_BF16}
 # tuning knob for experiments (tools/sweep_spmm.py); 0 = library default
 SPMM_VARIANT = int(os.environ.get("PGSD_SPMM_VARIANT", "0"))
 
-# 0 = auto (tcgen05 3xTF32 path when the shape fits, else FFMA), 1 = force FFMA, 2 = require tcgen05
+# 0 = auto (TMA-fed tcgen05 kernel when the shape fits, else register-staged tcgen05, else FFMA),
+# 1 = force FFMA, 2 = require the register-staged tcgen05 kernel, 16 = require the TMA-fed kernel
 DENSE_VARIANT = int(os.environ.get("PGSD_DENSE_VARIANT", "0"))
 
 # rows with more stored entries than this are aggregated by the hub-row kernel in slices
