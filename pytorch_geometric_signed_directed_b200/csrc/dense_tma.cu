@@ -260,11 +260,10 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
         for (int c = 0; c < p.n_chunks; ++c, ++uses) {
           const uint32_t stage = uses % S;
           mbar_wait_relaxed(bar_full + 8 * stage, (uses / S) & 1);
-          uint8_t* hi = a_stage + stage * STAGE_BYTES;
-          uint8_t* lo = hi + CHUNK_BYTES;
+          const uint32_t hi = a_addr + stage * STAGE_BYTES + ct * 16, lo = hi + CHUNK_BYTES;
           float4 v[UNITS];
 #pragma unroll
-          for (int i = 0; i < UNITS; ++i) v[i] = *reinterpret_cast<const float4*>(hi + (ct + i * NCV * 32) * 16);
+          for (int i = 0; i < UNITS; ++i) v[i] = lds_v4(hi + i * NCV * 32 * 16);
 #pragma unroll
           for (int i = 0; i < UNITS; ++i) {
             // the split is position-independent: unit q of the landed (swizzled) image stays unit q
@@ -272,8 +271,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
             vh.x = to_tf32(v[i].x), vh.y = to_tf32(v[i].y), vh.z = to_tf32(v[i].z), vh.w = to_tf32(v[i].w);
             vl.x = to_tf32(v[i].x - vh.x), vl.y = to_tf32(v[i].y - vh.y);
             vl.z = to_tf32(v[i].z - vh.z), vl.w = to_tf32(v[i].w - vh.w);
-            *reinterpret_cast<float4*>(hi + (ct + i * NCV * 32) * 16) = vh;
-            *reinterpret_cast<float4*>(lo + (ct + i * NCV * 32) * 16) = vl;
+            sts_v4(hi + i * NCV * 32 * 16, vh);
+            sts_v4(lo + i * NCV * 32 * 16, vl);
           }
           fence_async_smem();
           __syncwarp();

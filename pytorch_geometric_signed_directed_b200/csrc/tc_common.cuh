@@ -132,6 +132,19 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t da, uint64_t 
       : "memory");
 }
 
+// Explicit shared-space 128-bit accesses by 32-bit shared address.  The dynamic shared memory base is
+// rounded up to 1024 B through an integer cast, after which the compiler no longer knows the pointer
+// is shared and emits generic LD.E / ST.E (slower path, long-scoreboard latency) -- seen in the SASS
+// of the converter warps, session 17.
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
