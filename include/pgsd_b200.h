@@ -325,6 +325,41 @@ PGSD_API int pgsd_magnetic_q_grad(const int32_t* row_ptr, const int32_t* col, co
                                   const float* x_real, int64_t ldxr, const float* x_imag, int64_t ldxi,
                                   double scale, double* dq, pgsd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Sparse preprocessing primitives.  The reference prepares DiGCN / DGCN inputs with
+ * DENSE N x N matrices on the CPU (a dense (N+1)^2 eigen-decomposition and dense products):
+ *   utils/directed/get_adjs_DiGCN.py:113-190 (get_appr_directed_adj), :193-254 (get_second_directed_adj),
+ *   utils/directed/features_in_out.py:44-46 (directed_features_in_out).
+ * pytorch_geometric_signed_directed_b200/utils/directed.py composes the same operators from:
+ * ---------------------------------------------------------------------------------- */
+
+/* Sort COO entries by key (= row * n + col, < 2^key_bits) and sum the values of equal keys
+ * (torch.sparse_coo_tensor(...).to_dense() / torch.nonzero order of the reference: row-major).
+ * keys_out / vals_out need capacity n_entries; *n_unique_host = entries written. */
+PGSD_API int pgsd_coalesce_workspace_bytes(int64_t n_entries, size_t* bytes_host);
+PGSD_API int pgsd_coo_coalesce(const int64_t* keys, const float* vals, int64_t n_entries, int key_bits,
+                               int64_t* keys_out, float* vals_out, int64_t* n_unique_host, void* workspace,
+                               size_t workspace_bytes, pgsd_stream_t stream);
+
+/* Expand step of C = B^T diag(scale) B for a CSR matrix B [n_rows x n_cols]: row k with len_k entries
+ * emits its len_k^2 products (key = col[a] * n_cols + col[b], value = scale[k] * val[a] * val[b]);
+ * product_offsets [n_rows + 1] = exclusive prefix of len_k^2 (int64), n_products = its last element.
+ * Followed by pgsd_coo_coalesce this is an expand-sort-compress SpGEMM: P^T P and P P^T of
+ * get_adjs_DiGCN.py:231-232, A^T D^-1 A and A D^-1 A^T of features_in_out.py:44-46.
+ * val / scale may be NULL (ones). */
+PGSD_API int pgsd_gram_expand(const int32_t* row_ptr, const int32_t* col, const float* val, const float* scale,
+                              const int64_t* product_offsets, int64_t n_rows, int64_t n_cols,
+                              int64_t n_products, int64_t* keys_out, float* vals_out, pgsd_stream_t stream);
+
+/* Stationary vector of the personalised-PageRank chain of get_adjs_DiGCN.py:147-160 (the dense
+ * scipy.linalg.eig of an (N+1) x (N+1) matrix) by sparse fp64 power iteration:
+ *   pi = (1 - alpha) P^T pi + alpha / ((1 + alpha) N),   pi <- pi / sum(pi) is left to the caller.
+ * (row_ptr_dst, col_src, p) is P in CSR by DESTINATION (row j lists sources i with p[i -> j]).
+ * pi, scratch: [n] doubles.  The error contracts by (1 - alpha) per iteration. */
+PGSD_API int pgsd_ppr_stationary(const int32_t* row_ptr_dst, const int32_t* col_src, const float* p,
+                                 int64_t n, double alpha, int32_t n_iter, double* pi, double* scratch,
+                                 pgsd_stream_t stream);
+
 /* Halo pack for the node-range sharded path (no reference counterpart: the reference is
  * single-device): out[i, :] = x[index[i], :]  -- rows another rank asked for. */
 PGSD_API int pgsd_gather_rows(const void* x, int64_t ldx, const int32_t* index, int64_t n_index,

@@ -134,6 +134,16 @@ def coalesce(edge_index: Tensor, edge_attr=None, num_nodes: Optional[int] = None
     return out_index, scatter(edge_attr, seg, 0, out_index.size(1), red)
 
 
+def to_undirected(edge_index: Tensor, edge_attr: Optional[Tensor] = None, num_nodes: Optional[int] = None,
+                  reduce: str = 'add'):
+    """PyG to_undirected: both directions of every edge, coalesced (sorted, duplicates merged)."""
+    n = maybe_num_nodes(edge_index, num_nodes)
+    both = torch.cat([edge_index, edge_index.flip(0)], dim=1)
+    if edge_attr is None:
+        return coalesce(both, None, n)
+    return coalesce(both, torch.cat([edge_attr, edge_attr], dim=0), n, reduce)
+
+
 def to_scipy_sparse_matrix(edge_index: Tensor, edge_attr: Optional[Tensor] = None,
                            num_nodes: Optional[int] = None):
     import scipy.sparse as sp
@@ -337,7 +347,7 @@ def install(force: bool = False) -> bool:
     utils.num_nodes = num_nodes
 
     for f in (scatter, coalesce, remove_self_loops, add_self_loops, add_remaining_self_loops,
-              to_scipy_sparse_matrix, softmax, spmm):
+              to_scipy_sparse_matrix, softmax, spmm, to_undirected):
         setattr(utils, f.__name__, f)
     num_nodes.maybe_num_nodes = maybe_num_nodes
     conv.MessagePassing = MessagePassing

@@ -94,6 +94,10 @@ _PROTOTYPES = {
     "pgsd_magnet_layer_fused": (C.c_int, [C.POINTER(MagnetFusedArgs), _vp]),
     "pgsd_edge_softmax": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pgsd_xtg_accumulate": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "pgsd_coalesce_workspace_bytes": (C.c_int, [_i64, C.POINTER(C.c_size_t)]),
+    "pgsd_coo_coalesce": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
+    "pgsd_gram_expand": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "pgsd_ppr_stationary": (C.c_int, [_vp, _vp, _vp, _i64, C.c_double, _i32, _vp, _vp, _vp]),
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
 }
 

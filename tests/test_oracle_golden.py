@@ -170,3 +170,25 @@ def test_trainable_q_gradient_port(name, signed, norm):
     ((o_r * g["r1"]).sum() + (o_i * g["r2"]).sum()).backward()
     assert_close_rel(o_r, g["out_real"], 1e-5)
     assert_close_rel(q.grad, g["d_q"], 1e-4)
+
+
+# ------------------------------------------------------------------ preprocessing
+@pytest.mark.parametrize("name", ["prep_a", "prep_b", "prep_c"])
+def test_port_preprocessing_matches_reference_golden(name):
+    """oracle/port.py's sparse restatements of get_appr_directed_adj / get_second_directed_adj /
+    directed_features_in_out against the reference's own dense-eig / dense-mm / scipy-loop outputs."""
+    g = load_golden(name)
+    ei, n = g["edge_index"], int(g["n"])
+    ew = g["edge_weight"] if g["has_weight"] else None
+    a_ei, a_w = port.appr_directed_adj(float(g["alpha"]), ei, n, ew)
+    assert torch.equal(a_ei, g["appr_index"])
+    # the reference's pi is a float32 LAPACK eigenvector: agreement to a few fp32 ulps of the largest entry
+    assert_close_rel(a_w, g["appr_weight"], 2e-5, "appr weights")
+    s_ei, s_w = port.second_directed_adj(ei, n, ew)
+    assert torch.equal(s_ei, g["second_index"])
+    assert_close_rel(s_w, g["second_weight"], 1e-5, "second-order weights")
+    und, e_in, w_in, e_out, w_out = port.features_in_out(ei, n, ew)
+    assert torch.equal(und, g["undirected"])
+    assert torch.equal(e_in, g["in_index"]) and torch.equal(e_out, g["out_index"])
+    assert_close_rel(w_in, g["in_weight"], 1e-5, "A_in")
+    assert_close_rel(w_out, g["out_weight"], 1e-5, "A_out")
