@@ -44,6 +44,7 @@ struct SpmmParams {
   int use_groups;      // host-side switch: group-per-row kernel for short rows
   int long_thr;        // rows longer than this are aggregated by spmm_long_rows_kernel (0 = off)
   int keep_policy;     // L2 policy of the feature gathers: 0 evict_last (default), 1 normal, 2 evict_first
+  int shared_x;        // n_ops == 2 and both operators read the same matrix: gather once
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -240,7 +241,10 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
 // current row's gathers are outstanding (the index latency leaves the critical path).  Used when
 // the mean row length is small: per-owner column blocks of the sharded path (~deg/world entries
 // per row), low-degree graphs (SGCN's per-sign lists), L2-blocked column segments.
-template <int W, int LPR, int NOPS, int U, bool BF16, int THREADS, int MINB>
+// NX = number of DISTINCT gathered matrices: NOPS, or 1 when both operators read the same x (MagNet's
+// first layer is called with x_real and x_imag being one tensor, examples/magnet_node.py:61-62): the
+// neighbour row is then gathered once and multiplied by both values.
+template <int W, int LPR, int NOPS, int NX, int U, bool BF16, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmParams p) {
   using RV = RowVec<W, BF16>;
   constexpr int EPL = RV::EPL;
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
     for (int k = 0; k < NOPS; ++k) nv[k] = 0.f;
     bool next_issued = false;
     for (int j = 0; __any_sync(FULL, j < cnt); j += U) {
-      float d[NOPS][U][W];
+      float d[NX][U][W];
       float vv[NOPS][U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -314,8 +318,10 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
         for (int k = 0; k < NOPS; ++k) {
           const float t = __shfl_sync(FULL, v[k], idx & (LPR - 1), LPR);
           vv[k][u] = ok ? t : 0.f;
-          if (ok) RV::gather_raw(row_addr(xb[k], cc, ldx32[k]), pol_keep, d[k][u]);
+          if (k < NX) {
+            if (ok) RV::gather_raw(row_addr(xb[k], cc, ldx32[k]), pol_keep, d[k][u]);
             else RV::zero_raw(d[k][u]);
+          }
         }
       }
       if (!next_issued) {
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int k = 0; k < NOPS; ++k) RV::fma_raw(d[k][u], vv[k][u], acc[k]);
+        for (int k = 0; k < NOPS; ++k) RV::fma_raw(d[k < NX ? k : 0][u], vv[k][u], acc[k]);
     }
     if (!next_issued) {                                     // no group of this warp had entries
       if (more) load_batch(base + LPR, end, nc, nv);
@@ -540,12 +546,12 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const char* x, int64_t
 }
 
 // ---- host dispatch -------------------------------------------------------------------------
-template <int W, int LPR, int NOPS, int U, bool BF16>
+template <int W, int LPR, int NOPS, int U, bool BF16, int NX = NOPS>
 static int launch_groups(const SpmmParams& p, cudaStream_t st) {
   constexpr int THREADS = 256;
-  constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
+  constexpr int MINB = (NX * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
   constexpr int G = 32 / LPR;
-  auto kern = spmm_groups_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
+  auto kern = spmm_groups_kernel<W, LPR, NOPS, NX, U, BF16, THREADS, MINB>;
   int occ = 0;
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
   if (occ < 1) occ = 1;
@@ -590,6 +596,20 @@ static int dispatch_lpr(int lpr, const SpmmParams& p, cudaStream_t st) {
   return fail(PGSD_ERR_INVALID, "spmm: bad lanes-per-row %d", lpr);
 }
 
+// two operators over ONE gathered matrix (fp32, group-per-row kernel only)
+template <int W, int U>
+static int dispatch_lpr_shared(int lpr, const SpmmParams& p, cudaStream_t st) {
+  switch (lpr) {
+    case 1: return launch_groups<W, 1, 2, U, false, 1>(p, st);
+    case 2: return launch_groups<W, 2, 2, U, false, 1>(p, st);
+    case 4: return launch_groups<W, 4, 2, U, false, 1>(p, st);
+    case 8: return launch_groups<W, 8, 2, U, false, 1>(p, st);
+    case 16: return launch_groups<W, 16, 2, U, false, 1>(p, st);
+    case 32: return launch_groups<W, 32, 2, U, false, 1>(p, st);
+  }
+  return fail(PGSD_ERR_INVALID, "spmm: bad lanes-per-row %d", lpr);
+}
+
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace pgsd
@@ -613,6 +633,10 @@ static int dispatch_main(const pgsd_spmm_args* a, const SpmmParams& p, int W, in
     }
     if (W == 8) return dispatch_lpr<8, 1, 4, true>(lpr, p, st);
     return dispatch_lpr<4, 1, 4, true>(lpr, p, st);
+  }
+  if (a->n_ops == 2 && p.shared_x) {
+    if (W == 8) return U == 2 ? dispatch_lpr_shared<8, 2>(lpr, p, st) : dispatch_lpr_shared<8, 4>(lpr, p, st);
+    return U == 2 ? dispatch_lpr_shared<4, 2>(lpr, p, st) : dispatch_lpr_shared<4, 4>(lpr, p, st);
   }
   if (a->n_ops == 2) {
     if (W == 8) return U == 2 ? dispatch_lpr<8, 2, 2, false>(lpr, p, st)
@@ -686,12 +710,16 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   p.keep_policy = (a->variant >> 8) & 3;   // experiment knob (bits 8-9), 128-bit gather path only
   const bool can256 = vec32 && row_bytes <= 32 * 32;
   const bool can128 = vec16 && row_bytes <= 32 * 16;
+  // one tensor passed as both operands (variant bit 10 switches the sharing off, for A/B timing)
+  p.shared_x = a->n_ops == 2 && a->dtype == PGSD_F32 && p.use_groups && a->x[0] == a->x[1] &&
+               a->ldx[0] == a->ldx[1] && (a->variant & 0x400) == 0;
+  const int n_gathered = p.shared_x ? 1 : a->n_ops;
   int W = 0;
   if (want256 && can256) W = 8;
   else if (want128 && can128) W = 4;
   // measured defaults (profiles/r01_sweep_v*.jsonl): one operator -> 256-bit gathers with 4 loads
   // in flight (1.68 ms vs 2.21 ms at 40M nnz, F=64); two operators -> 128-bit gathers, U = 4
-  else if (a->n_ops == 1 && can256 && row_bytes >= 128) W = 8;
+  else if (n_gathered == 1 && can256 && row_bytes >= 128) W = 8;
   else if (can128) W = 4;
   else if (can256) W = 8;
 
@@ -710,7 +738,8 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   p.lpr_active = int(row_bytes / (4 * W));
   int lpr = 1;
   while (lpr < p.lpr_active) lpr <<= 1;
-  if (U != 2 && U != 4 && U != 8) U = (W == 8 && a->n_ops == 2) ? 2 : 4;
+  if (U != 2 && U != 4 && U != 8) U = (W == 8 && n_gathered == 2) ? 2 : 4;
+  if (p.shared_x && U == 8) U = 4;
   if (W == 8 && U == 8) U = 4;
 
   const bool hubs = a->n_long_rows > 0 && a->long_rows && a->long_chunk_ptr && a->long_row_threshold > 0 &&

@@ -15,6 +15,15 @@ kernel's `beta * z` epilogue) while round s+1 is in flight:
 
 Real and imaginary features travel interleaved as one [n_local, 2F] buffer, so each neighbour
 gather touches one contiguous 2F*4-byte row.
+
+Graphs whose edge list shards naturally (locality-ordered node ids: most columns of a row shard
+are local, the rest touch a thin band of each peer) take the HALO path instead (`mode="halo"`,
+chosen automatically when every rank needs less than PGSD_HALO_THRESHOLD of the remote rows): the
+plan is analysed once -- sorted unique remote columns per owner, request lists exchanged with an
+all-to-all -- and every step packs the rows each peer asked for (`pgsd_gather_rows`), exchanges
+them with ONE `all_to_all_single` (NCCL over NVLink) that runs while the local-column block is
+aggregated, and then aggregates the remote-column block straight from the received buffer (its
+columns are compact indices into that buffer).
 """
 from __future__ import annotations
 
@@ -76,6 +85,80 @@ def split_columns_by_owner(local: CSRPlan, bounds: Sequence[int], own_rank: int)
                               (col_s[sl] - bounds[b]).int().contiguous(), vals, diags, dconst))
         start += m
     return blocks
+
+
+def split_local_and_halo(local: CSRPlan, bounds: Sequence[int], own_rank: int):
+    """(own_block, halo_block, need): own_block keeps the entries whose column this rank owns
+    (columns re-based to the shard, carries the diagonal); halo_block keeps the others with the
+    column replaced by its position in the sorted list of DISTINCT remote columns -- which is the
+    row order of the receive buffer, because peers are laid out by rank and each sends the rows it
+    was asked for in ascending order.  need[b] = rows of shard b this rank reads (ascending, re-based
+    to shard b, int32); need[own_rank] is empty.  Entry order inside a row is preserved."""
+    dev = local.row_ptr.device
+    n_rows, world = local.n_dst, len(bounds) - 1
+    lo, hi = bounds[own_rank], bounds[own_rank + 1]
+    counts = (local.row_ptr[1:] - local.row_ptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), counts)
+    col = local.col.long()
+    is_own = (col >= lo) & (col < hi)
+
+    def sub_plan(mask, new_col, n_src, with_diag):
+        m = int(mask.sum().item())
+        rp = torch.zeros(n_rows + 1, dtype=torch.int32, device=dev)
+        if m:
+            rp[1:] = torch.cumsum(torch.bincount(rows[mask], minlength=n_rows), 0).int()
+        vals = [None if v is None else v[mask].contiguous() for v in local.val]
+        diags = [d if with_diag else None for d in local.diag]
+        dconst = [c if with_diag else 0.0 for c in local.diag_const]
+        return CSRPlan(n_rows, n_src, m, local.num_input_edges, rp, new_col.int().contiguous(), vals, diags, dconst)
+
+    own_block = sub_plan(is_own, col[is_own] - lo, hi - lo, True)
+    remote = ~is_own
+    uniq, inv = torch.unique(col[remote], sorted=True, return_inverse=True)
+    halo_block = sub_plan(remote, inv, max(int(uniq.numel()), 1), False)
+    b_t = torch.tensor(list(bounds), device=dev, dtype=torch.long)
+    owner = torch.bucketize(uniq, b_t[1:], right=True)
+    per_owner = torch.bincount(owner, minlength=world).tolist()
+    need, start = [], 0
+    for b in range(world):
+        need.append((uniq[start:start + per_owner[b]] - bounds[b]).int().contiguous())
+        start += per_owner[b]
+    return own_block, halo_block, need
+
+
+def _all_to_all(out: Tensor, inp: Tensor, out_splits, in_splits, group=None, async_op: bool = False):
+    """all_to_all_single with row splits (NCCL on the box; gloo implements it for the CPU tests)."""
+    return dist.all_to_all_single(out, inp, list(out_splits), list(in_splits), group=group, async_op=async_op)
+
+
+class HaloExchange:
+    """Request lists of the halo path.  After `setup`, rank r knows for every peer b which of ITS
+    rows b reads (`serve`, concatenated in peer order, with `serve_splits`) and how many rows it
+    receives from each peer (`need_splits`)."""
+
+    def __init__(self, rank: int, world: int, need: Sequence[Tensor], group=None):
+        self.rank, self.world, self.group = rank, world, group
+        dev = need[0].device
+        self.need_splits = [int(t.numel()) for t in need]
+        cnt_out = torch.tensor(self.need_splits, dtype=torch.int64, device=dev)
+        cnt_in = torch.empty_like(cnt_out)
+        _all_to_all(cnt_in, cnt_out, [1] * world, [1] * world, group)
+        self.serve_splits = [int(v) for v in cnt_in.tolist()]
+        req = torch.cat(list(need)) if sum(self.need_splits) else torch.empty(0, dtype=torch.int32, device=dev)
+        self.serve = torch.empty(sum(self.serve_splits), dtype=torch.int32, device=dev)
+        _all_to_all(self.serve, req, self.serve_splits, self.need_splits, group)
+        self.n_recv, self.n_send = sum(self.need_splits), sum(self.serve_splits)
+
+    def start(self, send: Tensor, recv: Tensor):
+        """One all-to-all of packed halo rows: `send` [n_send, w] holds the rows peers asked for,
+        `recv` [n_recv, w] receives the rows this rank asked for.  Returns the async work."""
+        return _all_to_all(recv, send, self.need_splits, self.serve_splits, self.group, async_op=True)
+
+
+def halo_fraction(need: Sequence[Tensor], bounds: Sequence[int], rank: int) -> float:
+    """Share of the REMOTE rows this rank reads (1.0 = the halo is the whole matrix)."""
+    remote = sum(bounds[b + 1] - bounds[b] for b in range(len(bounds) - 1) if b != rank)
+    return float(sum(int(t.numel()) for t in need)) / max(remote, 1)
 
 
 class RingExchange:
@@ -171,12 +254,32 @@ class ShardedAggregator:
     row-sharded plan, with the ring exchange overlapped block by block."""
 
     def __init__(self, local_plan: CSRPlan, bounds: Sequence[int], rank: int, world: int, group=None,
-                 aggregate_fn: Callable = _default_aggregate, mode: Optional[str] = None):
+                 aggregate_fn: Callable = _default_aggregate, mode: Optional[str] = None,
+                 gather_fn: Callable = None):
         self.bounds, self.rank, self.world = list(bounds), rank, world
         # "ring" (default): per-owner column blocks pipelined with the exchange.  "gather": receive
         # every shard into one [N, w] buffer, then ONE launch over all columns (exposes the whole
         # transfer; kept for comparison and for plans whose rows are too short to split).
-        self.mode = mode or os.environ.get("PGSD_SHARD_MODE", "ring")
+        # "halo": all-to-all of packed halo rows (graphs whose edge list shards naturally).  "auto"
+        # (default): halo when EVERY rank reads less than PGSD_HALO_THRESHOLD of the remote rows.
+        self.mode = mode or os.environ.get("PGSD_SHARD_MODE", "auto")
+        self.gather_fn = gather_fn
+        self.halo = None
+        if self.mode in ("auto", "halo") and world > 1:
+            own_block, halo_block, need = split_local_and_halo(local_plan, bounds, rank)
+            frac = torch.tensor([halo_fraction(need, bounds, rank)], dtype=torch.float32,
+                                device=local_plan.row_ptr.device)
+            dist.all_reduce(frac, op=dist.ReduceOp.MAX, group=group)
+            self.halo_fraction = float(frac.item())
+            if self.mode == "halo" or self.halo_fraction <= float(os.environ.get("PGSD_HALO_THRESHOLD", "0.5")):
+                self.mode = "halo"
+                self.own_block, self.halo_block = own_block, halo_block
+                self.halo = HaloExchange(rank, world, need, group)
+            else:
+                self.mode = "ring"
+            del own_block, halo_block, need
+        elif self.mode in ("auto", "halo"):
+            self.mode = "ring"
         # in gather mode x spans all nodes while the plan's rows are local: tell the kernel where
         # destination row 0 lives in x (diagonal term)
         self.local_plan = CSRPlan(local_plan.n_dst, local_plan.n_src, local_plan.nnz, local_plan.num_input_edges,
@@ -224,6 +327,8 @@ class ShardedAggregator:
         op_ids = tuple(range(n_ops))
         if self.mode == "gather":
             return self._gather_then_single(xs, op_ids, f, alpha, beta, zs)
+        if self.mode == "halo":
+            return self._halo_step(xs, op_ids, f, alpha, beta, zs)
         # interleave the operands: one [n_local, n_ops*F] send buffer
         pull = self._pull_exchange(xs[0], n_ops * f)
         if pull is not None:
@@ -269,6 +374,30 @@ def _gather_then_single(self, xs, op_ids, f, alpha, beta, zs):
 
 
 ShardedAggregator._gather_then_single = _gather_then_single
+
+
+def _halo_step(self, xs, op_ids, f, alpha, beta, zs):
+    """pack -> all_to_all (async) | own-column block -> wait -> remote-column block (+=)."""
+    n_ops, hx = len(xs), self.halo
+    key = ("halo", xs[0].dtype, xs[0].device, n_ops * f)
+    if self._recv is None or self._recv[0] != key:
+        mk = lambda rows: torch.empty((max(rows, 1), n_ops * f), dtype=xs[0].dtype, device=xs[0].device)
+        self._recv = (key, (mk(hx.n_send), mk(hx.n_recv)))
+    send, recv = self._recv[1]
+    gather = self.gather_fn or ops.gather_rows
+    if hx.n_send:
+        for k in range(n_ops):                     # halo pack: the rows the peers asked for
+            gather(xs[k], hx.serve, out=send[:hx.n_send, k * f:(k + 1) * f])
+    work = hx.start(send[:hx.n_send], recv[:hx.n_recv])
+    y = self.aggregate_fn(self.own_block, list(xs), op_ids, alpha, beta, zs, None)
+    work.wait()                                    # NCCL: the current stream waits; gloo: the host blocks
+    if self.halo_block.nnz:
+        views = [recv[:, k * f:(k + 1) * f] for k in range(n_ops)]
+        y = self.aggregate_fn(self.halo_block, views, op_ids, alpha, 1.0, y, y)
+    return y
+
+
+ShardedAggregator._halo_step = _halo_step
 
 
 class ShardedMagNetConv:

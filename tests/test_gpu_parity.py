@@ -609,3 +609,39 @@ def test_magnet_node_classification_model_golden():
     F_loss = torch.nn.functional.nll_loss(out, torch.randint(0, 5, (out.size(0),), device=DEV))
     F_loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("f", [64, 16, 128, 48])
+def test_shared_operand_gathers_once_and_is_bit_identical(f):
+    """x_real and x_imag being ONE tensor (examples/magnet_node.py:61-62 pass data.x for both): the
+    aggregation kernel gathers each neighbour row once for both operators.  Per-row summation order
+    is unchanged, so the result must be bit-identical to the two-gather launch (variant bit 0x400
+    switches the sharing off) and to a launch on a cloned second operand; layer output vs oracle."""
+    g = torch.Generator().manual_seed(100 + f)
+    n, e = 5003, 70_000
+    ei = torch.randint(0, n - 30, (2, e), generator=g)
+    ei[1, :900] = 11                                               # one long row
+    x = (torch.rand(n, f, generator=g) * 2 - 1).to(DEV)
+    z = [(torch.rand(n, f, generator=g) * 2 - 1).to(DEV) for _ in range(2)]
+    p = planmod.build_magnetic(ei.to(DEV), None, n, 0.25, "sym", 1.7)   # non-zero real diagonal
+    for kw in (dict(), dict(alpha=2.0, beta=-1.0, zs=z), dict(op_scale=(1.0, -1.0))):
+        for variant in (0, 2, 0x10 | 4, 0x20 | 2, 0x20 | 4):
+            shared = ops.spmm(p, [x, x], (0, 1), variant=variant, **kw)
+            split = ops.spmm(p, [x, x], (0, 1), variant=variant | 0x400, **kw)
+            cloned = ops.spmm(p, [x, x.clone()], (0, 1), variant=variant, **kw)
+            for a, b, c in zip(shared, split, cloned):
+                assert torch.equal(a, b) and torch.equal(a, c), f"variant {variant:#x} {list(kw)}"
+    # column slice of a wider buffer passed twice
+    wide = torch.zeros(n, 2 * f + 8, device=DEV)
+    wide[:, 8:8 + f] = x
+    sl = wide[:, 8:8 + f]
+    a = ops.spmm(p, [sl, sl], (0, 1))
+    b = ops.spmm(p, [x, x.clone()], (0, 1))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # the layer, called the way the reference's node-classification example calls it
+    conv = nn.MagNetConv(f, 32, K=2, q=0.2, trainable_q=False).to(DEV)
+    o_r, o_i = port.magnet_conv(x.cpu(), x.cpu(), ei, None, conv.weight.detach().cpu(),
+                                conv.bias.detach().cpu(), 0.2, "sym")
+    out_r, out_i = conv(x, x, ei.to(DEV))
+    assert_close_rel(out_r, o_r, 1e-5, "out_real")
+    assert_close_rel(out_i, o_i, 1e-5, "out_imag")
