@@ -134,6 +134,28 @@ PGSD_API int pgsd_build_magnetic_laplacian_theta(const int64_t* edge_row, const 
                                   int64_t* nnz_host, void* workspace, size_t workspace_bytes,
                                   pgsd_stream_t stream);
 
+/* Row-range build of the same plan for the node-range sharded path (no reference
+ * counterpart -- the reference is single-process): rank r builds only rows [row_lo, row_hi) from the
+ * edges incident to that node range (edges touching no node of the range are ignored; passing the
+ * whole list is allowed), in two phases around ONE all-gather:
+ *   begin : row_ptr [row_hi-row_lo+1], col / sym / theta [2E capacity] (sym = coalesced A+A^T weight,
+ *           theta = coalesced A-A^T of each stored entry, same (a,b)-sorted order and the same
+ *           in-edge-order duplicate sums as the full build) and deg_local [row_hi-row_lo] = row sums;
+ *   (caller all-gathers deg_local into deg_all [num_nodes])
+ *   finish: val_real / val_imag [nnz] (may alias sym / theta) and diag_real [row_hi-row_lo].
+ * Rows produced this way are bit-identical to the same rows of pgsd_build_magnetic_laplacian. */
+PGSD_API int pgsd_build_magnetic_rows_begin(const int64_t* edge_row, const int64_t* edge_col,
+                                  const float* edge_weight, int64_t num_edges, int64_t num_nodes,
+                                  int64_t row_lo, int64_t row_hi, int signed_mode,
+                                  int32_t* row_ptr, int32_t* col, float* sym, float* theta,
+                                  float* deg_local, int64_t* nnz_host, void* workspace,
+                                  size_t workspace_bytes, pgsd_stream_t stream);
+PGSD_API int pgsd_build_magnetic_rows_finish(const int32_t* row_ptr, const int32_t* col, const float* sym,
+                                  const float* theta, const float* deg_all, int64_t num_nodes,
+                                  int64_t row_lo, int64_t row_hi, double q, int normalization,
+                                  float lambda_max, float* val_real, float* val_imag,
+                                  float* diag_real, pgsd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Sparse aggregation (the hot loop): for every destination row r and operator k < n_ops
  *   agg_k[r] = diag_k[r] * x_k[r] + sum_{e in row r} val_k[e] * x_k[col[e]]

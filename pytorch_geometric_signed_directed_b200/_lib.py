@@ -85,6 +85,10 @@ _PROTOTYPES = {
     "pgsd_build_magnetic_laplacian_theta": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_double, C.c_int,
                                                       _f32, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp,
                                                       C.POINTER(_i64), _vp, C.c_size_t, _vp]),
+    "pgsd_build_magnetic_rows_begin": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp, _vp, _vp,
+                                                 _vp, _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
+    "pgsd_build_magnetic_rows_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_double,
+                                                  C.c_int, _f32, _vp, _vp, _vp, _vp]),
     "pgsd_magnetic_q_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
                                        _vp, _i64, _vp, _i64, C.c_double, _vp, _vp]),
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),

@@ -200,8 +200,8 @@ extern "C" int pgsd_dense_transform(const pgsd_dense_args* a, pgsd_stream_t stre
   }
   // variant: 0 = auto (TMA-fed tcgen05 kernel, else register-staged tcgen05 kernel, else FFMA), 1 = force FFMA,
   // 2 = require the tcgen05 path, 4 = require its warp-specialised kernel
-  // 16 = require the TMA-fed warp-specialised kernel (dense_tma.cu)
-  if (a->variant == 16) {
+  // 16 = require the TMA-fed warp-specialised kernel (dense_tma.cu); its ring depths may ride in bits 8-15
+  if ((a->variant & 0xff) == 16) {
     int handled = 0;
     int rc = dense_tma_try(a, st, &handled);
     if (rc != PGSD_OK) return rc;

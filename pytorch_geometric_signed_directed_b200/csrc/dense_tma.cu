@@ -10,8 +10,10 @@
 //   warp 0      : TMA producer -- one thread issues cp.async.bulk.tensor.2d per [128 rows x 128 B] chunk
 //                 (SWIZZLE_128B tensor maps, one per term; rows / k past the end are zero-filled by
 //                 the TMA unit) into an S-stage ring, completion on the stage's `full` mbarrier;
-//   warps 6..13 : converters (fp32 only) -- split the landed chunk in place into TF32 hi (same bytes)
-//                 and lo (second image of the stage), fence.proxy.async, arrive on `conv`;
+//   warps 6..13 : converters (fp32 only) -- split the landed chunk into TF32 hi (in place, same bytes) and
+//                 lo (a slot of a SHORT second ring: a lo image lives only from the split to the end of
+//                 its MMAs, so 2-3 slots serve any number of landing stages and the shared memory
+//                 they save buys landing stages = bytes in flight), fence.proxy.async, arrive on `conv`;
 //                 bf16 chunks are already MMA operands: no converter warps at all;
 //   warp 1      : MMA issuer -- waits `conv` (fp32) / `full` (bf16), issues the tcgen05.mma chain of the
 //                 chunk, tcgen05.commit -> `empty` (stage back to the producer); the last chunk of a
@@ -30,7 +32,8 @@ constexpr int TILE_M = 128;
 constexpr int MAX_TERMS = PGSD_DENSE_MAX_TERMS;
 constexpr int MAX_CHUNKS = 2 * PGSD_DENSE_MAX_TERMS;
 constexpr int MAX_SLABS = 16;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_LO = 4;
 constexpr int CHUNK_BYTES = TILE_M * 128;
 constexpr int EPI_WARPS = 4;
 constexpr int CONV_WARPS = 8;
@@ -38,7 +41,7 @@ constexpr int CONV_WARPS = 8;
 struct alignas(64) Params {
   CUtensorMap maps[MAX_TERMS];     // one [n_rows, k_t] tensor per term, box = [128 rows, 128 bytes]
   int64_t n_rows;
-  int32_t n_chunks, n_slabs, relu_mode, n_total, stages, pad;
+  int32_t n_chunks, n_slabs, relu_mode, n_total, stages, lo_stages;
   int16_t k0[MAX_CHUNKS];          // first k (elements) of the chunk inside its term
   int8_t term[MAX_CHUNKS];
   int8_t group[MAX_CHUNKS];
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   constexpr int ES = BF16 ? 2 : 4;
   constexpr int EPC = 16 / ES;
   constexpr int CK = 128 / ES;
-  constexpr int STAGE_BYTES = BF16 ? CHUNK_BYTES : 2 * CHUNK_BYTES;   // fp32: hi image (in place) + lo image
+  constexpr int STAGE_BYTES = CHUNK_BYTES;       // landing ring; fp32: becomes the hi image in place
   constexpr int HALF = N_OUT * 128;
   constexpr int SLAB_BYTES = BF16 ? HALF : 2 * HALF;
   constexpr int UMMA_K_BYTES = 32;
@@ -91,17 +94,19 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int S = p.stages;
+  const int S = p.stages, L = BF16 ? 0 : p.lo_stages;
   uint8_t* a_stage = smem;
-  uint8_t* w_smem = smem + S * STAGE_BYTES;
+  uint8_t* lo_ring = smem + S * STAGE_BYTES;
+  uint8_t* w_smem = lo_ring + L * CHUNK_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.n_slabs * SLAB_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + MAX_LO + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * N_OUT;
-  const uint32_t a_addr = smem_u32(a_stage), w_addr = smem_u32(w_smem);
+  const uint32_t a_addr = smem_u32(a_stage), lo_addr = smem_u32(lo_ring), w_addr = smem_u32(w_smem);
   const uint32_t bar_full = smem_u32(bars), bar_conv = bar_full + 8 * MAX_STAGES, bar_empty = bar_conv + 8 * MAX_STAGES;
-  const uint32_t bar_acc_full = bar_empty + 8 * MAX_STAGES, bar_acc_empty = bar_acc_full + 16;
+  const uint32_t bar_lo_empty = bar_empty + 8 * MAX_STAGES;
+  const uint32_t bar_acc_full = bar_lo_empty + 8 * MAX_LO, bar_acc_empty = bar_acc_full + 16;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
       mbar_init(bar_conv + 8 * s, NCV > 0 ? NCV : 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
+    for (int s = 0; s < MAX_LO; ++s) mbar_init(bar_lo_empty + 8 * s, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
       mbar_init(bar_acc_empty + 8 * a, EPI_WARPS);
@@ -171,7 +177,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
         tc_fence_after();
         if (lane == 0) {
           const uint32_t d = tmem_base + acc * ACC_COLS + uint32_t(p.group[c]) * N_OUT;
-          const uint32_t a_hi = a_addr + stage * STAGE_BYTES, a_lo = a_hi + CHUNK_BYTES;
+          const uint32_t a_hi = a_addr + stage * STAGE_BYTES;
+          const uint32_t a_lo = BF16 ? 0u : lo_addr + (uses % uint32_t(L > 0 ? L : 1)) * CHUNK_BYTES;
           const uint32_t w_hi = w_addr + uint32_t(p.slab[c]) * SLAB_BYTES, w_lo = w_hi + HALF;
 #pragma unroll
           for (int j = 0; j < 128 / UMMA_K_BYTES; ++j) {
@@ -186,6 +193,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
             }
           }
           tc_commit(bar_empty + 8 * stage);
+          if constexpr (!BF16) tc_commit(bar_lo_empty + 8 * (uses % uint32_t(L)));
           if (c == p.n_chunks - 1) tc_commit(bar_acc_full + 8 * acc);
         }
         __syncwarp();
@@ -259,11 +267,14 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int c = 0; c < p.n_chunks; ++c, ++uses) {
           const uint32_t stage = uses % S;
+          const uint32_t ls = uses % uint32_t(L);
           mbar_wait_relaxed(bar_full + 8 * stage, (uses / S) & 1);
-          const uint32_t hi = a_addr + stage * STAGE_BYTES + ct * 16, lo = hi + CHUNK_BYTES;
+          const uint32_t hi = a_addr + stage * STAGE_BYTES + ct * 16, lo = lo_addr + ls * CHUNK_BYTES + ct * 16;
           float4 v[UNITS];
 #pragma unroll
           for (int i = 0; i < UNITS; ++i) v[i] = lds_v4(hi + i * NCV * 32 * 16);
+          // the lo slot is free once the MMAs of the chunk that used it last (L chunks ago) completed
+          if (uses >= uint32_t(L)) mbar_wait_relaxed(bar_lo_empty + 8 * ls, ((uses / L) - 1) & 1);
 #pragma unroll
           for (int i = 0; i < UNITS; ++i) {
             // the split is position-independent: unit q of the landed (swizzled) image stays unit q
@@ -291,18 +302,21 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   }
 }
 
-static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages) {
-  return 1024 + size_t(stages) * (bf16 ? 1 : 2) * CHUNK_BYTES + size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 +
-         8 * (3 * MAX_STAGES + 4) + 16;
+static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_stages) {
+  return 1024 + size_t(stages + (bf16 ? 0 : lo_stages)) * CHUNK_BYTES +
+         size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (3 * MAX_STAGES + MAX_LO + 4) + 16;
 }
 
 template <int N_OUT, int GROUPS, bool BF16>
-static int launch(Params& p, cudaStream_t st) {
-  int stages = MAX_STAGES;
-  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages) > 220 * 1024) --stages;
-  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages) > 220 * 1024) return -1;
+static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo) {
+  // experiment knobs ride in the variant word (bits 8-11: lo slots, bits 12-15: landing stages); 0 = default
+  const int lo = BF16 ? 0 : (want_lo >= 1 && want_lo <= MAX_LO ? want_lo : 2);
+  int stages = (want_stages >= 2 && want_stages <= MAX_STAGES) ? want_stages : MAX_STAGES;
+  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo) > 220 * 1024) --stages;
+  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo) > 220 * 1024) return -1;
   p.stages = stages;
-  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages);
+  p.lo_stages = lo;
+  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo);
   auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
@@ -400,12 +414,13 @@ int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   }
   if (groups == 2 && !(seen_group[0] && seen_group[1])) return PGSD_OK;
   int rc = -1;
-#define PGSD_TMA(N_)                                                                                \
-  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st) : launch<N_, 1, true>(p, st);             \
-  else rc = groups == 2 ? launch<N_, 2, false>(p, st) : launch<N_, 1, false>(p, st);                \
+  const int ws = (a->variant >> 12) & 0xf, wl = (a->variant >> 8) & 0xf;
+#define PGSD_TMA(N_)                                                                                        \
+  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl) : launch<N_, 1, true>(p, st, ws, wl);     \
+  else rc = groups == 2 ? launch<N_, 2, false>(p, st, ws, wl) : launch<N_, 1, false>(p, st, ws, wl);        \
   break;
   switch (n_tile) {
-    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st) : launch<16, 1, false>(p, st); break;
+    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st, ws, wl) : launch<16, 1, false>(p, st, ws, wl); break;
     case 32: PGSD_TMA(32)
     case 64: PGSD_TMA(64)
     default: PGSD_TMA(128)

@@ -48,10 +48,11 @@ static inline unsigned blocks_for(int64_t n, int per = TPB) {
 
 // ---------------------------------------------------------------------------------- kernels
 
-// slots [0,E): (row,col) ; slots [E,2E): (col,row).  Self loops get the sentinel key.
+// slots [0,E): (row,col) ; slots [E,2E): (col,row).  Self loops get the sentinel key, and so do
+// entries whose row lies outside [row_lo, row_hi) (row-range build of one shard; rows are re-based).
 __global__ void k_keys_sym(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
-                           int64_t E, int64_t N, uint64_t sentinel, uint64_t* __restrict__ keys,
-                           uint32_t* __restrict__ slots, Counters* cnt) {
+                           int64_t E, int64_t N, int64_t row_lo, int64_t row_hi, uint64_t sentinel,
+                           uint64_t* __restrict__ keys, uint32_t* __restrict__ slots, Counters* cnt) {
   GRID_STRIDE(s, 2 * E) {
     const int64_t p = s < E ? s : s - E;
     const int64_t r = row[p], c = col[p];
@@ -59,7 +60,8 @@ __global__ void k_keys_sym(const int64_t* __restrict__ row, const int64_t* __res
     if (r < 0 || r >= N || c < 0 || c >= N) {
       cnt->err = 1;
     } else if (r != c) {
-      key = s < E ? uint64_t(r) * uint64_t(N) + uint64_t(c) : uint64_t(c) * uint64_t(N) + uint64_t(r);
+      const int64_t a = s < E ? r : c, b = s < E ? c : r;
+      if (a >= row_lo && a < row_hi) key = uint64_t(a - row_lo) * uint64_t(N) + uint64_t(b);
     }
     keys[s] = key;
     slots[s] = uint32_t(s);
@@ -174,6 +176,31 @@ __global__ void k_magnetic_values(const int32_t* __restrict__ urow, const int32_
     else mag = s;
     val_real[u] = scale_lmax(-(mag * cs), lambda_max);
     val_imag[u] = scale_lmax(mag * sn, lambda_max);
+  }
+}
+
+// Row-range variant (second phase of the sharded build): local row r is global node row_lo + r and
+// `deg` spans all nodes (all-gathered between the phases).  Same arithmetic, same operand order.
+__global__ void k_magnetic_values_rows(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ ucol,
+                                       const float* usym, const float* utheta,   // may alias the outputs
+                                       const float* __restrict__ deg, int64_t n_rows, int64_t row_lo,
+                                       float two_pi_q, int normalization, float lambda_max,
+                                       float* val_real, float* val_imag) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < n_rows;
+       r += (int64_t(gridDim.x) * blockDim.x) >> 5) {
+    const float da = normalization ? inv_sqrt_or_zero(deg[row_lo + r]) : 1.f;
+    for (int u = row_ptr[r] + lane; u < row_ptr[r + 1]; u += 32) {
+      const float s = usym[u] / 2;
+      const float th = utheta[u];
+      float sn, cs;
+      sincosf(two_pi_q * th, &sn, &cs);
+      float mag;
+      if (normalization) mag = (inv_sqrt_or_zero(deg[ucol[u]]) * s) * da;
+      else mag = s;
+      val_real[u] = scale_lmax(-(mag * cs), lambda_max);
+      val_imag[u] = scale_lmax(mag * sn, lambda_max);
+    }
   }
 }
 
@@ -508,16 +535,23 @@ static int build_magnetic_impl(
     const int64_t* edge_row, const int64_t* edge_col, const float* edge_weight, int64_t num_edges,
     int64_t num_nodes, double q, int normalization, float lambda_max, int signed_mode,
     int32_t* row_ptr, int32_t* col, float* val_real, float* val_imag, float* diag_real, float* theta,
-    int64_t* nnz_host, void* workspace, size_t workspace_bytes, pgsd_stream_t stream) {
+    int64_t* nnz_host, void* workspace, size_t workspace_bytes, pgsd_stream_t stream,
+    int64_t row_lo = 0, int64_t row_hi = -1, float* deg_out = nullptr) {
+  // deg_out != nullptr: structure phase of the row-range build -- rows [row_lo, row_hi) only,
+  // val_real / val_imag receive the coalesced A+A^T weight and Theta of every entry, deg_out the
+  // row sums; the values follow in pgsd_build_magnetic_rows_finish once deg is known for all nodes.
+  const bool structure_only = deg_out != nullptr;
+  if (row_hi < 0) row_hi = num_nodes;
   int rc = check_sizes(num_nodes, num_edges);
   if (rc != PGSD_OK) return rc;
-  PGSD_REQUIRE(row_ptr && diag_real && nnz_host, "build_magnetic_laplacian: null pointer");
+  PGSD_REQUIRE(row_ptr && (diag_real || structure_only) && nnz_host, "build_magnetic_laplacian: null pointer");
+  PGSD_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= num_nodes, "build_magnetic_laplacian: bad row range");
   PGSD_REQUIRE(num_edges == 0 || (edge_row && edge_col && col && val_real && val_imag),
                "build_magnetic_laplacian: null pointer");
   PGSD_REQUIRE(signed_mode >= 0 && signed_mode <= 2, "build_magnetic_laplacian: bad signed_mode");
   PGSD_REQUIRE(workspace != nullptr, "build_magnetic_laplacian: null workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t E = num_edges, N = num_nodes, M = 2 * E;
+  const int64_t E = num_edges, N = num_nodes, M = 2 * E, NL = row_hi - row_lo;
   SymSpace s = carve_sym(workspace, E, N);
   if (s.total > workspace_bytes)
     return fail(PGSD_ERR_WORKSPACE, "build_magnetic_laplacian: workspace %zu < %zu",
@@ -525,9 +559,9 @@ static int build_magnetic_impl(
   PGSD_CUDA(cudaMemsetAsync(s.cnt, 0, sizeof(Counters), st));
   Counters hc{};
   if (M > 0) {
-    const int bits = bit_length(uint64_t(N) * uint64_t(N)) + 1;
+    const int bits = bit_length(uint64_t(NL > 0 ? NL : 1) * uint64_t(N)) + 1;
     const uint64_t sentinel = (uint64_t(1) << bits) - 1;
-    k_keys_sym<<<blocks_for(M), TPB, 0, st>>>(edge_row, edge_col, E, N, sentinel, s.keys_a,
+    k_keys_sym<<<blocks_for(M), TPB, 0, st>>>(edge_row, edge_col, E, N, row_lo, row_hi, sentinel, s.keys_a,
                                               s.slots_a, s.cnt);
     PGSD_LAUNCH_CHECK("k_keys_sym");
     cub::DoubleBuffer<uint64_t> dk(s.keys_a, s.keys_b);
@@ -555,8 +589,20 @@ static int build_magnetic_impl(
   rc = read_counters(s.cnt, &hc, st);
   if (rc != PGSD_OK) return rc;
   *nnz_host = hc.nnz;
-  k_row_ptr<<<blocks_for(int64_t(hc.nnz) + 1), TPB, 0, st>>>(s.urow, &s.cnt->nnz, hc.nnz, N, row_ptr);
+  k_row_ptr<<<blocks_for(int64_t(hc.nnz) + 1), TPB, 0, st>>>(s.urow, &s.cnt->nnz, hc.nnz, NL, row_ptr);
   PGSD_LAUNCH_CHECK("k_row_ptr");
+  if (structure_only) {
+    if (NL > 0) {
+      k_degree<<<blocks_for(NL * 32), TPB, 0, st>>>(row_ptr, s.usym, s.uabs, signed_mode, NL, deg_out);
+      PGSD_LAUNCH_CHECK("k_degree");
+    }
+    if (hc.nnz > 0) {
+      PGSD_CUDA(cudaMemcpyAsync(val_real, s.usym, size_t(hc.nnz) * 4, cudaMemcpyDeviceToDevice, st));
+      PGSD_CUDA(cudaMemcpyAsync(val_imag, s.utheta, size_t(hc.nnz) * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return PGSD_OK;
+  }
+  PGSD_REQUIRE(row_lo == 0 && row_hi == N, "build_magnetic_laplacian: a row range needs the two-phase build");
   if (N > 0) {
     k_degree<<<blocks_for(N * 32), TPB, 0, st>>>(row_ptr, s.usym, s.uabs, signed_mode, N, s.deg);
     PGSD_LAUNCH_CHECK("k_degree");
@@ -594,4 +640,34 @@ extern "C" int pgsd_build_magnetic_laplacian_theta(
   return build_magnetic_impl(edge_row, edge_col, edge_weight, num_edges, num_nodes, q, normalization,
                              lambda_max, signed_mode, row_ptr, col, val_real, val_imag, diag_real,
                              theta, nnz_host, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pgsd_build_magnetic_rows_begin(
+    const int64_t* edge_row, const int64_t* edge_col, const float* edge_weight, int64_t num_edges,
+    int64_t num_nodes, int64_t row_lo, int64_t row_hi, int signed_mode, int32_t* row_ptr, int32_t* col,
+    float* sym, float* theta, float* deg_local, int64_t* nnz_host, void* workspace, size_t workspace_bytes,
+    pgsd_stream_t stream) {
+  PGSD_REQUIRE(deg_local != nullptr, "build_magnetic_rows_begin: null deg_local");
+  return build_magnetic_impl(edge_row, edge_col, edge_weight, num_edges, num_nodes, 0.0, 0, 2.0f, signed_mode,
+                             row_ptr, col, sym, theta, nullptr, nullptr, nnz_host, workspace, workspace_bytes,
+                             stream, row_lo, row_hi, deg_local);
+}
+
+extern "C" int pgsd_build_magnetic_rows_finish(
+    const int32_t* row_ptr, const int32_t* col, const float* sym, const float* theta, const float* deg_all,
+    int64_t num_nodes, int64_t row_lo, int64_t row_hi, double q, int normalization, float lambda_max,
+    float* val_real, float* val_imag, float* diag_real, pgsd_stream_t stream) {
+  PGSD_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= num_nodes, "build_magnetic_rows_finish: bad row range");
+  const int64_t NL = row_hi - row_lo;
+  if (NL == 0) return PGSD_OK;
+  PGSD_REQUIRE(row_ptr && deg_all && diag_real, "build_magnetic_rows_finish: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float two_pi_q = float(2.0 * 3.14159265358979323846 * q);
+  k_magnetic_values_rows<<<blocks_for(NL * 32), TPB, 0, st>>>(row_ptr, col, sym, theta, deg_all, NL, row_lo,
+                                                             two_pi_q, normalization, lambda_max, val_real,
+                                                             val_imag);
+  PGSD_LAUNCH_CHECK("k_magnetic_values_rows");
+  k_magnetic_diag<<<blocks_for(NL), TPB, 0, st>>>(deg_all + row_lo, NL, normalization, lambda_max, diag_real);
+  PGSD_LAUNCH_CHECK("k_magnetic_diag");
+  return PGSD_OK;
 }

@@ -386,8 +386,13 @@ def _halo_step(self, xs, op_ids, f, alpha, beta, zs):
     send, recv = self._recv[1]
     gather = self.gather_fn or ops.gather_rows
     if hx.n_send:
+        vec = (f * xs[0].element_size()) % 16 == 0 or self.gather_fn is not None
         for k in range(n_ops):                     # halo pack: the rows the peers asked for
-            gather(xs[k], hx.serve, out=send[:hx.n_send, k * f:(k + 1) * f])
+            dst = send[:hx.n_send, k * f:(k + 1) * f]
+            if vec and xs[k].data_ptr() % 16 == 0 and (xs[k].stride(0) * xs[k].element_size()) % 16 == 0:
+                gather(xs[k], hx.serve, out=dst)
+            else:                                  # odd widths (the reference's tests use F = 2, 3)
+                dst.copy_(xs[k].index_select(0, hx.serve.long()))
     work = hx.start(send[:hx.n_send], recv[:hx.n_recv])
     y = self.aggregate_fn(self.own_block, list(xs), op_ids, alpha, beta, zs, None)
     work.wait()                                    # NCCL: the current stream waits; gloo: the host blocks
@@ -398,6 +403,59 @@ def _halo_step(self, xs, op_ids, f, alpha, beta, zs):
 
 
 ShardedAggregator._halo_step = _halo_step
+
+
+def incident_edges(edge_index: Tensor, edge_weight: Optional[Tensor], lo: int, hi: int):
+    """Edges with an endpoint in [lo, hi), original order kept (duplicates are summed in edge order)."""
+    r, c = edge_index[0], edge_index[1]
+    m = ((r >= lo) & (r < hi)) | ((c >= lo) & (c < hi))
+    return edge_index[:, m].contiguous(), (None if edge_weight is None else edge_weight[m].contiguous())
+
+
+def route_edges(edge_chunk: Tensor, weight_chunk: Optional[Tensor], bounds: Sequence[int], rank: int, world: int,
+                group=None):
+    """All-to-all of the symmetrised-edge build: rank r holds a contiguous slice of the
+    global COO list; edge (i, j) is sent to owner(i) and, when different, owner(j).  Slices arrive in
+    source-rank order and every sender keeps its own order, so the received list is the global list
+    restricted to this rank's incident edges IN THE ORIGINAL ORDER -- which the in-edge-order duplicate
+    sums of the builder (PyG coalesce semantics) rely on."""
+    dev = edge_chunk.device
+    b_t = torch.tensor(list(bounds), device=dev, dtype=torch.long)
+    o_r = torch.bucketize(edge_chunk[0], b_t[1:], right=True)
+    o_c = torch.bucketize(edge_chunk[1], b_t[1:], right=True)
+    has_w = weight_chunk is not None
+    sends, counts = [], []
+    for b in range(world):
+        m = (o_r == b) | (o_c == b)
+        cols = [edge_chunk[0][m], edge_chunk[1][m]]
+        if has_w:
+            cols.append(weight_chunk[m].float().view(torch.int32).long())     # bit pattern rides along
+        sends.append(torch.stack(cols, 1))
+        counts.append(int(m.sum().item()))
+    send = torch.cat(sends).contiguous()
+    cnt_out = torch.tensor(counts, dtype=torch.int64, device=dev)
+    cnt_in = torch.empty_like(cnt_out)
+    _all_to_all(cnt_in, cnt_out, [1] * world, [1] * world, group)
+    in_counts = [int(v) for v in cnt_in.tolist()]
+    recv = torch.empty((sum(in_counts), send.size(1)), dtype=torch.int64, device=dev)
+    _all_to_all(recv, send, in_counts, counts, group)
+    ei = recv[:, :2].t().contiguous()
+    ew = recv[:, 2].int().view(torch.float32).contiguous() if has_w else None
+    return ei, ew
+
+
+def allgather_rows(local: Tensor, bounds: Sequence[int], group=None) -> Tensor:
+    """Concatenation over ranks of per-shard vectors of (possibly) different lengths."""
+    world = len(bounds) - 1
+    sizes = [bounds[b + 1] - bounds[b] for b in range(world)]
+    m = max(sizes)
+    padded = torch.zeros(m, dtype=local.dtype, device=local.device)
+    padded[:local.numel()] = local
+    out = torch.empty(world * m, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    if all(sz == m for sz in sizes):
+        return out
+    return torch.cat([out[b * m:b * m + sizes[b]] for b in range(world)])
 
 
 class ShardedMagNetConv:
@@ -411,22 +469,39 @@ class ShardedMagNetConv:
         self.agg = None
         self.local_nnz = 0
 
-    def build(self, edge_index: Tensor, edge_weight: Optional[Tensor] = None, lambda_max: float = 2.0):
-        """Every rank builds the global operator (replicated preprocessing, outside the timed
-        step) and keeps its row range.  TODO(round 2): distributed build -- all-to-all of the
-        symmetrised edges by row owner + all-gather of deg^-1/2."""
+    def build(self, edge_index: Tensor, edge_weight: Optional[Tensor] = None, lambda_max: float = 2.0,
+              replicated: bool = True):
+        """Distributed operator build: every rank builds ONLY its rows, from the edges
+        incident to its node range, and the ranks exchange one all-gather of the node degrees
+        (4 B/node) between the structure and the value phase (`plan.build_magnetic_rows`).
+        replicated=True : `edge_index` is the whole edge list on every rank -> the incident edges are
+                          selected locally (order-preserving mask), no edge traffic;
+        replicated=False: `edge_index` is this rank's contiguous SLICE of the global edge list (slices
+                          in rank order) -> edges are first routed to the owners of both endpoints with
+                          an all-to-all (`route_edges`)."""
         c = self.conv
-        full = _plan.build_magnetic(edge_index, edge_weight, self.n_total, c._q_value(), c.normalization,
-                                    lambda_max, c._signed_mode())
-        local = split_rows(full, self.bounds[self.rank], self.bounds[self.rank + 1])
-        # detach the slices from the global arrays so those can be freed
-        local.col = local.col.clone()
-        local.val = [None if v is None else v.clone() for v in local.val]
-        local.diag = [None if d is None else d.clone() for d in local.diag]
-        local.meta = {}
+        lo, hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        if os.environ.get("PGSD_REPLICATED_BUILD", "0") == "1" and replicated:
+            # round-1 behaviour, kept for A/B checks: global plan on every rank, rows sliced out
+            full = _plan.build_magnetic(edge_index, edge_weight, self.n_total, c._q_value(), c.normalization,
+                                        lambda_max, c._signed_mode())
+            local = split_rows(full, lo, hi)
+            local.col = local.col.clone()
+            local.val = [None if v is None else v.clone() for v in local.val]
+            local.diag = [None if d is None else d.clone() for d in local.diag]
+            local.meta = {}
+            del full
+        else:
+            if replicated:
+                ei, ew = incident_edges(edge_index, edge_weight, lo, hi)
+            else:
+                ei, ew = route_edges(edge_index, edge_weight, self.bounds, self.rank, self.world, self.group)
+            local = _plan.build_magnetic_rows(ei, ew, self.n_total, lo, hi, c._q_value(), c.normalization,
+                                              lambda_max, c._signed_mode(),
+                                              allgather_deg=lambda d: allgather_rows(d, self.bounds, self.group))
+            local.meta = {}
         self.local_nnz = local.nnz
         self.agg = ShardedAggregator(local, self.bounds, self.rank, self.world, self.group)
-        del full
         return self
 
     def __call__(self, x_real: Tensor, x_imag: Tensor):

@@ -218,6 +218,57 @@ def build_magnetic(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, q:
     return CSRPlan(n, n, k, e, row_ptr, col[:k], [vr[:k], vi[:k]], [diag[:n], None], [0.0, 0.0], meta=meta)
 
 
+def build_magnetic_rows(edge_index: Tensor, edge_weight: Optional[Tensor], n: int, row_lo: int, row_hi: int,
+                        q: float, normalization: Optional[str], lambda_max: float, signed_mode: int = 0,
+                        allgather_deg=None) -> CSRPlan:
+    """Rows [row_lo, row_hi) of the magnetic plan (columns global), built from the edges incident to
+    that node range only (`pgsd_build_magnetic_rows_begin` / `_finish`).
+    `allgather_deg(deg_local [row_hi-row_lo]) -> deg_all [n]` supplies the one exchange the build
+    needs (every node's degree, 4 B/node); None = the range is the whole graph.
+    The result is bit-identical to the same rows of `build_magnetic`."""
+    ei, ew = _prep_edges(edge_index, edge_weight)
+    dev, e, nl = ei.device, ei.size(1), row_hi - row_lo
+    cap = max(2 * e, 1)
+    with torch.cuda.device(dev):
+        row_ptr = torch.empty(nl + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(cap, dtype=torch.int32, device=dev)
+        vr = torch.empty(cap, dtype=torch.float32, device=dev)
+        vi = torch.empty(cap, dtype=torch.float32, device=dev)
+        deg = torch.zeros(max(nl, 1), dtype=torch.float32, device=dev)
+        diag = torch.empty(max(nl, 1), dtype=torch.float32, device=dev)
+        ws = _workspace(n, e, dev)
+        nnz = C.c_int64(0)
+        lib = _lib.load()
+        _lib.check(lib.pgsd_build_magnetic_rows_begin(
+            ei[0].data_ptr(), ei[1].data_ptr(), _ptr(ew), e, n, row_lo, row_hi, int(signed_mode),
+            row_ptr.data_ptr(), col.data_ptr(), vr.data_ptr(), vi.data_ptr(), deg.data_ptr(), C.byref(nnz),
+            ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "pgsd_build_magnetic_rows_begin")
+        del ws
+        if allgather_deg is None:
+            if nl != n:
+                raise ValueError("build_magnetic_rows: a proper row range needs allgather_deg")
+            deg_all = deg[:n]
+        else:
+            deg_all = allgather_deg(deg[:nl])
+        if deg_all.numel() != n or deg_all.dtype != torch.float32:
+            raise ValueError("build_magnetic_rows: allgather_deg must return a float32 [n] tensor")
+        deg_all = deg_all.contiguous()
+        _lib.check(lib.pgsd_build_magnetic_rows_finish(
+            row_ptr.data_ptr(), col.data_ptr(), vr.data_ptr(), vi.data_ptr(), deg_all.data_ptr(), n, row_lo,
+            row_hi, float(q), 1 if normalization == "sym" else 0, float(lambda_max), vr.data_ptr(),
+            vi.data_ptr(), diag.data_ptr(), _stream_ptr(dev)), "pgsd_build_magnetic_rows_finish")
+    k = nnz.value
+    # compact the 2E-capacity arrays (a shard keeps ~1/world of them)
+    col, vr, vi = col[:k].clone(), vr[:k].clone(), vi[:k].clone()
+    meta = {"q": q, "normalization": normalization, "lambda_max": float(lambda_max), "diag_real": diag[:nl],
+            "row_lo": row_lo}
+    if normalization == "sym":
+        import numpy as np
+        dc = float(np.float32(np.float32(2.0) / np.float32(lambda_max)) - np.float32(1.0))
+        return CSRPlan(nl, n, k, e, row_ptr, col, [vr, vi], [None, None], [dc, 0.0], meta=meta)
+    return CSRPlan(nl, n, k, e, row_ptr, col, [vr, vi], [diag[:nl], None], [0.0, 0.0], meta=meta)
+
+
 def magnetic_cached_result(plan: CSRPlan):
     """Re-materialise MagNetConv.cached_result (nn/directed/MagNetConv.py:181) from a plan:
     (edge_index_real [2, nnz+2N], edge_index_imag [2, nnz+N], norm_real, norm_imag).

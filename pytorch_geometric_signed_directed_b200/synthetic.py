@@ -109,6 +109,27 @@ def dsbm_edges(n: int, k: int = 3, p: Optional[float] = None, num_edges: Optiona
     return edge_index[:, order].contiguous(), labels
 
 
+def locality_edges(n: int, num_edges: int, band: int, long_range: float = 0.0, seed: int = 0,
+                   device: str = "cpu") -> Tensor:
+    """A directed graph whose edge list shards naturally under a 1-D node-range split: node ids
+    carry locality (a road network / mesh / time-ordered citation graph after a bandwidth-reducing
+    ordering), every edge i -> j has |i - j| <= band, except a `long_range` share that lands
+    anywhere.  No reference counterpart (the reference has no distributed path); used to exercise
+    the halo exchange of distributed.py.  Returns edge_index int64 [2, E'] (self-loops and
+    duplicates removed, edge order shuffled)."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    src = torch.randint(0, n, (num_edges,), generator=gen, device=device)
+    off = torch.randint(-band, band + 1, (num_edges,), generator=gen, device=device)
+    dst = (src + off).clamp_(0, n - 1)
+    if long_range > 0:
+        far = torch.rand(num_edges, generator=gen, device=device) < long_range
+        dst = torch.where(far, torch.randint(0, n, (num_edges,), generator=gen, device=device), dst)
+    keep = src != dst
+    src, dst = _dedup(src[keep], dst[keep], n)
+    order = torch.randperm(src.numel(), generator=gen, device=device)
+    return torch.stack([src[order], dst[order]]).contiguous()
+
+
 def ssbm_edges(n: int, k: int = 3, p: Optional[float] = None, num_entries: Optional[int] = None,
                eta: float = 0.1, size_ratio: float = 2.0, seed: int = 0,
                device: str = "cpu") -> Tuple[Tensor, Tensor, Tensor]:

@@ -82,6 +82,61 @@ def _worker(rank, world, port_no, n, e, f):
         dist.destroy_process_group()
 
 
+def _torch_gather(x, index, out=None):
+    res = x[index.long()]
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+def _halo_worker(rank, world, port_no, n, e, f, band, long_range):
+    """Halo path: request lists through all-to-all, per-step pack -> all_to_all_single -> two blocks."""
+    from pytorch_geometric_signed_directed_b200 import synthetic
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ei = synthetic.locality_edges(n, e, band, long_range, seed=3)
+        g = torch.Generator().manual_seed(1)
+        xr = torch.rand(n, f, generator=g) * 2 - 1
+        xi = torch.rand(n, f, generator=g) * 2 - 1
+        full = _plan_from_oracle(ei, n)
+        bounds = pgd.node_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        local = pgd.split_rows(full, lo, hi)
+        own, halo, need = pgd.split_local_and_halo(local, bounds, rank)
+        assert own.nnz + halo.nnz == local.nnz and need[rank].numel() == 0
+        # the compact columns of the halo block index the concatenation of the need lists
+        cat = torch.cat([need[b].long() + bounds[b] for b in range(world)])
+        counts = (local.row_ptr[1:] - local.row_ptr[:-1]).long()
+        colg = local.col.long()
+        remote = (colg < lo) | (colg >= hi)
+        assert torch.equal(cat[halo.col.long()], colg[remote])                  # same entries, same order
+        assert torch.equal(cat, torch.unique(colg[remote]))                     # sorted, distinct
+        agg = pgd.ShardedAggregator(local, bounds, rank, world, aggregate_fn=_torch_aggregate, mode="auto",
+                                    gather_fn=_torch_gather)
+        expect_halo = long_range == 0.0
+        assert agg.mode == ("halo" if expect_halo else "ring"), (agg.mode, agg.halo_fraction)
+        if expect_halo:
+            assert agg.halo.n_recv == cat.numel() and agg.halo_fraction < 0.5
+            # what the peers were told to serve is exactly what this rank needs (round trip)
+            got = torch.empty(agg.halo.n_recv, dtype=torch.int32)
+            pgd._all_to_all(got, agg.halo.serve + lo, agg.halo.need_splits, agg.halo.serve_splits)
+            assert torch.equal(got.long(), cat)
+        ref = _torch_aggregate(full, [xr, xi], (0, 1), 1.0, 0.0, None, None)
+        t1 = agg([xr[lo:hi], xi[lo:hi]])
+        for k in range(2):
+            assert torch.allclose(t1[k], ref[k][lo:hi], atol=1e-5), f"rank {rank} op {k}"
+        ref2 = _torch_aggregate(full, ref, (0, 1), 2.0, -1.0, [xr, xi], None)
+        t2 = agg(t1, alpha=2.0, beta=-1.0, zs=[xr[lo:hi], xi[lo:hi]])
+        t2b = agg(t1, alpha=2.0, beta=-1.0, zs=[xr[lo:hi], xi[lo:hi]])          # buffers are reused
+        for k in range(2):
+            assert torch.allclose(t2[k], ref2[k][lo:hi], atol=1e-5), f"rank {rank} cheb op {k}"
+            assert torch.equal(t2[k], t2b[k])
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -100,3 +155,43 @@ def test_node_bounds_and_ring_schedule():
     assert pgd.node_bounds(8_000_000, 8)[-1] == 8_000_000
     ring = pgd.RingExchange(rank=1, world=4)
     assert [ring.source_of_round(s) for s in (1, 2, 3)] == [0, 3, 2]
+
+
+@pytest.mark.parametrize("world,long_range", [(2, 0.0), (3, 0.0), (2, 0.2)])
+def test_halo_exchange_on_a_naturally_sharding_graph(world, long_range):
+    """Locality-ordered graph: thin halo -> `auto` picks the all-to-all halo path; with 20 % long-range
+    edges the halo is most of the matrix and `auto` must fall back to the ring all-gather."""
+    mp.spawn(_halo_worker, args=(world, _free_port(), 600, 9000, 8, 25, long_range), nprocs=world, join=True)
+
+
+def test_halo_fraction():
+    need = [torch.arange(3, dtype=torch.int32), torch.empty(0, dtype=torch.int32), torch.arange(5, dtype=torch.int32)]
+    assert pgd.halo_fraction(need, [0, 10, 20, 30], 1) == 8 / 20
+
+
+def _route_worker(rank, world, port_no, n, e):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        ei = torch.randint(0, n, (2, e), generator=g)
+        ew = torch.rand(e, generator=g) - 0.5
+        bounds = pgd.node_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        cuts = [(r * e) // world for r in range(world + 1)]            # contiguous slices of the edge list
+        sl = slice(cuts[rank], cuts[rank + 1])
+        want_ei, want_ew = pgd.incident_edges(ei, ew, lo, hi)
+        got_ei, got_ew = pgd.route_edges(ei[:, sl].contiguous(), ew[sl].contiguous(), bounds, rank, world)
+        assert torch.equal(got_ei, want_ei) and torch.equal(got_ew, want_ew)     # same edges, ORIGINAL order
+        got_ei2, none = pgd.route_edges(ei[:, sl].contiguous(), None, bounds, rank, world)
+        assert none is None and torch.equal(got_ei2, want_ei)
+        # uneven shards: all-gather of per-shard vectors
+        mine = torch.arange(lo, hi, dtype=torch.float32) * 0.5
+        assert torch.equal(pgd.allgather_rows(mine, bounds), torch.arange(n, dtype=torch.float32) * 0.5)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_edge_routing_for_the_distributed_build(world):
+    mp.spawn(_route_worker, args=(world, _free_port(), 101, 3000), nprocs=world, join=True)

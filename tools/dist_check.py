@@ -1,8 +1,11 @@
 """Run under torchrun (NCCL): the node-range sharded MagNetConv must reproduce the single-GPU
-layer bit-for-bit in structure and to rounding in values.  Usage:
+layer to rounding, on a permuted DSBM graph (halo = whole matrix -> ring all-gather) and on a
+locality-ordered graph (thin halo -> all-to-all of packed halo rows).  Usage:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29533 tools/dist_check.py
+        --master-port 29533 tools/dist_check.py [--bench]
+`--bench` additionally times the sharded step of the halo path at 1M nodes / 20M edges per rank.
 """
+import json
 import os
 import sys
 
@@ -19,32 +22,70 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 
 n_total, e_total, f = 50_000 * world + 37, 1_000_000 * world, 64
-ei, _ = synthetic.dsbm_edges(n_total, 3, num_edges=e_total, seed=0, device=dev)
 gen = torch.Generator(device=dev).manual_seed(7)          # same stream on every rank
 x_real = torch.rand(n_total, f, generator=gen, device=dev) * 2 - 1
 x_imag = torch.rand(n_total, f, generator=gen, device=dev) * 2 - 1
-ok = True
-for K in (1, 2):
-    torch.manual_seed(K)
-    conv = nn.MagNetConv(f, f, K=K, q=0.25, trainable_q=False, cached=True).to(dev)
-    with torch.no_grad():
-        conv.bias.uniform_(-0.2, 0.2)
-    full_r, full_i = conv(x_real, x_imag, ei)
-    sh = pgd.ShardedMagNetConv(conv, n_total, rank, world).build(ei)
-    lo, hi = sh.bounds[rank], sh.bounds[rank + 1]
-    for it in range(3):                                   # repeated calls reuse the recv buffers
-        out_r, out_i = sh(x_real[lo:hi].contiguous(), x_imag[lo:hi].contiguous())
-    torch.cuda.synchronize()
-    for got, ref, nm in ((out_r, full_r[lo:hi], "real"), (out_i, full_i[lo:hi], "imag")):
-        err = (got - ref).abs().max().item()
-        scale = ref.abs().max().item()
-        good = err <= 2e-6 * scale
-        ok &= good
-        print(f"[rank {rank}] K={K} out_{nm}: max err {err:.3e} (scale {scale:.3e}) {'OK' if good else 'FAIL'}",
-              flush=True)
+
+
+def check(gname, want_mode, ei):
+    ok = True
+    for K in (1, 2):
+        torch.manual_seed(K)
+        conv = nn.MagNetConv(f, f, K=K, q=0.25, trainable_q=False, cached=True).to(dev)
+        with torch.no_grad():
+            conv.bias.uniform_(-0.2, 0.2)
+        full_r, full_i = conv(x_real, x_imag, ei)
+        sh = pgd.ShardedMagNetConv(conv, n_total, rank, world).build(ei)
+        lo, hi = sh.bounds[rank], sh.bounds[rank + 1]
+        for it in range(3):                                   # repeated calls reuse the buffers
+            out_r, out_i = sh(x_real[lo:hi].contiguous(), x_imag[lo:hi].contiguous())
+        torch.cuda.synchronize()
+        ok &= sh.agg.mode == want_mode
+        for got, ref, nm in ((out_r, full_r[lo:hi], "real"), (out_i, full_i[lo:hi], "imag")):
+            err = (got - ref).abs().max().item()
+            scale = ref.abs().max().item()
+            good = err <= 2e-6 * scale
+            ok &= good
+            print(f"[rank {rank}] {gname} mode={sh.agg.mode} K={K} out_{nm}: max err {err:.3e} "
+                  f"(scale {scale:.3e}) {'OK' if good else 'FAIL'}", flush=True)
+    return ok
+
+
+ok = check("dsbm", "ring", synthetic.dsbm_edges(n_total, 3, num_edges=e_total, seed=0, device=dev)[0])
+ok &= check("local", "halo", synthetic.locality_edges(n_total, e_total, 2000, 0.0, seed=0, device=dev))
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("DIST_CHECK", "PASS" if flag.item() == 1 else "FAIL", f"world={world}", flush=True)
+
+if "--bench" in sys.argv and flag.item() == 1:
+    # weak scaling of the halo path: 1M nodes / 20M edges per rank, |i - j| <= 50k
+    del x_real, x_imag
+    n_b, e_b = 1_000_000 * world, 20_000_000 * world
+    ei = synthetic.locality_edges(n_b, e_b, 50_000, 0.0, seed=1, device=dev)
+    conv = nn.MagNetConv(f, f, K=1, q=0.25, trainable_q=False, cached=True).to(dev)
+    sh = pgd.ShardedMagNetConv(conv, n_b, rank, world).build(ei)
+    e_in = ei.size(1)
+    del ei
+    xr = torch.rand(sh.n_local, f, device=dev) * 2 - 1
+    xi = torch.rand(sh.n_local, f, device=dev) * 2 - 1
+    with torch.no_grad():
+        for _ in range(5):
+            sh(xr, xi)
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            sh(xr, xi)
+        b.record()
+        dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / 20], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"what": "halo_path_weak_scaling", "world": world, "mode": sh.agg.mode,
+                          "halo_fraction": sh.agg.halo_fraction, "ms_per_step": t.item(),
+                          "edges_per_s": e_in / (t.item() * 1e-3), "edges_total": e_in,
+                          "halo_rows_received_rank0": sh.agg.halo.n_recv if sh.agg.halo else None,
+                          "graph": "locality_edges band=50k, 1M nodes / 20M edges per rank"}), flush=True)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)
