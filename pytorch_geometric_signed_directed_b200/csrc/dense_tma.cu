@@ -10,7 +10,7 @@
 //   warp 0      : TMA producer -- one thread issues cp.async.bulk.tensor.2d per [128 rows x 128 B] chunk
 //                 (SWIZZLE_128B tensor maps, one per term; rows / k past the end are zero-filled by
 //                 the TMA unit) into an S-stage ring, completion on the stage's `full` mbarrier;
-//   warps 6..13 : converters (fp32 only) -- split the landed chunk into TF32 hi (in place, same bytes) and
+//   warps 10..17: converters (fp32 only) -- split the landed chunk into TF32 hi (in place, same bytes) and
 //                 lo (a slot of a SHORT second ring: a lo image lives only from the split to the end of
 //                 its MMAs, so 2-3 slots serve any number of landing stages and the shared memory
 //                 they save buys landing stages = bytes in flight), fence.proxy.async, arrive on `conv`;
@@ -18,8 +18,10 @@
 //   warp 1      : MMA issuer -- waits `conv` (fp32) / `full` (bf16), issues the tcgen05.mma chain of the
 //                 chunk, tcgen05.commit -> `empty` (stage back to the producer); the last chunk of a
 //                 tile also commits to `acc_full`;
-//   warps 2..5  : epilogue -- tcgen05.ld of the finished accumulators (TMEM double-buffered, so tile
-//                 t+1 accumulates while tile t is stored), mix/bias/mask, streaming stores.
+//   warps 2..9  : epilogue -- tcgen05.ld of the finished accumulators (TMEM double-buffered, so tile
+//                 t+1 accumulates while tile t is stored; two warps per TMEM lane quarter), mix/bias/mask,
+//                 swizzled staging tile in shared memory, one TMA store per [128 rows x 128 B] box
+//                 (rows narrower than 128 B: per-lane streaming stores).
 #include <cuda.h>
 
 #include "tc_common.cuh"
@@ -33,13 +35,14 @@ constexpr int MAX_TERMS = PGSD_DENSE_MAX_TERMS;
 constexpr int MAX_CHUNKS = 2 * PGSD_DENSE_MAX_TERMS;
 constexpr int MAX_SLABS = 16;
 constexpr int MAX_STAGES = 12;
-constexpr int MAX_LO = 4;
+constexpr int MAX_LO = 6;
 constexpr int CHUNK_BYTES = TILE_M * 128;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;    // two per TMEM lane quarter, alternating 16-column blocks
 constexpr int CONV_WARPS = 8;
 
 struct alignas(64) Params {
   CUtensorMap maps[MAX_TERMS];     // one [n_rows, k_t] tensor per term, box = [128 rows, 128 bytes]
+  CUtensorMap out_maps[2];         // outputs, same box (epilogue: registers -> swizzled staging -> TMA store)
   int64_t n_rows;
   int32_t n_chunks, n_slabs, relu_mode, n_total, stages, lo_stages;
   int16_t k0[MAX_CHUNKS];          // first k (elements) of the chunk inside its term
@@ -53,10 +56,25 @@ struct alignas(64) Params {
   const float* bias;
   char* y[2];
   int64_t ldy_bytes[2];
+  int32_t conv_groups;             // converter warps work on this many chunks at once (1, 2 or 4)
+  int32_t dbg;                     // timing experiments only (variant bits 16-18): 1 no stores, 2 no split, 4 no MMAs
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the staging buffers of all committed stores have been read (they may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(8 * 32) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -86,6 +104,9 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   constexpr int SLAB_BYTES = BF16 ? HALF : 2 * HALF;
   constexpr int UMMA_K_BYTES = 32;
   constexpr int ACC_COLS = GROUPS * N_OUT;
+  // output rows of at least 128 B leave through TMA stores; narrower ones through per-lane stores
+  constexpr bool TMA_STORE = N_OUT * ES >= 128;
+  constexpr int CBR = 128 / (16 * ES);           // 16-column blocks per 128-byte box row: 2 (fp32) / 4 (bf16)
   constexpr uint32_t TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64
                                : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   constexpr uint32_t FMT = BF16 ? 1u : 2u;
@@ -97,7 +118,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   const int S = p.stages, L = BF16 ? 0 : p.lo_stages;
   uint8_t* a_stage = smem;
   uint8_t* lo_ring = smem + S * STAGE_BYTES;
-  uint8_t* w_smem = lo_ring + L * CHUNK_BYTES;
+  uint8_t* out_stage = lo_ring + L * CHUNK_BYTES;            // GROUPS boxes of [128 rows x 128 B]
+  uint8_t* w_smem = out_stage + (TMA_STORE ? GROUPS * CHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.n_slabs * SLAB_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + MAX_LO + 4);
 
@@ -117,7 +139,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   if (tid == 32) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, NCV > 0 ? NCV : 1);
+      mbar_init(bar_conv + 8 * s, NCV > 0 ? NCV / p.conv_groups : 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < MAX_LO; ++s) mbar_init(bar_lo_empty + 8 * s, 1);
@@ -167,41 +189,48 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
     }
   } else if (warp == 1) {
     // ========================================================================== MMA issuer
-    uint32_t uses = 0, it = 0;
+    // The whole warp runs this loop converged (all operands stay warp-uniform); one elected lane issues.
+    const uint32_t a_lo32 = desc_lo(a_addr), l_lo32 = BF16 ? 0u : desc_lo(lo_addr), w_lo32 = desc_lo(w_addr);
+    constexpr uint32_t KSTEP = UMMA_K_BYTES >> 4;              // descriptor units per MMA along K
+    uint32_t uses = 0, it = 0, stage = 0, ls = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       if (it >= 2) mbar_wait_relaxed(bar_acc_empty + 8 * acc, ((it >> 1) - 1) & 1);   // epilogue drained this buffer
       for (int c = 0; c < p.n_chunks; ++c, ++uses) {
-        const uint32_t stage = uses % S;
         mbar_wait_relaxed((BF16 ? bar_full : bar_conv) + 8 * stage, (uses / S) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t d = tmem_base + acc * ACC_COLS + uint32_t(p.group[c]) * N_OUT;
-          const uint32_t a_hi = a_addr + stage * STAGE_BYTES;
-          const uint32_t a_lo = BF16 ? 0u : lo_addr + (uses % uint32_t(L > 0 ? L : 1)) * CHUNK_BYTES;
-          const uint32_t w_hi = w_addr + uint32_t(p.slab[c]) * SLAB_BYTES, w_lo = w_hi + HALF;
+        const uint32_t d = tmem_base + acc * ACC_COLS + uint32_t(p.group[c]) * N_OUT;
+        const uint32_t da_hi = a_lo32 + stage * (STAGE_BYTES >> 4);
+        const uint32_t da_lo = l_lo32 + ls * (CHUNK_BYTES >> 4);
+        const uint32_t dw_hi = w_lo32 + uint32_t(p.slab[c]) * (SLAB_BYTES >> 4), dw_lo = dw_hi + (HALF >> 4);
+        const uint32_t acc0 = p.first[c] ? 0u : 1u;
+        if (elect_one()) {
+          if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int j = 0; j < 128 / UMMA_K_BYTES; ++j) {
-            const uint32_t ko = j * UMMA_K_BYTES;
-            const uint32_t acc0 = (p.first[c] && j == 0) ? 0u : 1u;
-            if constexpr (BF16) {
-              mma_bf16(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
-            } else {
-              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_hi + ko), IDESC, acc0);
-              mma_tf32(d, make_desc(a_lo + ko), make_desc(w_hi + ko), IDESC, 1u);
-              mma_tf32(d, make_desc(a_hi + ko), make_desc(w_lo + ko), IDESC, 1u);
+            for (int j = 0; j < 128 / UMMA_K_BYTES; ++j) {
+              if constexpr (BF16) {
+                mma_lo<true>(d, da_hi + j * KSTEP, dw_hi + j * KSTEP, IDESC, j == 0 ? acc0 : 1u);
+              } else {
+                mma_lo<false>(d, da_hi + j * KSTEP, dw_hi + j * KSTEP, IDESC, j == 0 ? acc0 : 1u);
+                mma_lo<false>(d, da_lo + j * KSTEP, dw_hi + j * KSTEP, IDESC, 1u);
+                mma_lo<false>(d, da_hi + j * KSTEP, dw_lo + j * KSTEP, IDESC, 1u);
+              }
             }
           }
           tc_commit(bar_empty + 8 * stage);
-          if constexpr (!BF16) tc_commit(bar_lo_empty + 8 * (uses % uint32_t(L)));
+          if constexpr (!BF16) tc_commit(bar_lo_empty + 8 * ls);
           if (c == p.n_chunks - 1) tc_commit(bar_acc_full + 8 * acc);
         }
         __syncwarp();
+        stage = (stage + 1 == uint32_t(S)) ? 0u : stage + 1;
+        if constexpr (!BF16) ls = (ls + 1 == uint32_t(L)) ? 0u : ls + 1;
       }
     }
   } else if (warp < 2 + EPI_WARPS) {
     // ============================================================================ epilogue
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;            // which of the two warps of the quarter: even / odd column blocks
+    constexpr int NCB = N_OUT / 16;
     const uint64_t pol_stream = policy_evict_first();
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -210,29 +239,102 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
       tc_fence_after();
       const int64_t row = tile * TILE_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
+      if constexpr (TMA_STORE) {
+        // rounds of one 128-byte-wide box per group: tcgen05.ld -> mix/bias/mask -> swizzled staging
+        // (conflict-free: lane = row, 16-byte unit ^ (row & 7)) -> one TMA store per group.  Full-line,
+        // asynchronous writes instead of 32 scattered 16-byte pieces per store instruction.
+        const uint32_t st_addr = smem_u32(out_stage) + uint32_t(q * 32 + lane) * 128;
 #pragma unroll 1
-      for (int cb = 0; cb < N_OUT / 16; ++cb) {
-        float a[16], b[16];
+        for (int rd = 0; rd < NCB / CBR; ++rd) {
+          if (warp == 2 && lane == 0) tma_store_wait_read();   // staging of the previous round is free
+          epi_bar_sync();
+#pragma unroll 1
+          for (int k = half; k < CBR; k += 2) {
+            const int cb = rd * CBR + k;
+            float a[16], b[16], bs[16];
+            tmem_ld<16>(taddr + cb * 16, a);
+            if (GROUPS == 2) tmem_ld<16>(taddr + N_OUT + cb * 16, b);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)           // issued while the TMEM loads are in flight
+              bs[i] = (p.bias && n0 + cb * 16 + i < p.n_total) ? __ldg(p.bias + n0 + cb * 16 + i) : 0.f;
+            tmem_ld_wait();
+            if (rd == NCB / CBR - 1 && k + 2 >= CBR) {   // last TMEM read of this warp for this buffer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (GROUPS == 2) {
+                const float o0 = (a[i] - b[i]) + bs[i], o1 = (a[i] + b[i]) + bs[i];
+                const float m = (p.relu_mode == 1 && !(o0 >= 0.f)) ? 0.f : 1.f;
+                a[i] = p.relu_mode == 1 ? o0 * m : o0;
+                b[i] = p.relu_mode == 1 ? o1 * m : o1;
+              } else {
+                a[i] = a[i] + bs[i];
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+              const float* o = g ? b : a;
+              const uint32_t base = st_addr + g * CHUNK_BYTES;
+              if constexpr (BF16) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  float4 pk;
+                  pk.x = __uint_as_float(pack_bf16(o[8 * j], o[8 * j + 1]));
+                  pk.y = __uint_as_float(pack_bf16(o[8 * j + 2], o[8 * j + 3]));
+                  pk.z = __uint_as_float(pack_bf16(o[8 * j + 4], o[8 * j + 5]));
+                  pk.w = __uint_as_float(pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+                  sts_v4(base + (uint32_t((k * 2 + j) ^ (lane & 7)) << 4), pk);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts_v4(base + (uint32_t((k * 4 + j) ^ (lane & 7)) << 4),
+                         make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+              }
+            }
+          }
+          fence_async_smem();
+          epi_bar_sync();
+          if (warp == 2 && lane == 0 && !(p.dbg & 1)) {
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g)
+              tma_store_2d(&p.out_maps[g], n0 + rd * CBR * 16, int(tile * TILE_M), smem_u32(out_stage) + g * CHUNK_BYTES);
+            tma_store_commit();
+          }
+        }
+      } else {
+      if (half >= NCB) {                         // N_OUT = 16: the odd warps have no column block
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      }
+#pragma unroll 1
+      for (int cb = half; cb < NCB; cb += 2) {
+        float a[16], b[16], bs[16];
         tmem_ld<16>(taddr + cb * 16, a);
         if (GROUPS == 2) tmem_ld<16>(taddr + N_OUT + cb * 16, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)             // issued while the TMEM loads are in flight
+          bs[i] = (p.bias && n0 + cb * 16 + i < p.n_total) ? __ldg(p.bias + n0 + cb * 16 + i) : 0.f;
         tmem_ld_wait();
-        if (cb == N_OUT / 16 - 1) {              // everything of this buffer is in registers
+        if (cb + 2 >= NCB) {                     // everything this warp reads of the buffer is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
         }
         const int ncol = n0 + cb * 16;
-        if (row < p.n_rows && ncol < p.n_total) {
+        if (row < p.n_rows && ncol < p.n_total && !(p.dbg & 1)) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float bs = p.bias ? __ldg(p.bias + ncol + i) : 0.f;
             if (GROUPS == 2) {
-              const float o0 = (a[i] - b[i]) + bs, o1 = (a[i] + b[i]) + bs;
+              const float o0 = (a[i] - b[i]) + bs[i], o1 = (a[i] + b[i]) + bs[i];
               const float m = (p.relu_mode == 1 && !(o0 >= 0.f)) ? 0.f : 1.f;
               a[i] = p.relu_mode == 1 ? o0 * m : o0;
               b[i] = p.relu_mode == 1 ? o1 * m : o1;
             } else {
-              a[i] = a[i] + bs;
+              a[i] = a[i] + bs[i];
             }
           }
 #pragma unroll
@@ -257,37 +359,51 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
           }
         }
       }
+      }
     }
+    if (TMA_STORE && warp == 2 && lane == 0) tma_store_wait_all();   // global writes complete before exit
   } else {
     // ================================================================ converters (fp32 only)
     if constexpr (!BF16) {
-      const int ct = tid - (2 + EPI_WARPS) * 32;           // 0 .. NCV*32-1
-      constexpr int UNITS = CHUNK_BYTES / 16 / (NCV * 32);  // 16-byte units per thread and chunk
-      uint32_t uses = 0;
+      // G groups of NCV / G warps; group g splits the chunks u = g (mod G), so G chunks are in
+      // conversion at once and the LDS -> split -> STS -> fence.proxy.async -> arrive latency of one
+      // chunk overlaps the next ones' (with one group that chain paced the whole kernel)
+      const int cw = warp - (2 + EPI_WARPS);                // 0 .. NCV-1
+      const int G = p.conv_groups, wpg = NCV / G;
+      const int grp = cw % G, tig = (cw / G) * 32 + lane;   // thread inside its group
+      const uint32_t gstride = uint32_t(wpg) * 32 * 16;     // bytes between the units of one thread
+      uint32_t uses = 0, stage = 0, ls = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int c = 0; c < p.n_chunks; ++c, ++uses) {
-          const uint32_t stage = uses % S;
-          const uint32_t ls = uses % uint32_t(L);
-          mbar_wait_relaxed(bar_full + 8 * stage, (uses / S) & 1);
-          const uint32_t hi = a_addr + stage * STAGE_BYTES + ct * 16, lo = lo_addr + ls * CHUNK_BYTES + ct * 16;
-          float4 v[UNITS];
+          if (int(uses % uint32_t(G)) == grp) {
+            mbar_wait_relaxed(bar_full + 8 * stage, (uses / S) & 1);
+            // the lo slot is free once the MMAs of the chunk that used it last (L chunks ago) completed
+            if (uses >= uint32_t(L)) mbar_wait_relaxed(bar_lo_empty + 8 * ls, ((uses / L) - 1) & 1);
+            const uint32_t hi = a_addr + stage * STAGE_BYTES + tig * 16, lo = lo_addr + ls * CHUNK_BYTES + tig * 16;
+            if (!(p.dbg & 2)) {
+              for (int b = 0; b < G; ++b) {                 // 4 G units per thread, 4 at a time
+                const uint32_t ob = uint32_t(b) * 4 * gstride;
+                float4 v[4];
 #pragma unroll
-          for (int i = 0; i < UNITS; ++i) v[i] = lds_v4(hi + i * NCV * 32 * 16);
-          // the lo slot is free once the MMAs of the chunk that used it last (L chunks ago) completed
-          if (uses >= uint32_t(L)) mbar_wait_relaxed(bar_lo_empty + 8 * ls, ((uses / L) - 1) & 1);
+                for (int i = 0; i < 4; ++i) v[i] = lds_v4(hi + ob + i * gstride);
 #pragma unroll
-          for (int i = 0; i < UNITS; ++i) {
-            // the split is position-independent: unit q of the landed (swizzled) image stays unit q
-            float4 vh, vl;
-            vh.x = to_tf32(v[i].x), vh.y = to_tf32(v[i].y), vh.z = to_tf32(v[i].z), vh.w = to_tf32(v[i].w);
-            vl.x = to_tf32(v[i].x - vh.x), vl.y = to_tf32(v[i].y - vh.y);
-            vl.z = to_tf32(v[i].z - vh.z), vl.w = to_tf32(v[i].w - vh.w);
-            sts_v4(hi + i * NCV * 32 * 16, vh);
-            sts_v4(lo + i * NCV * 32 * 16, vl);
+                for (int i = 0; i < 4; ++i) {
+                  // the split is position-independent: unit q of the landed (swizzled) image stays unit q
+                  float4 vh, vl;
+                  vh.x = to_tf32(v[i].x), vh.y = to_tf32(v[i].y), vh.z = to_tf32(v[i].z), vh.w = to_tf32(v[i].w);
+                  vl.x = to_tf32(v[i].x - vh.x), vl.y = to_tf32(v[i].y - vh.y);
+                  vl.z = to_tf32(v[i].z - vh.z), vl.w = to_tf32(v[i].w - vh.w);
+                  sts_v4(hi + ob + i * gstride, vh);
+                  sts_v4(lo + ob + i * gstride, vl);
+                }
+              }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_conv + 8 * stage);
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_conv + 8 * stage);
+          stage = (stage + 1 == uint32_t(S)) ? 0u : stage + 1;
+          ls = (ls + 1 == uint32_t(L)) ? 0u : ls + 1;
         }
       }
     }
@@ -302,21 +418,32 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   }
 }
 
-static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_stages) {
-  return 1024 + size_t(stages + (bf16 ? 0 : lo_stages)) * CHUNK_BYTES +
+static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_stages, int groups) {
+  const bool tma_store = n_tile * (bf16 ? 2 : 4) >= 128;
+  return 1024 + size_t(stages + (bf16 ? 0 : lo_stages) + (tma_store ? groups : 0)) * CHUNK_BYTES +
          size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (3 * MAX_STAGES + MAX_LO + 4) + 16;
 }
 
 template <int N_OUT, int GROUPS, bool BF16>
-static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo) {
-  // experiment knobs ride in the variant word (bits 8-11: lo slots, bits 12-15: landing stages); 0 = default
-  const int lo = BF16 ? 0 : (want_lo >= 1 && want_lo <= MAX_LO ? want_lo : 2);
+static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int want_cg) {
+  // experiment knobs ride in the variant word (bits 8-11: lo slots, bits 12-15: landing stages,
+  // bits 20-22: converter groups); 0 = default
+  // Ring invariants (mbarrier waits only tell odd from even phases, so no waiter may run a whole phase
+  // ahead): converter groups <= landing stages <= 2 * lo slots.  Preferred: 2 groups, 3 lo slots; shapes
+  // whose weights leave little shared memory fall back to 1 group, 2 lo slots.
+  int cg = (want_cg == 1 || want_cg == 2 || want_cg == 4) ? want_cg : 2;
+  int lo = BF16 ? 0 : (want_lo >= 1 && want_lo <= MAX_LO ? want_lo : cg + 1);
+  const size_t budget = 220 * 1024;
+  if (!BF16 && smem_bytes(p.n_slabs, N_OUT, BF16, 3, lo, GROUPS) > budget) cg = 1, lo = 2;
   int stages = (want_stages >= 2 && want_stages <= MAX_STAGES) ? want_stages : MAX_STAGES;
-  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo) > 220 * 1024) --stages;
-  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo) > 220 * 1024) return -1;
+  if (!BF16 && stages > 2 * lo) stages = 2 * lo;
+  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, GROUPS) > budget) --stages;
+  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, GROUPS) > budget) return -1;
+  if (cg > stages) cg = stages >= 2 ? 2 : 1;
+  p.conv_groups = cg;
   p.stages = stages;
   p.lo_stages = lo;
-  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo);
+  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, GROUPS);
   auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
@@ -377,6 +504,17 @@ int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
     if (!al16(a->y[i]) || ((a->ldy[i] * es) & 15)) return PGSD_OK;
     p.y[i] = static_cast<char*>(a->y[i]);
     p.ldy_bytes[i] = a->ldy[i] * es;
+    if (n_tile * es >= 128) {                 // TMA-store epilogue: [n_rows, n_out] tensor, box = [128 rows, 128 B]
+      const cuuint64_t gdim[2] = {cuuint64_t(n), cuuint64_t(a->n_rows)};
+      const cuuint64_t gstride[1] = {cuuint64_t(a->ldy[i]) * es};
+      const cuuint32_t box[2] = {cuuint32_t(ck), cuuint32_t(TILE_M)};
+      const cuuint32_t estride[2] = {1, 1};
+      const CUresult r = enc(&p.out_maps[i], bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                             2, a->y[i], gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return PGSD_OK;
+    }
   }
   bool seen_group[2] = {false, false};
   for (int t = 0; t < a->n_terms; ++t) {
@@ -415,12 +553,14 @@ int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   if (groups == 2 && !(seen_group[0] && seen_group[1])) return PGSD_OK;
   int rc = -1;
   const int ws = (a->variant >> 12) & 0xf, wl = (a->variant >> 8) & 0xf;
+  p.dbg = (a->variant >> 16) & 7;
+  const int wg = (a->variant >> 20) & 7;
 #define PGSD_TMA(N_)                                                                                        \
-  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl) : launch<N_, 1, true>(p, st, ws, wl);     \
-  else rc = groups == 2 ? launch<N_, 2, false>(p, st, ws, wl) : launch<N_, 1, false>(p, st, ws, wl);        \
+  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl, wg) : launch<N_, 1, true>(p, st, ws, wl, wg);     \
+  else rc = groups == 2 ? launch<N_, 2, false>(p, st, ws, wl, wg) : launch<N_, 1, false>(p, st, ws, wl, wg);        \
   break;
   switch (n_tile) {
-    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st, ws, wl) : launch<16, 1, false>(p, st, ws, wl); break;
+    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st, ws, wl, wg) : launch<16, 1, false>(p, st, ws, wl, wg); break;
     case 32: PGSD_TMA(32)
     case 64: PGSD_TMA(64)
     default: PGSD_TMA(128)

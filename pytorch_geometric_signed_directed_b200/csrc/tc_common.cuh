@@ -73,6 +73,56 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t 
       : "memory");
 }
 
+// The same MMAs with the descriptors split into their 32-bit halves: the high word of a K-major
+// SWIZZLE_128B descriptor is a constant and the low word is (address >> 4) | 1 << 16, so stepping along
+// K or to another stage is ONE 32-bit add on the low word.  The single MMA-issuing thread is the pacing
+// resource of the transform kernels (measured: ~160 cycles per MMA with make_desc() per operand, against
+// a tensor-pipe floor of 32), so every instruction between two UTCHMMAs counts.
+constexpr uint32_t DESC_HI = uint32_t(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <bool BF16>
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t da_lo, uint32_t db_lo, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(da_lo), "r"(db_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(da_lo), "r"(db_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+  }
+}
+// one lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers when the
+// surrounding code is not divergent, which `if (lane == 0)` is)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 template <int CPW>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[CPW]);
 template <>
