@@ -57,6 +57,7 @@ struct alignas(64) Params {
   char* y[2];
   int64_t ldy_bytes[2];
   int32_t conv_groups;             // converter warps work on this many chunks at once (1, 2 or 4)
+  int32_t epi_rb, epi_ns;          // epilogue staging: boxes per group and round, staging sets (1 or 2)
   int32_t dbg;                     // timing experiments only (variant bits 16-18): 1 no stores, 2 no split, 4 no MMAs
 };
 
@@ -72,6 +73,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the staging buffers of all committed stores have been read (they may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(8 * 32) : "memory");
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   uint8_t* a_stage = smem;
   uint8_t* lo_ring = smem + S * STAGE_BYTES;
   uint8_t* out_stage = lo_ring + L * CHUNK_BYTES;            // GROUPS boxes of [128 rows x 128 B]
-  uint8_t* w_smem = out_stage + (TMA_STORE ? GROUPS * CHUNK_BYTES : 0);
+  uint8_t* w_smem = out_stage + (TMA_STORE ? p.epi_ns * p.epi_rb * GROUPS * CHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + p.n_slabs * SLAB_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + MAX_LO + 4);
 
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
     const int half = (warp - 2) >> 2;            // which of the two warps of the quarter: even / odd column blocks
     constexpr int NCB = N_OUT / 16;
     const uint64_t pol_stream = policy_evict_first();
-    uint32_t it = 0;
+    uint32_t it = 0, rounds = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       mbar_wait_relaxed(bar_acc_full + 8 * acc, (it >> 1) & 1);
@@ -240,68 +242,88 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
       const int64_t row = tile * TILE_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * ACC_COLS;
       if constexpr (TMA_STORE) {
-        // rounds of one 128-byte-wide box per group: tcgen05.ld -> mix/bias/mask -> swizzled staging
-        // (conflict-free: lane = row, 16-byte unit ^ (row & 7)) -> one TMA store per group.  Full-line,
-        // asynchronous writes instead of 32 scattered 16-byte pieces per store instruction.
-        const uint32_t st_addr = smem_u32(out_stage) + uint32_t(q * 32 + lane) * 128;
+        // rounds of RB 128-byte-wide boxes per group: tcgen05.ld -> mix/bias/mask -> swizzled staging
+        // (conflict-free: lane = row, 16-byte unit ^ (row & 7)) -> one TMA store per box.  Full-line,
+        // asynchronous writes instead of 32 scattered 16-byte pieces per store instruction.  With two
+        // staging sets the stores of round r are still reading set r & 1 while round r + 1 fills the other.
+        constexpr int NB = NCB / CBR;                          // boxes per group and tile
+        constexpr int NCI = (GROUPS == 1 && BF16) ? 2 : 1;     // column blocks per TMEM wait
+        const int RB = p.epi_rb, NS = p.epi_ns;
+        const uint32_t set_bytes = uint32_t(GROUPS * RB) * CHUNK_BYTES;
+        const uint32_t row_off = uint32_t(q * 32 + lane) * 128;
 #pragma unroll 1
-        for (int rd = 0; rd < NCB / CBR; ++rd) {
-          if (warp == 2 && lane == 0) tma_store_wait_read();   // staging of the previous round is free
+        for (int rd = 0; rd < NB / RB; ++rd, ++rounds) {
+          const uint32_t set_addr = smem_u32(out_stage) + (NS == 2 ? (rounds & 1) * set_bytes : 0u);
+          if (warp == 2 && lane == 0) {                        // this set's previous stores have read it
+            if (NS == 2) tma_store_wait_read1(); else tma_store_wait_read();
+          }
           epi_bar_sync();
 #pragma unroll 1
-          for (int k = half; k < CBR; k += 2) {
-            const int cb = rd * CBR + k;
-            float a[16], b[16], bs[16];
-            tmem_ld<16>(taddr + cb * 16, a);
-            if (GROUPS == 2) tmem_ld<16>(taddr + N_OUT + cb * 16, b);
+          for (int kk0 = half * NCI; kk0 < RB * CBR; kk0 += 2 * NCI) {
+            float a[NCI][16], b[NCI][16], bs[NCI][16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)           // issued while the TMEM loads are in flight
-              bs[i] = (p.bias && n0 + cb * 16 + i < p.n_total) ? __ldg(p.bias + n0 + cb * 16 + i) : 0.f;
+            for (int n = 0; n < NCI; ++n) {
+              const int cb = rd * RB * CBR + kk0 + n;
+              tmem_ld<16>(taddr + cb * 16, a[n]);
+              if (GROUPS == 2) tmem_ld<16>(taddr + N_OUT + cb * 16, b[n]);
+            }
+#pragma unroll
+            for (int n = 0; n < NCI; ++n)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {       // issued while the TMEM loads are in flight
+                const int col = n0 + (rd * RB * CBR + kk0 + n) * 16 + i;
+                bs[n][i] = (p.bias && col < p.n_total) ? __ldg(p.bias + col) : 0.f;
+              }
             tmem_ld_wait();
-            if (rd == NCB / CBR - 1 && k + 2 >= CBR) {   // last TMEM read of this warp for this buffer
+            if (rd == NB / RB - 1 && kk0 + 2 * NCI >= RB * CBR) {   // last TMEM read of this warp for this buffer
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (GROUPS == 2) {
-                const float o0 = (a[i] - b[i]) + bs[i], o1 = (a[i] + b[i]) + bs[i];
-                const float m = (p.relu_mode == 1 && !(o0 >= 0.f)) ? 0.f : 1.f;
-                a[i] = p.relu_mode == 1 ? o0 * m : o0;
-                b[i] = p.relu_mode == 1 ? o1 * m : o1;
-              } else {
-                a[i] = a[i] + bs[i];
-              }
-            }
+            for (int n = 0; n < NCI; ++n) {
+              const int kk = kk0 + n, bx = kk / CBR, k = kk % CBR;
 #pragma unroll
-            for (int g = 0; g < GROUPS; ++g) {
-              const float* o = g ? b : a;
-              const uint32_t base = st_addr + g * CHUNK_BYTES;
-              if constexpr (BF16) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  float4 pk;
-                  pk.x = __uint_as_float(pack_bf16(o[8 * j], o[8 * j + 1]));
-                  pk.y = __uint_as_float(pack_bf16(o[8 * j + 2], o[8 * j + 3]));
-                  pk.z = __uint_as_float(pack_bf16(o[8 * j + 4], o[8 * j + 5]));
-                  pk.w = __uint_as_float(pack_bf16(o[8 * j + 6], o[8 * j + 7]));
-                  sts_v4(base + (uint32_t((k * 2 + j) ^ (lane & 7)) << 4), pk);
+              for (int i = 0; i < 16; ++i) {
+                if (GROUPS == 2) {
+                  const float o0 = (a[n][i] - b[n][i]) + bs[n][i], o1 = (a[n][i] + b[n][i]) + bs[n][i];
+                  const float m = (p.relu_mode == 1 && !(o0 >= 0.f)) ? 0.f : 1.f;
+                  a[n][i] = p.relu_mode == 1 ? o0 * m : o0;
+                  b[n][i] = p.relu_mode == 1 ? o1 * m : o1;
+                } else {
+                  a[n][i] = a[n][i] + bs[n][i];
                 }
-              } else {
+              }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  sts_v4(base + (uint32_t((k * 4 + j) ^ (lane & 7)) << 4),
-                         make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+              for (int g = 0; g < GROUPS; ++g) {
+                const float* o = g ? b[n] : a[n];
+                const uint32_t base = set_addr + uint32_t(g * RB + bx) * CHUNK_BYTES + row_off;
+                if constexpr (BF16) {
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    float4 pk;
+                    pk.x = __uint_as_float(pack_bf16(o[8 * j], o[8 * j + 1]));
+                    pk.y = __uint_as_float(pack_bf16(o[8 * j + 2], o[8 * j + 3]));
+                    pk.z = __uint_as_float(pack_bf16(o[8 * j + 4], o[8 * j + 5]));
+                    pk.w = __uint_as_float(pack_bf16(o[8 * j + 6], o[8 * j + 7]));
+                    sts_v4(base + (uint32_t((k * 2 + j) ^ (lane & 7)) << 4), pk);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    sts_v4(base + (uint32_t((k * 4 + j) ^ (lane & 7)) << 4),
+                           make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+                }
               }
             }
           }
           fence_async_smem();
           epi_bar_sync();
           if (warp == 2 && lane == 0 && !(p.dbg & 1)) {
-#pragma unroll
             for (int g = 0; g < GROUPS; ++g)
-              tma_store_2d(&p.out_maps[g], n0 + rd * CBR * 16, int(tile * TILE_M), smem_u32(out_stage) + g * CHUNK_BYTES);
+              for (int bx = 0; bx < RB; ++bx)
+                tma_store_2d(&p.out_maps[g], n0 + (rd * RB + bx) * CBR * 16, int(tile * TILE_M),
+                             set_addr + uint32_t(g * RB + bx) * CHUNK_BYTES);
             tma_store_commit();
           }
         }
@@ -418,14 +440,13 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   }
 }
 
-static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_stages, int groups) {
-  const bool tma_store = n_tile * (bf16 ? 2 : 4) >= 128;
-  return 1024 + size_t(stages + (bf16 ? 0 : lo_stages) + (tma_store ? groups : 0)) * CHUNK_BYTES +
+static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_stages, int out_boxes) {
+  return 1024 + size_t(stages + (bf16 ? 0 : lo_stages) + out_boxes) * CHUNK_BYTES +
          size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (3 * MAX_STAGES + MAX_LO + 4) + 16;
 }
 
 template <int N_OUT, int GROUPS, bool BF16>
-static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int want_cg) {
+static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int want_cg, int want_epi) {
   // experiment knobs ride in the variant word (bits 8-11: lo slots, bits 12-15: landing stages,
   // bits 20-22: converter groups); 0 = default
   // Ring invariants (mbarrier waits only tell odd from even phases, so no waiter may run a whole phase
@@ -434,16 +455,39 @@ static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int 
   int cg = (want_cg == 1 || want_cg == 2 || want_cg == 4) ? want_cg : 2;
   int lo = BF16 ? 0 : (want_lo >= 1 && want_lo <= MAX_LO ? want_lo : cg + 1);
   const size_t budget = 220 * 1024;
-  if (!BF16 && smem_bytes(p.n_slabs, N_OUT, BF16, 3, lo, GROUPS) > budget) cg = 1, lo = 2;
+  constexpr bool TMA_STORE = N_OUT * (BF16 ? 2 : 4) >= 128;
+  constexpr int NB = TMA_STORE ? N_OUT * (BF16 ? 2 : 4) / 128 : 0;    // 128-byte boxes per group and tile
+  // epilogue staging, best first: the whole tile per round in two sets, ... , one box per round in one set;
+  // a candidate must leave room for 4 landing stages (3 when the weights are large)
+  int rb = 1, ns = 1;
+  if (TMA_STORE) {
+    const int cand[4][2] = {{NB, 2}, {NB, 1}, {1, 2}, {1, 1}};
+    bool found = false;
+    for (int min_stages = 4; min_stages >= 3 && !found; --min_stages)
+      for (int c = 0; c < 4 && !found; ++c)
+        if (smem_bytes(p.n_slabs, N_OUT, BF16, min_stages, lo, cand[c][0] * cand[c][1] * GROUPS) <= budget) {
+          rb = cand[c][0], ns = cand[c][1];
+          found = true;
+        }
+  }
+  if (want_epi == 1) rb = 1, ns = 1;                     // experiment knob (variant bits 24-25)
+  if (want_epi == 2) rb = 1, ns = 2;
+  if (want_epi == 3) rb = NB > 0 ? NB : 1, ns = 1;
+  int out_boxes = TMA_STORE ? rb * ns * GROUPS : 0;
+  if (!BF16 && smem_bytes(p.n_slabs, N_OUT, BF16, 3, lo, out_boxes) > budget) {
+    cg = 1, lo = 2, rb = 1, ns = 1;
+    out_boxes = TMA_STORE ? GROUPS : 0;
+  }
   int stages = (want_stages >= 2 && want_stages <= MAX_STAGES) ? want_stages : MAX_STAGES;
   if (!BF16 && stages > 2 * lo) stages = 2 * lo;
-  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, GROUPS) > budget) --stages;
-  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, GROUPS) > budget) return -1;
+  while (stages > 2 && smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, out_boxes) > budget) --stages;
+  if (smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, out_boxes) > budget) return -1;
   if (cg > stages) cg = stages >= 2 ? 2 : 1;
   p.conv_groups = cg;
   p.stages = stages;
   p.lo_stages = lo;
-  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, GROUPS);
+  p.epi_rb = rb, p.epi_ns = ns;
+  const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, out_boxes);
   auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
@@ -554,13 +598,13 @@ int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   int rc = -1;
   const int ws = (a->variant >> 12) & 0xf, wl = (a->variant >> 8) & 0xf;
   p.dbg = (a->variant >> 16) & 7;
-  const int wg = (a->variant >> 20) & 7;
+  const int wg = (a->variant >> 20) & 7, we = (a->variant >> 24) & 3;
 #define PGSD_TMA(N_)                                                                                        \
-  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl, wg) : launch<N_, 1, true>(p, st, ws, wl, wg);     \
-  else rc = groups == 2 ? launch<N_, 2, false>(p, st, ws, wl, wg) : launch<N_, 1, false>(p, st, ws, wl, wg);        \
+  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl, wg, we) : launch<N_, 1, true>(p, st, ws, wl, wg, we);     \
+  else rc = groups == 2 ? launch<N_, 2, false>(p, st, ws, wl, wg, we) : launch<N_, 1, false>(p, st, ws, wl, wg, we);        \
   break;
   switch (n_tile) {
-    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st, ws, wl, wg) : launch<16, 1, false>(p, st, ws, wl, wg); break;
+    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st, ws, wl, wg, we) : launch<16, 1, false>(p, st, ws, wl, wg, we); break;
     case 32: PGSD_TMA(32)
     case 64: PGSD_TMA(64)
     default: PGSD_TMA(128)
