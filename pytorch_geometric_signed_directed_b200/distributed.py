@@ -39,6 +39,17 @@ from . import ops, plan as _plan
 from .plan import CSRPlan
 
 
+# Set to a list to record (label, cuda event) pairs of one sharded step on the compute stream
+# (tools/dist_check.py --trace prints the timeline); None = off.
+TRACE = None
+
+
+def _now_event():
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
 def node_bounds(n_total: int, world: int) -> List[int]:
     """bounds[r] = first node of rank r; bounds[world] = n_total (1-D node-range split)."""
     return [(r * n_total) // world for r in range(world + 1)]
@@ -211,8 +222,10 @@ class SymmetricPullExchange:
         grp = group if group is not None else dist.group.WORLD
         self.send = [symm_mem.empty((rows_max, width), dtype=dtype, device=device) for _ in range(2)]
         self.hdl = [symm_mem.rendezvous(t, grp) for t in self.send]
-        # two copy streams: consecutive rounds overlap on different copy engines
-        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(int(os.environ.get("PGSD_COPY_STREAMS", "2")))]
+        # ONE copy stream by default: shards arrive one after the other in the order the blocks consume
+        # them, so the first one is there as early as possible (N=4 timeline, session 29: first shard at
+        # 1.4 ms instead of 2.0 ms with two concurrent copies sharing the link; step 4.8 vs 5.3 ms)
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(int(os.environ.get("PGSD_COPY_STREAMS", "1")))]
         self.calls = 0
         self.width, self.dtype = width, dtype
 
@@ -331,6 +344,13 @@ class ShardedAggregator:
             return self._halo_step(xs, op_ids, f, alpha, beta, zs)
         # interleave the operands: one [n_local, n_ops*F] send buffer
         pull = self._pull_exchange(xs[0], n_ops * f)
+        views = lambda buf: [buf[:, k * f:(k + 1) * f] for k in range(n_ops)]
+        trace = TRACE is not None and xs[0].is_cuda
+        mark = (lambda name: TRACE.append((name, _now_event()))) if trace else (lambda name: None)
+        mark("start")
+        # (Packing and publishing on a side stream, beside the own-column block, was measured and is
+        # slower -- session 30, N=4: the pack and the first pull then compete with that block for HBM,
+        # the first shard lands at 1.9 ms instead of 1.4 ms.)
         if pull is not None:
             send = pull.send_buffer(self.n_local)
             for k in range(n_ops):
@@ -344,15 +364,18 @@ class ShardedAggregator:
             works = pull.start(send, recv)
         else:
             works = self.ring.start(send, recv)
-        views = lambda buf: [buf[:, k * f:(k + 1) * f] for k in range(n_ops)]
+        own_views = views(send)
         # own block first: it needs nothing from the network and carries the diagonal + beta*z
-        y = self.aggregate_fn(self.blocks[self.rank], views(send), op_ids, alpha, beta, zs, None)
+        y = self.aggregate_fn(self.blocks[self.rank], own_views, op_ids, alpha, beta, zs, None)
+        mark(f"block{self.rank}(own) done")
         for src, reqs in works:
             for w in reqs:
                 w.wait()            # NCCL: makes the current stream wait; gloo: blocks the host
+            mark(f"shard{src} arrived")
             if self.blocks[src].nnz == 0:
                 continue
             y = self.aggregate_fn(self.blocks[src], views(recv[src]), op_ids, alpha, 1.0, y, y)
+            mark(f"block{src} done")
         return y
 
 

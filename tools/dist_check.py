@@ -51,8 +51,10 @@ def check(gname, want_mode, ei):
     return ok
 
 
-ok = check("dsbm", "ring", synthetic.dsbm_edges(n_total, 3, num_edges=e_total, seed=0, device=dev)[0])
-ok &= check("local", "halo", synthetic.locality_edges(n_total, e_total, 2000, 0.0, seed=0, device=dev))
+ok = True
+if "--skip-check" not in sys.argv:
+    ok = check("dsbm", "ring", synthetic.dsbm_edges(n_total, 3, num_edges=e_total, seed=0, device=dev)[0])
+    ok &= check("local", "halo", synthetic.locality_edges(n_total, e_total, 2000, 0.0, seed=0, device=dev))
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
@@ -87,5 +89,28 @@ if "--bench" in sys.argv and flag.item() == 1:
                           "edges_per_s": e_in / (t.item() * 1e-3), "edges_total": e_in,
                           "halo_rows_received_rank0": sh.agg.halo.n_recv if sh.agg.halo else None,
                           "graph": "locality_edges band=50k, 1M nodes / 20M edges per rank"}), flush=True)
+if "--trace" in sys.argv and flag.item() == 1:
+    # timeline of one sharded step of the all-gather path at bench scale (1M nodes / 20M edges per rank)
+    n_b, e_b = 1_000_000 * world, 20_000_000 * world
+    ei = synthetic.dsbm_edges(n_b, 3, num_edges=e_b, seed=0, device=dev)[0]
+    conv = nn.MagNetConv(f, f, K=1, q=0.25, trainable_q=False, cached=True).to(dev)
+    sh = pgd.ShardedMagNetConv(conv, n_b, rank, world).build(ei)
+    del ei
+    xr = torch.rand(sh.n_local, f, device=dev) * 2 - 1
+    xi = torch.rand(sh.n_local, f, device=dev) * 2 - 1
+    with torch.no_grad():
+        for _ in range(5):
+            sh(xr, xi)
+        for rep in range(2):
+            dist.barrier(); torch.cuda.synchronize()
+            pgd.TRACE = []
+            t0 = pgd._now_event()
+            sh(xr, xi)
+            t1 = pgd._now_event()
+            torch.cuda.synchronize()
+            tr, pgd.TRACE = pgd.TRACE, None
+            if rank in (0, world - 1) and rep == 1:
+                line = " | ".join(f"{nm} {t0.elapsed_time(ev):.2f}" for nm, ev in tr)
+                print(f"[rank {rank}] TRACE ms from step start: {line} | step end {t0.elapsed_time(t1):.2f}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)
