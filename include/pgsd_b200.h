@@ -245,7 +245,8 @@ typedef struct pgsd_dense_args {
   void* y[2];
   int64_t ldy[2];
   int32_t relu_mode;         /* 0 none; 1 complex ReLU (mask = y0 >= 0 applied to y0, y1):
-                                nn/directed/complex_relu.py:17-34 (combine == 1 only)   */
+                                nn/directed/complex_relu.py:17-34 (combine == 1 only);
+                                2 tanh (combine == 0 only): nn/signed/SGCN.py:93-96     */
   int32_t variant;           /* 0 = auto: TMA-fed warp-specialised tcgen05 kernel, else the
                                 register-staged tcgen05 kernel, else FFMA; 1 = FFMA; 2 / 4 / 8 =
                                 register-staged tcgen05 (synchronous / warp-specialised / deep

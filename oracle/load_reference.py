@@ -86,4 +86,13 @@ def ref_classes():
             setattr(us, name, None)
     out["SDRLayer"] = load("nn.signed.SDGNN").SDRLayer
     out["MagNet_node_classification"] = load("nn.directed.MagNet_node_classification").MagNet_node_classification
+    out["DiGCN_Inception_Block_node_classification"] = load(
+        "nn.directed.DiGCN_Inception_Block_node_classification").DiGCN_Inception_Block_node_classification
+    # SGCN.py imports the TSVD initialiser and two loss modules from utils.signed (scikit-learn pipelines
+    # outside the hot path); its constructor instantiates the losses, forward() never touches them
+    import torch as _torch
+    for name in ("Link_Sign_Entropy_Loss", "Sign_Structure_Loss"):
+        if getattr(us, name, None) is None:
+            setattr(us, name, lambda *a, **k: _torch.nn.Identity())
+    out["SGCN"] = load("nn.signed.SGCN").SGCN
     return out

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(DT) dense_ffma_kernel(const DenseParams p) {
         }
       } else {
         o0 = acc[0][i][j] + b;
+        if (p.relu_mode == 2) o0 = tanhf(o0);   // SGCN.py:93-96: z = tanh(conv(...))
       }
       if constexpr (BF16) {
         reinterpret_cast<__nv_bfloat16*>(p.y[0])[r * p.ldy[0] + n] = __float2bfloat16_rn(o0);

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_tc_kernel(const __grid_const
             }
           } else {
             o0[i] = a[i] + bs;
+            if (p.relu_mode == 2) o0[i] = tanhf(o0[i]);
           }
         }
 #pragma unroll
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dense_tc_ws_kernel(const __grid
             b[i] = p.relu_mode == 1 ? o1 * m : o1;
           } else {
             a[i] = a[i] + bs;
+            if (p.relu_mode == 2) a[i] = tanhf(a[i]);
           }
         }
 #pragma unroll

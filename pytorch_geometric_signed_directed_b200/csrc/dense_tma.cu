@@ -93,7 +93,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   }
 }
 
-template <int N_OUT, int GROUPS, bool BF16>
+// TANH: the tanh epilogue (SGCN.py:93-96) is a compile-time variant -- as a run-time branch its inlined
+// tanhf cost the epilogue-bound bf16 instantiation 20 % (0.19 -> 0.235 ms, session 32)
+template <int N_OUT, int GROUPS, bool BF16, bool TANH>
 __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32, 1)
     dense_tma_kernel(const __grid_constant__ Params p) {
   constexpr int NCV = BF16 ? 0 : CONV_WARPS;
@@ -294,6 +296,10 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
                   a[n][i] = a[n][i] + bs[n][i];
                 }
               }
+              if constexpr (TANH) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[n][i] = tanhf(a[n][i]);
+              }
 #pragma unroll
               for (int g = 0; g < GROUPS; ++g) {
                 const float* o = g ? b[n] : a[n];
@@ -358,6 +364,10 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
             } else {
               a[i] = a[i] + bs[i];
             }
+          }
+          if constexpr (TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = tanhf(a[i]);
           }
 #pragma unroll
           for (int g = 0; g < GROUPS; ++g) {
@@ -445,7 +455,7 @@ static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_
          size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (3 * MAX_STAGES + MAX_LO + 4) + 16;
 }
 
-template <int N_OUT, int GROUPS, bool BF16>
+template <int N_OUT, int GROUPS, bool BF16, bool TANH = false>
 static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int want_cg, int want_epi) {
   // experiment knobs ride in the variant word (bits 8-11: lo slots, bits 12-15: landing stages,
   // bits 20-22: converter groups); 0 = default
@@ -488,7 +498,7 @@ static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int 
   p.lo_stages = lo;
   p.epi_rb = rb, p.epi_ns = ns;
   const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, out_boxes);
-  auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16>;
+  auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16, TANH>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
   const int n_col_tiles = (p.n_total + N_OUT - 1) / N_OUT;
@@ -599,12 +609,18 @@ int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   const int ws = (a->variant >> 12) & 0xf, wl = (a->variant >> 8) & 0xf;
   p.dbg = (a->variant >> 16) & 7;
   const int wg = (a->variant >> 20) & 7, we = (a->variant >> 24) & 3;
+  const bool tanh_epi = a->relu_mode == 2;
+  if (tanh_epi && (bf16 || groups == 2)) return PGSD_OK;    // other kernels handle it
 #define PGSD_TMA(N_)                                                                                        \
-  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl, wg, we) : launch<N_, 1, true>(p, st, ws, wl, wg, we);     \
-  else rc = groups == 2 ? launch<N_, 2, false>(p, st, ws, wl, wg, we) : launch<N_, 1, false>(p, st, ws, wl, wg, we);        \
+  if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl, wg, we) : launch<N_, 1, true>(p, st, ws, wl, wg, we); \
+  else if (groups == 2) rc = launch<N_, 2, false>(p, st, ws, wl, wg, we);                                    \
+  else rc = tanh_epi ? launch<N_, 1, false, true>(p, st, ws, wl, wg, we) : launch<N_, 1, false>(p, st, ws, wl, wg, we); \
   break;
   switch (n_tile) {
-    case 16: rc = groups == 2 ? launch<16, 2, false>(p, st, ws, wl, wg, we) : launch<16, 1, false>(p, st, ws, wl, wg, we); break;
+    case 16:
+      if (groups == 2) rc = launch<16, 2, false>(p, st, ws, wl, wg, we);
+      else rc = tanh_epi ? launch<16, 1, false, true>(p, st, ws, wl, wg, we) : launch<16, 1, false>(p, st, ws, wl, wg, we);
+      break;
     case 32: PGSD_TMA(32)
     case 64: PGSD_TMA(64)
     default: PGSD_TMA(128)

@@ -10,7 +10,8 @@ from .complex_relu import complex_relu_layer
 from .dgcn_simpa import DGCNConv, SIMPA
 from .sdr_layer import GATConv, SDRLayer
 from .magnet_model import MagNet_node_classification
+from .models import DiGCN_Inception_Block_node_classification, SGCN
 
 __all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv", "SNEAConv",
            "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA", "GATConv", "SDRLayer",
-           "MagNet_node_classification"]
+           "MagNet_node_classification", "DiGCN_Inception_Block_node_classification", "SGCN"]

@@ -56,7 +56,8 @@ class DiGCNConv(torch.nn.Module):
         self._plan, self._cached_inputs = None, None
 
     def _aggregate(self, xw: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor],
-                   out: Optional[Tensor] = None) -> Tensor:
+                   out: Optional[Tensor] = None, add: Optional[Tensor] = None) -> Tensor:
+        """`add`: a tensor summed into the result inside the aggregation epilogue (beta * z)."""
         if self.cached and self._plan is not None and edge_index.size(1) != self.cached_num_edges:
             raise RuntimeError(
                 'Cached {} number of edges, but found {}. Please '
@@ -72,6 +73,8 @@ class DiGCNConv(torch.nn.Module):
             n = xw.size(0)
             self._plan = _plan.build_csr(edge_index, edge_weight, n, n, "source_to_target")
             self._cached_inputs = (edge_index, edge_weight)
+        if add is not None:
+            return ag.spmm(self._plan, [xw], (0,), bias=self.bias, beta=1.0, zs=[add])[0]
         return ag.spmm(self._plan, [xw], (0,), bias=self.bias, out=None if out is None else [out])[0]
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Optional[Tensor] = None) -> Tensor:
@@ -100,6 +103,24 @@ class DiGCN_InceptionBlock(torch.nn.Module):
         self.ln.reset_parameters()
         self.conv1.reset_parameters()
         self.conv2.reset_parameters()
+
+    def forward_sum(self, x: Tensor, edge_index: Tensor, edge_weight: Tensor, edge_index2: Tensor,
+                    edge_weight2: Tensor) -> Tensor:
+        """x0 + x1 + x2 (DiGCN_Inception_Block_node_classification.py:55,63,71) without materialising
+        x1 and x2: each aggregation adds the running sum in its epilogue."""
+        buf, out_dim = self._transform(x)
+        y = self.conv1._aggregate(buf[:, out_dim:2 * out_dim], edge_index, edge_weight, add=buf[:, :out_dim])
+        return self.conv2._aggregate(buf[:, 2 * out_dim:], edge_index2, edge_weight2, add=y)
+
+    def _transform(self, x: Tensor):
+        _plan.require_cuda(x, "x")
+        out_dim = self.conv1.out_channels
+        w_all = torch.cat([self.ln.weight.t().float(), self.conv1.weight.float(),
+                           self.conv2.weight.float()], dim=1)                   # [in, 3*out]
+        b_all = None
+        if self.ln.bias is not None:
+            b_all = torch.cat([self.ln.bias.float(), torch.zeros(2 * out_dim, device=x.device)])
+        return ag.dense([(x, w_all, 0)], 3 * out_dim, bias=b_all)[0], out_dim      # [N, 3*out]
 
     def forward(self, x: Tensor, edge_index: Tensor, edge_weight: Tensor, edge_index2: Tensor,
                 edge_weight2: Tensor) -> Tuple[Tensor, Tensor, Tensor]:

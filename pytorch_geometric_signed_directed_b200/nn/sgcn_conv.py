@@ -54,6 +54,8 @@ class SGCNConv(torch.nn.Module):
         self.lin_b = _Lin(mult * in_dim, out_dim, bias)
         self.lin_u = _Lin(mult * in_dim, out_dim, bias)
         self._plans = _plan.PlanCache(capacity=4)
+        # set by the SGCN model wrapper: z = tanh(conv(...)) (SGCN.py:93-96) as the transform's epilogue
+        self.fused_tanh = False
 
     def reset_parameters(self):
         self.lin_b.reset_parameters()
@@ -95,9 +97,13 @@ class SGCNConv(torch.nn.Module):
         bias = None
         if self.lin_b.bias is not None:
             bias = torch.cat([self.lin_b.bias, self.lin_u.bias])
-        out = ag.dense(terms, 2 * fo, bias=bias)[0]
+        fuse = self.fused_tanh and not self.norm_emb and not ag._needs_grad(
+            [t for t, _, _ in terms] + [self.lin_b.weight, self.lin_u.weight, bias])
+        out = ag.dense(terms, 2 * fo, bias=bias, relu_mode=2 if fuse else 0)[0]
         if self.norm_emb:
             out = F.normalize(out, p=2, dim=-1)
+        if self.fused_tanh and not fuse:
+            out = torch.tanh(out)
         return out
 
     def __repr__(self) -> str:

@@ -645,3 +645,70 @@ def test_shared_operand_gathers_once_and_is_bit_identical(f):
     out_r, out_i = conv(x, x, ei.to(DEV))
     assert_close_rel(out_r, o_r, 1e-5, "out_real")
     assert_close_rel(out_i, o_i, 1e-5, "out_imag")
+
+
+def test_digcn_inception_model_golden_and_training():
+    """BASELINE config 3 as a model: three inception blocks, x0 + x1 + x2 fused into the aggregation epilogues."""
+    g = load_golden("digcn_ib_model", DEV)
+    model = nn.DiGCN_Inception_Block_node_classification(7, 16, 4, dropout=0.5).to(DEV).eval()
+    model.load_state_dict({k.replace("__", "."): v for k, v in g.items()
+                           if k not in ("x", "out", "ei1", "w1", "ei2", "w2")})
+    args = (g["x"], (g["ei1"], g["ei2"]), (g["w1"], g["w2"]))
+    with torch.no_grad():
+        y = model(*args)
+    assert_close_rel(y, g["out"], 1e-5)
+    # the unfused route (three tensors, explicit sum) agrees with the fused epilogue sum
+    with torch.no_grad():
+        x0, x1, x2 = model.ib1(g["x"], g["ei1"], g["w1"], g["ei2"], g["w2"])
+        s = model.ib1.forward_sum(g["x"], g["ei1"], g["w1"], g["ei2"], g["w2"])
+    assert_close_rel(s, x0 + x1 + x2, 2e-6)
+    # training mode (dropout active): gradients reach every parameter; eval result unchanged afterwards
+    model.train()
+    out = model(*args)
+    torch.nn.functional.nll_loss(out, torch.randint(0, 4, (out.size(0),), device=DEV)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    model.eval()
+    # no-dropout training path differentiates through the fused sum: compare with torch autograd of the oracle
+    m2 = nn.DiGCN_Inception_Block_node_classification(7, 16, 4, dropout=0.0).to(DEV).train()
+    m2.load_state_dict(model.state_dict())
+    m2(*args).sum().backward()
+    blocks = []
+    leaves = []
+    for i in (1, 2, 3):
+        blk = [g[f"ib{i}__{nm}"].cpu().clone().requires_grad_(True)
+               for nm in ("ln__weight", "ln__bias", "conv1__weight", "conv1__bias", "conv2__weight", "conv2__bias")]
+        blocks.append(tuple(blk))
+        leaves += blk
+    port.digcn_inception_model(g["x"].cpu(), g["ei1"].cpu(), g["w1"].cpu(), g["ei2"].cpu(), g["w2"].cpu(),
+                               blocks).sum().backward()
+    got = [p.grad for _, p in sorted(m2.named_parameters(), key=lambda kv: kv[0])]
+    names = sorted(n for n, _ in m2.named_parameters())
+    ref = {f"ib{i}.{nm.replace('__', '.')}": t.grad for i, blk in zip((1, 2, 3), blocks)
+           for nm, t in zip(("ln__weight", "ln__bias", "conv1__weight", "conv1__bias", "conv2__weight",
+                             "conv2__bias"), blk)}
+    for nme, gr in zip(names, got):
+        assert_close_rel(gr, ref[nme], 5e-5, f"grad {nme}")
+
+
+@pytest.mark.parametrize("name,norm_emb", [("sgcn_model", False), ("sgcn_model_norm", True)])
+def test_sgcn_model_golden(name, norm_emb):
+    """BASELINE config 4 as a model: sign split, conv1 + deep layers, tanh as the transform's epilogue."""
+    g = load_golden(name, DEV)
+    m = nn.SGCN(140, g["edge_index_s"], in_dim=12, out_dim=16, layer_num=3, init_emb=g["x"].clone(),
+                norm_emb=norm_emb).to(DEV).eval()
+    assert torch.equal(m.pos_edge_index, g["pos_edge_index"]) and torch.equal(m.neg_edge_index, g["neg_edge_index"])
+    m.load_state_dict({k.replace("__", "."): v for k, v in g.items()
+                       if k not in ("out", "edge_index_s", "pos_edge_index", "neg_edge_index")})
+    with torch.no_grad():
+        z = m()
+    assert_close_rel(z, g["out"], 1e-5)
+    # with gradients required the tanh runs unfused; same values
+    m.train()
+    for p in m.parameters():
+        p.requires_grad_(True)
+    z2 = m()
+    assert_close_rel(z2, g["out"], 1e-5)
+    z2.sum().backward()
+    assert all(p.grad is not None for n_, p in m.named_parameters() if n_ != "x")
+    with pytest.raises(NotImplementedError):
+        nn.SGCN(140, g["edge_index_s"], in_dim=12, out_dim=16)

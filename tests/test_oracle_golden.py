@@ -192,3 +192,24 @@ def test_port_preprocessing_matches_reference_golden(name):
     assert torch.equal(e_in, g["in_index"]) and torch.equal(e_out, g["out_index"])
     assert_close_rel(w_in, g["in_weight"], 1e-5, "A_in")
     assert_close_rel(w_out, g["out_weight"], 1e-5, "A_out")
+
+
+def test_digcn_inception_model_port():
+    g = load_golden("digcn_ib_model")
+    blocks = [tuple(g[f"ib{i}__{nm}"] for nm in ("ln__weight", "ln__bias", "conv1__weight", "conv1__bias",
+                                                 "conv2__weight", "conv2__bias")) for i in (1, 2, 3)]
+    y = port.digcn_inception_model(g["x"], g["ei1"], g["w1"], g["ei2"], g["w2"], blocks)
+    assert_close_rel(y, g["out"], 1e-5)
+
+
+@pytest.mark.parametrize("name,norm_emb", [("sgcn_model", False), ("sgcn_model_norm", True)])
+def test_sgcn_model_port(name, norm_emb):
+    g = load_golden(name)
+    layers = [tuple(g[f"{pre}__{nm}"] for nm in ("lin_b__weight", "lin_b__bias", "lin_u__weight", "lin_u__bias"))
+              for pre in ("conv1", "convs__0", "convs__1")]
+    z = port.sgcn_model(g["x"], g["edge_index_s"], layers, norm_emb=norm_emb)
+    assert_close_rel(z, g["out"], 1e-5)
+    # integer plumbing of SGCN.py:53-54 is bit-exact
+    e = g["edge_index_s"]
+    assert torch.equal(e[e[:, 2] > 0][:, :2].t(), g["pos_edge_index"])
+    assert torch.equal(e[e[:, 2] < 0][:, :2].t(), g["neg_edge_index"])

@@ -63,7 +63,13 @@ with torch.no_grad():
     emit(config="C3 DiGCN_InceptionBlock 500k/2x10M/128 bf16", ms=ms, edges_per_s=nnz / ms * 1e3,
          alg_gb=b_alg / 1e9, alg_gbs=b_alg / ms / 1e6, frac=b_alg / ms / 1e6 / PEAK,
          kernels_ms=breakdown(lambda: blk(x, ei1, w1, ei2, w2)))
-    del ei1, ei2, w1, w2, x, blk
+    # C3 as a model: DiGCN_Inception_Block_node_classification (3 blocks, x0+x1+x2 fused into the aggregation epilogues)
+    mdl = nn.DiGCN_Inception_Block_node_classification(f, f, 16, dropout=0.5).to(dev).to(torch.bfloat16).eval()
+    mdl(x, (ei1, ei2), (w1, w2))
+    ms = timeit(lambda: mdl(x, (ei1, ei2), (w1, w2)))
+    emit(config="C3 DiGCN_Inception_Block_node_classification 3 blocks 500k/2x10M/128->128->16 bf16 (inference)", ms=ms,
+         edges_per_s=3 * nnz / ms * 1e3, kernels_ms=breakdown(lambda: mdl(x, (ei1, ei2), (w1, w2))))
+    del ei1, ei2, w1, w2, x, blk, mdl
     torch.cuda.empty_cache()
 
     # ---- C4: SGCN (in=64, out=64 -> conv1 64->32|32, conv2 (32|32)->32|32), 2M nodes, 40M signed entries
@@ -82,7 +88,16 @@ with torch.no_grad():
          alg_gbs=b1 / ms1 / 1e6, frac=b1 / ms1 / 1e6 / PEAK, kernels_ms=breakdown(lambda: c1(x, pos, neg)))
     emit(config="C4 SGCNConv layer 2 2M/40M/(32|32) fp32", ms=ms2, edges_per_s=nnz / ms2 * 1e3, alg_gb=b1 / 1e9,
          alg_gbs=b1 / ms2 / 1e6, frac=b1 / ms2 / 1e6 / PEAK, kernels_ms=breakdown(lambda: c2(z1, pos, neg)))
-    del pos, neg, x, z1
+    # C4 as a model: SGCN(in=64, out=64, 2 layers), tanh fused into each layer's transform
+    es = torch.cat([torch.cat([pos.t(), torch.ones(pos.size(1), 1, dtype=torch.long, device=dev)], 1),
+                    torch.cat([neg.t(), -torch.ones(neg.size(1), 1, dtype=torch.long, device=dev)], 1)], 0)
+    sg = nn.SGCN(n, es, in_dim=64, out_dim=64, layer_num=2, init_emb=x).to(dev).eval()
+    del es
+    sg()
+    ms = timeit(lambda: sg())
+    emit(config="C4 SGCN model 2 layers 2M/40M/64 fp32 (inference)", ms=ms, edges_per_s=2 * nnz / ms * 1e3,
+         alg_gb=2 * b1 / 1e9, alg_gbs=2 * b1 / ms / 1e6, frac=2 * b1 / ms / 1e6 / PEAK, kernels_ms=breakdown(lambda: sg()))
+    del pos, neg, x, z1, sg
     torch.cuda.empty_cache()
 
     # ---- C2 as a whole model: MagNet_node_classification, 2 layers, 1M nodes / 20M edges / 64 hidden
