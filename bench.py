@@ -12,10 +12,11 @@ the whole graph.  metric = input edges aggregated per second = E_input / t_step.
             H2D of x_real/x_imag and D2H of out_real/out_imag inside the timed region.
   roofline: dominant kernel = pgsd_spmm_csr; algorithmic bytes / its CUDA-event duration measured
             inside the timed region, against MEASURED_PEAKS.json's hbm_gbs.
-  cpu_baseline: oracle/port.py (the reference's CPU op sequence) on a bounded 1/4-scale sample.
+  cpu_baseline: oracle/port.py (the reference's CPU op sequence) on a bounded 1/8-scale sample.
 N > 1 ("weak" scaling): the graph grows to N*1M nodes / N*20M edges, destination rows are
-sharded by node range, feature shards travel over NCCL in a ring pipelined with the per-shard
-column-block aggregation (pytorch_geometric_signed_directed_b200/distributed.py).
+sharded by node range, every rank builds only its rows of the operator, and feature shards are pulled over
+NVLink by the copy engines (symmetric peer memory; NCCL send/recv ring as fallback), pipelined with the
+per-shard column-block aggregation (pytorch_geometric_signed_directed_b200/distributed.py).
 `--impl reference` times the CPU port only (rank 0), same metric/config.
 """
 from __future__ import annotations
@@ -207,7 +208,10 @@ def bench_config(n_gpus):
                         f"(cyclic K=3, eta=0.1, size_ratio=1.5), {n_gpus}x(1M nodes / 20M directed edges), "
                         f"64->64 features, fp32 (BASELINE configs[1] layer shape)",
             "nodes_per_gpu": N_PER_GPU, "edges_per_gpu": E_PER_GPU, "feat": FEAT,
-            "parallelism": "single GPU" if n_gpus == 1 else f"node-range row shards x{n_gpus}, NCCL ring halo exchange",
+            "parallelism": "single GPU" if n_gpus == 1 else
+                           f"node-range row shards x{n_gpus}; feature shards all-gathered over NVLink (copy-engine pulls "
+                           f"from symmetric peer memory, NCCL send/recv ring as fallback), pipelined with per-shard "
+                           f"column-block aggregation; operator built per rank (row-range build + degree all-gather)",
             "l2": "inputs larger than L2 (x_real+x_imag 512 MB, plan 0.5 GB vs 126 MB L2); no explicit flush"}
 
 
@@ -255,6 +259,7 @@ def run_gpu_arm(args, rank, world):
             with torch.no_grad():
                 return sharded(x_real, x_imag)
         nnz, n_rows = sharded.local_nnz, n_local
+        exchange_mode = sharded.agg.mode
     if world > 1:
         del ei
     torch.cuda.synchronize()
@@ -469,6 +474,10 @@ def run_gpu_arm(args, rank, world):
         "cold_ms_per_step": cold_ms,   # cached=False: plan build + forward (reference: ~48 s on CPU)
         "shared_input": shared,
     }
+    if world > 1:
+        pull = sharded.agg._pull[1] if sharded.agg._pull else None
+        line["exchange"] = {"mode": exchange_mode, "transport": "symmetric-memory copy-engine pull" if pull is not None
+                            else "nccl send/recv ring", "halo_fraction": getattr(sharded.agg, "halo_fraction", None)}
     if shared:
         shared["frac"] = shared["algorithmic_bytes"] / (shared["ms_per_step"] * 1e-3) / 1e9 / peak
     emit_json(line)

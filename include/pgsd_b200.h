@@ -389,6 +389,16 @@ PGSD_API int pgsd_gather_rows(const void* x, int64_t ldx, const int32_t* index, 
                      int32_t feat, int32_t dtype, void* out, int64_t ldo,
                      pgsd_stream_t stream);
 
+/* Signed-triangle motif counts (SDGNN / SiGAT preprocessing; replaces the Python set loops of
+ * nn/signed/SDGNN.py:153-254 get_features()/build_adj_lists() and nn/signed/SiGAT.py:93-186).
+ * row_ptr4 / col4: HOST arrays of 4 DEVICE pointers -- the CSR neighbour lists pos_out, pos_in, neg_out,
+ * neg_in of every node, each row sorted and duplicate-free (the reference keeps Python sets).
+ * counts[e*16 + t] = |N_lu(t)(edge_u[e]) intersect N_lv(t)(edge_v[e])| in the order of the reference's tuple
+ * (d1_1..d1_4, d2_1..d2_4, d3_1..d3_4, d4_1..d4_4).  Exact integers. */
+PGSD_API int pgsd_signed_triangle_counts(const int32_t* const* row_ptr4, const int32_t* const* col4,
+                                  const int64_t* edge_u, const int64_t* edge_v, int64_t n_edges,
+                                  int64_t n_nodes, int32_t* counts, pgsd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,19 +80,20 @@ def ref_classes():
     # SDGNN.py imports losses / feature builders from utils.signed (sklearn, scipy pipelines that the
     # SDRLayer itself never touches): give the empty package module placeholder attributes
     us = sys.modules[_PKG + ".utils.signed"]
+    import torch as _torch
     for name in ("create_spectral_features", "Sign_Product_Entropy_Loss", "Sign_Direction_Loss",
-                 "Sign_Triangle_Loss"):
-        if not hasattr(us, name):
-            setattr(us, name, None)
+                 "Sign_Triangle_Loss", "Link_Sign_Product_Loss", "Link_Sign_Entropy_Loss", "Sign_Structure_Loss"):
+        if getattr(us, name, None) is None:      # the model constructors instantiate their loss modules
+            setattr(us, name, lambda *a, **k: _torch.nn.Identity())
     out["SDRLayer"] = load("nn.signed.SDGNN").SDRLayer
     out["MagNet_node_classification"] = load("nn.directed.MagNet_node_classification").MagNet_node_classification
     out["DiGCN_Inception_Block_node_classification"] = load(
         "nn.directed.DiGCN_Inception_Block_node_classification").DiGCN_Inception_Block_node_classification
     # SGCN.py imports the TSVD initialiser and two loss modules from utils.signed (scikit-learn pipelines
     # outside the hot path); its constructor instantiates the losses, forward() never touches them
-    import torch as _torch
-    for name in ("Link_Sign_Entropy_Loss", "Sign_Structure_Loss"):
-        if getattr(us, name, None) is None:
-            setattr(us, name, lambda *a, **k: _torch.nn.Identity())
     out["SGCN"] = load("nn.signed.SGCN").SGCN
+    # SDGNN / SiGAT: the constructors instantiate their loss modules; forward() and build_adj_lists() (the parts
+    # restated here) never touch them
+    out["SDGNN"] = load("nn.signed.SDGNN").SDGNN
+    out["SiGAT"] = load("nn.signed.SiGAT").SiGAT
     return out

@@ -89,6 +89,7 @@ _PROTOTYPES = {
                                                  _vp, _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
     "pgsd_build_magnetic_rows_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_double,
                                                   C.c_int, _f32, _vp, _vp, _vp, _vp]),
+    "pgsd_signed_triangle_counts": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i64, _i64, _vp, _vp]),
     "pgsd_magnetic_q_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
                                        _vp, _i64, _vp, _i64, C.c_double, _vp, _vp]),
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),

@@ -11,7 +11,9 @@ from .dgcn_simpa import DGCNConv, SIMPA
 from .sdr_layer import GATConv, SDRLayer
 from .magnet_model import MagNet_node_classification
 from .models import DiGCN_Inception_Block_node_classification, SGCN
+from .signed_models import SDGNN, SiGAT
 
 __all__ = ["MagNetConv", "MSConv", "DiGCNConv", "DiGCN_InceptionBlock", "SGCNConv", "SNEAConv",
            "Conv_Base", "DIMPA", "complex_relu_layer", "DGCNConv", "SIMPA", "GATConv", "SDRLayer",
-           "MagNet_node_classification", "DiGCN_Inception_Block_node_classification", "SGCN"]
+           "MagNet_node_classification", "DiGCN_Inception_Block_node_classification", "SGCN",
+           "SDGNN", "SiGAT"]

@@ -66,7 +66,8 @@ class GATConv(torch.nn.Module):
             return _plan.build_csr(ei.contiguous(), None, n, n, "source_to_target")
         return self._plans.get((edge_index,), (n, self.add_self_loops), build)
 
-    def forward(self, x: Tensor, edge_index: Tensor) -> Tensor:
+    def forward(self, x: Tensor, edge_index: Tensor, out: Tensor = None) -> Tensor:
+        """`out`: optional [N, out_channels] destination (may be a column slice of a wider buffer)."""
         _plan.require_cuda(x, "x")
         n, c = x.size(0), self.out_channels
         p = self._plan_for(edge_index, n)
@@ -78,7 +79,7 @@ class GATConv(torch.nn.Module):
                                          slope=self.negative_slope, want_alpha=True)
             weighted = CSRPlan(p.n_dst, p.n_src, p.nnz, p.num_input_edges, p.row_ptr, p.col, [alphas[0]],
                                [None], [0.0])
-            return ops.spmm(weighted, [h], (0,), bias=self.bias)[0]
+            return ops.spmm(weighted, [h], (0,), bias=self.bias, out=None if out is None else [out])[0]
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})'
@@ -113,5 +114,5 @@ class SDRLayer(torch.nn.Module):
             fi = x.size(1)
             # cat([x] + neigh_feats) @ W0^T  ==  sum of column-block terms (no concatenation)
             terms = [(f, w0[i * fi:(i + 1) * fi], 0) for i, f in enumerate(feats)]
-            hid = torch.tanh(ops.dense(terms, l0.out_features, bias=l0.bias)[0])
+            hid = ops.dense(terms, l0.out_features, bias=l0.bias, relu_mode=2)[0]     # Tanh as the epilogue
             return ops.dense([(hid, l2.weight.t(), 0)], l2.out_features, bias=l2.bias)[0]

@@ -213,3 +213,38 @@ def test_sgcn_model_port(name, norm_emb):
     e = g["edge_index_s"]
     assert torch.equal(e[e[:, 2] > 0][:, :2].t(), g["pos_edge_index"])
     assert torch.equal(e[e[:, 2] < 0][:, :2].t(), g["neg_edge_index"])
+
+
+def test_motif_mining_port_matches_reference_lists():
+    """SDGNN / SiGAT build_adj_lists: the port's set loops reproduce the reference's adjacency lists (as sorted
+    edge sets) and SDGNN's triangle weights exactly."""
+    g = load_golden("sdgnn_model")
+    lists, tri = port.sdgnn_motifs(g["edge_index_s"], 90)
+    for i, e in enumerate(lists):
+        assert torch.equal(e, g[f"list_{i}"])
+    assert [t[0] for t in tri] == g["tri_row"].tolist() and [t[1] for t in tri] == g["tri_col"].tolist()
+    assert [t[2] for t in tri] == g["tri_val"].tolist()
+    s = load_golden("sigat_model")
+    for i, e in enumerate(port.sigat_motifs(s["edge_index_s"], 90)):
+        assert torch.equal(e, s[f"list_{i}"]), f"SiGAT list {i}"
+
+
+def _gat_params(g, prefix, k):
+    return [(g[f"{prefix}agg_{i}__lin__weight"], g[f"{prefix}agg_{i}__att_src"], g[f"{prefix}agg_{i}__att_dst"],
+             g[f"{prefix}agg_{i}__bias"]) for i in range(k)]
+
+
+def test_sdgnn_and_sigat_forward_port():
+    g = load_golden("sdgnn_model")
+    lists = [g[f"list_{i}"] for i in range(4)]
+    x = g["x"]
+    for l in range(2):
+        pre = f"SDRLayer_{l}__"
+        x = port.sdr_layer(x, lists, _gat_params(g, pre, 4), g[pre + "mlp_layer__0__weight"],
+                           g[pre + "mlp_layer__0__bias"], g[pre + "mlp_layer__2__weight"], g[pre + "mlp_layer__2__bias"])
+    assert_close_rel(x, g["out"], 1e-5)
+    s = load_golden("sigat_model")
+    lists = [s[f"list_{i}"] for i in range(38)]
+    z = port.sigat_forward(s["x"], lists, _gat_params(s, "", 38), s["mlp_layer__0__weight"], s["mlp_layer__0__bias"],
+                           s["mlp_layer__2__weight"], s["mlp_layer__2__bias"])
+    assert_close_rel(z, s["out"], 1e-5)
