@@ -712,3 +712,91 @@ def test_sgcn_model_golden(name, norm_emb):
     assert all(p.grad is not None for n_, p in m.named_parameters() if n_ != "x")
     with pytest.raises(NotImplementedError):
         nn.SGCN(140, g["edge_index_s"], in_dim=12, out_dim=16)
+
+
+# ------------------------------------------------ BASELINE configs 3 and 4 at full size
+
+def _rows_subproblem(edge_index, sel, n):
+    """Edges whose destination (edge_index[1]) is in `sel`, relabelled so that the oracle can run on a small
+    graph: returns (sub_edge_index on compact ids, mask of kept edges, compact id -> original id, positions of
+    sel inside the compact ids).  Rows outside `sel` of the small problem are NOT comparable (their in-edges were
+    dropped); rows in `sel` see exactly their original in-neighbourhood."""
+    keep = torch.isin(edge_index[1], sel)
+    sub = edge_index[:, keep]
+    ids, inv = torch.unique(torch.cat([sel, sub[0], sub[1]]), return_inverse=True)
+    k = sel.numel()
+    pos_sel = inv[:k]
+    sub_c = torch.stack([inv[k:k + sub.size(1)], inv[k + sub.size(1):]])
+    return sub_c, keep, ids, pos_sel
+
+
+def test_sgcn_full_size_config4():
+    """BASELINE config 4: SSBM 2M nodes / 40M signed entries / 64 -> 32|32.  Integer in-degree counts exact
+    (plan row lengths vs bincount), mean aggregation linear, and 2000 random destination rows against the
+    oracle evaluated on their induced in-neighbourhood sub-problem."""
+    n = 2_000_000
+    pos, neg, _ = synthetic.ssbm_edges(n, 3, num_entries=40_000_000, eta=0.1, seed=0, device=DEV)
+    x = torch.randn(n, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    conv = nn.SGCNConv(64, 32, first_aggr=True).to(DEV)
+    with torch.no_grad():
+        out = conv(x, pos, neg)
+    assert out.shape == (n, 64) and torch.isfinite(out).all()
+    for ei in (pos, neg):
+        p = conv._plan_for(ei, n, n)
+        assert torch.equal((p.row_ptr[1:] - p.row_ptr[:-1]).long(), torch.bincount(ei[1], minlength=n))
+        assert p.nnz == ei.size(1)
+    p = conv._plan_for(pos, n, n)
+    y = torch.randn(n, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    a = ops.spmm(p, [x], (0,), mean=True)[0]
+    b = ops.spmm(p, [y], (0,), mean=True)[0]
+    c = ops.spmm(p, [0.5 * x - 2.0 * y], (0,), mean=True)[0]
+    assert_close_rel(c, 0.5 * a - 2.0 * b, 2e-6, "linearity of the mean aggregation")
+    sel = torch.randperm(n, generator=torch.Generator().manual_seed(2))[:2000].to(DEV)
+    sp, _, ids_p, pos_p = _rows_subproblem(pos, sel, n)
+    # one compact id space for both signs: run the two signs as separate sub-problems sharing `sel`
+    sn, _, ids_n, pos_n = _rows_subproblem(neg, sel, n)
+    wb, bb = conv.lin_b.weight.detach().cpu(), conv.lin_b.bias.detach().cpu()
+    wu, bu = conv.lin_u.weight.detach().cpu(), conv.lin_u.bias.detach().cpu()
+    empty = torch.zeros((2, 0), dtype=torch.long)
+    ref_b = port.sgcn_conv(x[ids_p].cpu(), sp.cpu(), empty, wb, bb, wu, bu, first_aggr=True, norm_emb=False)
+    ref_u = port.sgcn_conv(x[ids_n].cpu(), empty, sn.cpu(), wb, bb, wu, bu, first_aggr=True, norm_emb=False)
+    got = out[sel].cpu()
+    scale = out.abs().max().item()
+    assert (got[:, :32] - ref_b[pos_p.cpu(), :32]).abs().max().item() <= 1e-5 * scale
+    assert (got[:, 32:] - ref_u[pos_n.cpu(), 32:]).abs().max().item() <= 1e-5 * scale
+
+
+def test_inception_block_full_size_config3():
+    """BASELINE config 3: DiGCN_InceptionBlock, 500k nodes / 2 x 10M weighted entries / 128 features, bf16.
+    x0 against a dense fp32 product on sampled rows, x1 / x2 on 2000 random rows against the oracle on the induced
+    sub-problem (bf16 tolerance 1e-2: inputs, xW and outputs are each rounded once), aggregation linearity."""
+    n, e, f = 500_000, 10_000_000, 128
+    ei1, _ = synthetic.dsbm_edges(n, 3, num_edges=e, seed=1, device=DEV)
+    ei2, _ = synthetic.dsbm_edges(n, 3, num_edges=e, seed=2, device=DEV)
+    w1, w2 = synthetic.sym_norm_weights(ei1, n), synthetic.sym_norm_weights(ei2, n)
+    x = (torch.rand(n, f, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0)) * 2 - 1).bfloat16()
+    blk = nn.DiGCN_InceptionBlock(f, f).to(DEV)
+    with torch.no_grad():
+        blk.conv1.bias.uniform_(-0.2, 0.2)
+        blk.conv2.bias.uniform_(-0.2, 0.2)
+        x0, x1, x2 = blk(x, ei1, w1, ei2, w2)
+        s = blk.forward_sum(x, ei1, w1, ei2, w2)
+    for t in (x0, x1, x2, s):
+        assert t.dtype == torch.bfloat16 and t.shape == (n, f) and torch.isfinite(t.float()).all()
+    assert_close_rel(s.float(), x0.float() + x1.float() + x2.float(), 2e-2, "fused x0 + x1 + x2")
+    sel = torch.randperm(n, generator=torch.Generator().manual_seed(3))[:2000].to(DEV)
+    xf = x.float()
+    ref0 = torch.nn.functional.linear(xf[sel], blk.ln.weight.detach(), blk.ln.bias.detach())
+    assert_close_rel(x0[sel].float(), ref0, 1e-2, "x0")
+    for ei, w, conv, got in ((ei1, w1, blk.conv1, x1), (ei2, w2, blk.conv2, x2)):
+        sub, keep, ids, pos_sel = _rows_subproblem(ei, sel, n)
+        ref = port.digcn_conv(xf[ids].cpu(), sub.cpu(), w[keep].cpu(), conv.weight.detach().cpu(),
+                              conv.bias.detach().cpu())[pos_sel.cpu()]
+        assert_close_rel(got[sel].float().cpu(), ref, 1e-2, "aggregated rows")
+    # linearity of the bf16 aggregation (fp32 accumulation, one rounding at the end)
+    p = blk.conv1._plan
+    a = ops.spmm(p, [x], (0,))[0].float()
+    y = (torch.rand(n, f, device=DEV) * 2 - 1).bfloat16()
+    b = ops.spmm(p, [y], (0,))[0].float()
+    c = ops.spmm(p, [(x.float() + y.float()).bfloat16()], (0,))[0].float()
+    assert_close_rel(c, a + b, 2e-2, "linearity")
