@@ -800,3 +800,39 @@ def test_inception_block_full_size_config3():
     b = ops.spmm(p, [y], (0,))[0].float()
     c = ops.spmm(p, [(x.float() + y.float()).bfloat16()], (0,))[0].float()
     assert_close_rel(c, a + b, 2e-2, "linearity")
+
+
+def test_uncached_layer_reuses_its_plan_only_for_identical_tensors():
+    """cached=False (the reference's default) re-normalises every call; here the plan of the previous call is
+    reused while the very same edge tensors come back unchanged, and rebuilt as soon as anything differs --
+    outputs always follow the tensors passed in."""
+    g = torch.Generator().manual_seed(11)
+    n, e, f = 3000, 40_000, 16
+    ei = torch.randint(0, n, (2, e), generator=g).to(DEV)
+    ew = (torch.rand(e, generator=g) + 0.5).to(DEV)
+    x = (torch.rand(n, f, generator=g) * 2 - 1).to(DEV)
+    conv = nn.MagNetConv(f, f, K=2, q=0.2, trainable_q=False, cached=False).to(DEV)
+
+    def oracle(weights):
+        return port.magnet_conv(x.cpu(), x.cpu(), ei.cpu(), weights.cpu(), conv.weight.detach().cpu(),
+                                conv.bias.detach().cpu(), 0.2, "sym")
+    a = conv(x, x, ei, ew)
+    p1 = conv._plan
+    b = conv(x, x, ei, ew)
+    assert conv._plan is p1 and torch.equal(a[0], b[0])                 # same tensors, untouched: reused
+    assert_close_rel(a[0], oracle(ew)[0], 1e-5)
+    ew.mul_(2.0)                                                         # in-place edit bumps the version counter
+    c = conv(x, x, ei, ew)
+    assert conv._plan is not p1
+    assert_close_rel(c[0], oracle(ew)[0], 1e-5)
+    assert_close_rel(c[1], oracle(ew)[1], 1e-5)
+    p2 = conv._plan
+    d = conv(x, x, ei.clone(), ew)                                       # equal values, different tensor: rebuilt
+    assert conv._plan is not p2 and torch.equal(c[0], d[0])
+    p3 = conv._plan
+    conv(x, x, ei, ew, lambda_max=torch.tensor(1.5))                     # another operator from the same tensors
+    assert conv._plan is not p3
+    ref = nn.MagNetConv(f, f, K=2, q=0.2, trainable_q=False, cached=True).to(DEV)
+    ref.load_state_dict(conv.state_dict())
+    r = ref(x, x, ei, ew, lambda_max=torch.tensor(1.5))
+    assert torch.equal(conv(x, x, ei, ew, lambda_max=torch.tensor(1.5))[0], r[0])
