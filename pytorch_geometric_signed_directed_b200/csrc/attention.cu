@@ -10,7 +10,7 @@
 //       y[i] = xd0[i] * sum_{e in type 0} alpha_e + xd1[i] * sum_{e in type 1} alpha_e
 //   mode B (GATConv-style): alpha_e is written per stored entry; the weighted aggregation
 //       sum alpha_e x_j then runs through pgsd_spmm_csr with val = alpha.
-// One warp per destination row; up to two edge types, each with its own CSR plan.
+// One lane group per destination row; up to two edge types, each with its own CSR plan.
 #include "common.cuh"
 
 namespace pgsd {
@@ -45,44 +45,76 @@ __device__ __forceinline__ float warp_add(float v) {
   return v;
 }
 
+// One LPR-lane group per destination row (rows have ~10-20 entries: a whole warp per row leaves most lanes
+// idle), ONE pass over the entries for the softmax statistics: every lane keeps a running maximum and the
+// exponent sums relative to it (rescaled when the maximum moves), the group merges the (max, sums) triples
+// with shuffles.  Mode A needs nothing else; mode B revisits the entries once to write alpha.  The first
+// version of this kernel used a warp per row and re-gathered / re-evaluated every entry in three passes
+// (0.75 ms per 20M entries; this one: see profiles/README.md).
+template <int LPR>
 __global__ void __launch_bounds__(256) edge_softmax_kernel(const AttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps_total = int64_t(gridDim.x) * 8;
-  for (int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5); row < p.n_rows; row += warps_total) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+  const int64_t warp_id = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t stride = int64_t(gridDim.x) * 8 * G;
+  const bool vec = (p.feat % 4 == 0) && p.y != nullptr && (reinterpret_cast<uintptr_t>(p.y) % 16 == 0) &&
+                   (p.ldy % 4 == 0) && (reinterpret_cast<uintptr_t>(p.xd[0]) % 16 == 0) && (p.ldxd[0] % 4 == 0) &&
+                   (p.n_types == 1 || ((reinterpret_cast<uintptr_t>(p.xd[1]) % 16 == 0) && (p.ldxd[1] % 4 == 0)));
+  for (int64_t base = warp_id * G; base < p.n_rows; base += stride) {      // warp-uniform trip count
+    const int64_t row = base + g;
+    const bool live = row < p.n_rows;
     int b[2] = {0, 0}, e[2] = {0, 0};
     float sd[2] = {0.f, 0.f};
-    for (int t = 0; t < p.n_types; ++t) {
-      b[t] = p.row_ptr[t][row], e[t] = p.row_ptr[t][row + 1];
-      sd[t] = p.s_dst[t][row];
-    }
-    // pass 1: row maximum
-    float m = -INFINITY;
+    if (live)
+      for (int t = 0; t < p.n_types; ++t) {
+        b[t] = __ldg(p.row_ptr[t] + row), e[t] = __ldg(p.row_ptr[t] + row + 1);
+        sd[t] = __ldg(p.s_dst[t] + row);
+      }
+    float m = -INFINITY, sum[2] = {0.f, 0.f};
     for (int t = 0; t < p.n_types; ++t)
-      for (int k = b[t] + lane; k < e[t]; k += 32)
-        m = fmaxf(m, attn_act(p.s_src[t][p.col[t][k]] + sd[t], p.act, p.slope));
-    m = warp_max(m);
-    // pass 2: exponent sums per type
-    float sum[2] = {0.f, 0.f};
-    for (int t = 0; t < p.n_types; ++t) {
-      float acc = 0.f;
-      for (int k = b[t] + lane; k < e[t]; k += 32)
-        acc += expf(attn_act(p.s_src[t][p.col[t][k]] + sd[t], p.act, p.slope) - m);
-      sum[t] = warp_add(acc);
+      for (int k = b[t] + l; k < e[t]; k += LPR) {
+        const float v = attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope);
+        if (v > m) {
+          const float sc = expf(m - v);          // exp(-inf) = 0 on the first entry
+          sum[0] *= sc, sum[1] *= sc, m = v;
+        }
+        sum[t] += expf(v - m);
+      }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(FULL, m, o, LPR);
+      const float a0 = __shfl_xor_sync(FULL, sum[0], o, LPR), a1 = __shfl_xor_sync(FULL, sum[1], o, LPR);
+      const float mn = fmaxf(m, m2);
+      const float f1 = (m == -INFINITY) ? 0.f : expf(m - mn), f2 = (m2 == -INFINITY) ? 0.f : expf(m2 - mn);
+      sum[0] = sum[0] * f1 + a0 * f2, sum[1] = sum[1] * f1 + a1 * f2, m = mn;
     }
     const float inv = 1.0f / (sum[0] + sum[1] + 1e-16f);
     // mode B: per-entry alpha
     for (int t = 0; t < p.n_types; ++t)
       if (p.alpha_out[t] != nullptr)
-        for (int k = b[t] + lane; k < e[t]; k += 32)
-          p.alpha_out[t][k] = expf(attn_act(p.s_src[t][p.col[t][k]] + sd[t], p.act, p.slope) - m) * inv;
+        for (int k = b[t] + l; k < e[t]; k += LPR)
+          p.alpha_out[t][k] =
+              expf(attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope) - m) * inv;
     // mode A: y[i] = xd0[i] * P + xd1[i] * N
-    if (p.y != nullptr) {
-      const bool any = (e[0] - b[0]) + (e[1] - b[1]) > 0;
-      const float w0 = any ? sum[0] * inv : 0.f, w1 = any ? sum[1] * inv : 0.f;
-      for (int f = lane; f < p.feat; f += 32) {
-        float v = w0 * p.xd[0][row * p.ldxd[0] + f];
-        if (p.n_types == 2) v = fmaf(w1, p.xd[1][row * p.ldxd[1] + f], v);
-        p.y[row * p.ldy + f] = v;
+    if (p.y != nullptr && live) {
+      const float w0 = sum[0] * inv, w1 = sum[1] * inv;       // an isolated row: 0 * 1e16 = 0
+      if (vec) {
+        for (int f = l * 4; f < p.feat; f += LPR * 4) {
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.xd[0] + row * p.ldxd[0] + f));
+          float4 v = make_float4(w0 * x0.x, w0 * x0.y, w0 * x0.z, w0 * x0.w);
+          if (p.n_types == 2) {
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(p.xd[1] + row * p.ldxd[1] + f));
+            v.x = fmaf(w1, x1.x, v.x), v.y = fmaf(w1, x1.y, v.y), v.z = fmaf(w1, x1.z, v.z), v.w = fmaf(w1, x1.w, v.w);
+          }
+          *reinterpret_cast<float4*>(p.y + row * p.ldy + f) = v;
+        }
+      } else {
+        for (int f = l; f < p.feat; f += LPR) {
+          float v = w0 * p.xd[0][row * p.ldxd[0] + f];
+          if (p.n_types == 2) v = fmaf(w1, p.xd[1][row * p.ldxd[1] + f], v);
+          p.y[row * p.ldy + f] = v;
+        }
       }
     }
   }
@@ -111,9 +143,10 @@ extern "C" int pgsd_edge_softmax(const pgsd_attn_args* a, pgsd_stream_t stream) 
     }
   }
   p.y = a->y, p.ldy = a->ldy;
-  int64_t grid = ceil_div<int64_t>(a->n_rows, 8);
+  constexpr int LPR = 8;                                    // 4 rows per warp
+  int64_t grid = ceil_div<int64_t>(a->n_rows, 8 * (32 / LPR));
   if (grid > int64_t(sm_count()) * 8) grid = int64_t(sm_count()) * 8;
-  edge_softmax_kernel<<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  edge_softmax_kernel<LPR><<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   PGSD_LAUNCH_CHECK("edge_softmax_kernel");
   return PGSD_OK;
 }

@@ -66,23 +66,59 @@ class GATConv(torch.nn.Module):
             return _plan.build_csr(ei.contiguous(), None, n, n, "source_to_target")
         return self._plans.get((edge_index,), (n, self.add_self_loops), build)
 
+    def score_weights(self) -> Tensor:
+        """[in, 2]: the two attention scores are linear in x -- (x W^T) . a = x . (W a) -- so they come from x
+        directly, and several GATConvs reading the same x share one transform launch for all their scores."""
+        w = self.lin.weight.detach().t().float()                                           # [in, C]
+        att = torch.stack([self.att_src.detach().view(-1), self.att_dst.detach().view(-1)], dim=1).float()
+        return w @ att
+
+    def aggregate(self, h: Tensor, s_src: Tensor, s_dst: Tensor, edge_index: Tensor, out: Tensor = None,
+                  accumulate_into: Tensor = None) -> Tensor:
+        """softmax over the incoming edges + weighted sum of h (+ bias), given h = x W^T and the per-node scores.
+        `accumulate_into`: running sum the result is ADDED to in the aggregation epilogue (no bias then; used
+        when the layer that follows is linear and has been folded into h, see SDRLayer.forward)."""
+        p = self._plan_for(edge_index, h.size(0))
+        _, alphas = ops.edge_softmax([p], [s_src], [s_dst], act="leaky_relu", slope=self.negative_slope,
+                                     want_alpha=True)
+        weighted = CSRPlan(p.n_dst, p.n_src, p.nnz, p.num_input_edges, p.row_ptr, p.col, [alphas[0]], [None], [0.0])
+        if accumulate_into is not None:
+            return ops.spmm(weighted, [h], (0,), beta=1.0, zs=[accumulate_into], out=[accumulate_into])[0]
+        return ops.spmm(weighted, [h], (0,), bias=self.bias, out=None if out is None else [out])[0]
+
     def forward(self, x: Tensor, edge_index: Tensor, out: Tensor = None) -> Tensor:
         """`out`: optional [N, out_channels] destination (may be a column slice of a wider buffer)."""
         _plan.require_cuda(x, "x")
-        n, c = x.size(0), self.out_channels
-        p = self._plan_for(edge_index, n)
         with torch.no_grad():
-            h = ops.dense([(x, self.lin.weight.t(), 0)], c)[0]
-            att = torch.stack([self.att_src.view(c), self.att_dst.view(c)], dim=1)      # [C, 2]
-            s = ops.dense([(h, att, 0)], 2)[0]
-            _, alphas = ops.edge_softmax([p], [s[:, 0]], [s[:, 1]], act="leaky_relu",
-                                         slope=self.negative_slope, want_alpha=True)
-            weighted = CSRPlan(p.n_dst, p.n_src, p.nnz, p.num_input_edges, p.row_ptr, p.col, [alphas[0]],
-                               [None], [0.0])
-            return ops.spmm(weighted, [h], (0,), bias=self.bias, out=None if out is None else [out])[0]
+            h, s = gat_transforms(x, [self])
+            return self.aggregate(h[0], s[0][0], s[0][1], edge_index, out)
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})'
+
+
+def gat_transforms(x: Tensor, gats: List["GATConv"], scores_only: bool = False):
+    """h_k = x W_k^T and the score pairs of several GATConvs that read the same x, in TWO launches: one transform
+    with the weights side by side ([in, k*C]; every h_k is a column block of its output) and one with all score
+    vectors side by side, zero-padded to a width the tensor-core kernels take ([in, 2k] -> 16 / 32 / 64 / 128).
+    Returns ([h_k], [(s_src_k, s_dst_k)])."""
+    c = gats[0].out_channels
+    k = len(gats)
+    hs = None
+    if not scores_only:
+        w_all = torch.cat([g.lin.weight.detach().t().float() for g in gats], dim=1)           # [in, k*C]
+        h_all = ops.dense([(x, w_all, 0)], k * c)[0]
+        hs = [h_all[:, i * c:(i + 1) * c] for i in range(k)]
+    sw = torch.cat([g.score_weights() for g in gats], dim=1)                                   # [in, 2k]
+    width = next((w for w in (16, 32, 64, 128) if w >= 2 * k), None)
+    if width is None:
+        width = -(-2 * k // 128) * 128
+    if x.dtype == torch.bfloat16 and width < 32:
+        width = 32
+    sw = torch.nn.functional.pad(sw, (0, width - 2 * k))
+    s_all = ops.dense([(x, sw, 0)], width)[0].float()
+    ss = [(s_all[:, 2 * i].contiguous(), s_all[:, 2 * i + 1].contiguous()) for i in range(k)]
+    return hs, ss
 
 
 class SDRLayer(torch.nn.Module):
@@ -106,13 +142,29 @@ class SDRLayer(torch.nn.Module):
             agg.reset_parameters()
 
     def forward(self, x: Tensor) -> Tensor:
+        """mlp(cat([x] + [agg_k(x, edges_k)])) with the first Linear folded THROUGH the aggregations: it is linear,
+        so  (sum_j alpha_ij h_kj + b_k) M_k = sum_j alpha_ij (h_kj M_k) + b_k M_k  -- every GATConv aggregates
+        x (W_k^T M_k) and adds into one [N, out] accumulator in its epilogue.  The k aggregated [N, C] tensors, their
+        concatenation and the [N, (k+1) C] x [(k+1) C, out] transform (whose weights do not fit the tensor-core
+        kernel's shared memory) never exist; the attention scores still come from h_k = x W_k^T."""
         _plan.require_cuda(x, "x")
         with torch.no_grad():
-            feats = [x] + [agg(x, edges) for edges, agg in zip(self.edge_lists, self.aggs)]
             l0, l2 = self.mlp_layer[0], self.mlp_layer[2]
-            w0 = l0.weight.t()                                     # [in*(k+1), out] view
-            fi = x.size(1)
-            # cat([x] + neigh_feats) @ W0^T  ==  sum of column-block terms (no concatenation)
-            terms = [(f, w0[i * fi:(i + 1) * fi], 0) for i, f in enumerate(feats)]
-            hid = ops.dense(terms, l0.out_features, bias=l0.bias, relu_mode=2)[0]     # Tanh as the epilogue
+            k, fi = len(self.aggs), x.size(1)
+            w0 = l0.weight.detach().t().float()                                  # [fi + k*C, out]
+            c = (w0.size(0) - fi) // max(k, 1)
+            blocks = [w0[fi + i * c: fi + (i + 1) * c] for i in range(k)]         # M_k
+            bias0 = l0.bias.detach().float().clone() if l0.bias is not None else w0.new_zeros(w0.size(1))
+            for agg, m in zip(self.aggs, blocks):
+                if agg.bias is not None:
+                    bias0 += agg.bias.detach().float() @ m
+            acc = ops.dense([(x, w0[:fi], 0)], l0.out_features, bias=bias0)[0]    # x M_0 + b_0 + sum_k b_k M_k
+            if k:
+                folded = torch.cat([agg.lin.weight.detach().t().float() @ m for agg, m in zip(self.aggs, blocks)], 1)
+                hp_all = ops.dense([(x, folded, 0)], k * l0.out_features)[0]      # [N, k*out]
+                _, ss = gat_transforms(x, self.aggs, scores_only=True)
+                o = l0.out_features
+                for i, (edges, agg) in enumerate(zip(self.edge_lists, self.aggs)):
+                    agg.aggregate(hp_all[:, i * o:(i + 1) * o], ss[i][0], ss[i][1], edges, accumulate_into=acc)
+            hid = torch.tanh_(acc)
             return ops.dense([(hid, l2.weight.t(), 0)], l2.out_features, bias=l2.bias)[0]

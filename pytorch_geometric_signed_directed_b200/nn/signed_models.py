@@ -16,7 +16,7 @@ from torch import Tensor
 
 from .. import ops, plan as _plan
 from ..utils import signed as _signed
-from .sdr_layer import GATConv, SDRLayer
+from .sdr_layer import GATConv, SDRLayer, gat_transforms
 
 
 def _split_signed(edge_index_s: Tensor):
@@ -113,13 +113,14 @@ class SiGAT(torch.nn.Module):
             # its column block in place, and the first Linear reads it as ONE term
             wide = torch.empty((n, x.size(1) + k * c), dtype=x.dtype, device=x.device)
             wide[:, :x.size(1)] = x
+            hs, ss = gat_transforms(x, self.aggs)                # 38 transforms + 76 score vectors: two launches
             for i, (edges, agg) in enumerate(zip(self.edge_lists, self.aggs)):
                 lo = x.size(1) + i * c
                 sl = wide[:, lo:lo + c]
                 if (sl.data_ptr() % 16) or (c * x.element_size()) % 16:
-                    sl.copy_(agg(x, edges))                      # widths the vector kernels cannot write in place
+                    sl.copy_(agg.aggregate(hs[i], ss[i][0], ss[i][1], edges))   # widths the vector kernels cannot write in place
                 else:
-                    agg(x, edges, out=sl)
+                    agg.aggregate(hs[i], ss[i][0], ss[i][1], edges, out=sl)
             l0, l2 = self.mlp_layer[0], self.mlp_layer[2]
             hid = ops.dense([(wide, l0.weight.t(), 0)], l0.out_features, bias=l0.bias, relu_mode=2)[0]
             return ops.dense([(hid, l2.weight.t(), 0)], l2.out_features, bias=l2.bias)[0]

@@ -59,20 +59,38 @@ class SNEAConv(torch.nn.Module):
             return _plan.build_csr(ei.contiguous(), None, n, n, "source_to_target")
         return self._plans.get((edge_index,), (n, with_loops), build)
 
-    def _scores(self, x: Tensor, alpha_lin: torch.nn.Linear) -> Tuple[Tensor, Tensor]:
-        # Linear(2*out -> 1) on [x_j || x_i]  ==  x_j . a_j  +  (x_i . a_i + c)
-        w = alpha_lin.weight.detach().view(2, self.out_dim).t()          # [out, 2]: (a_j, a_i)
-        bias = torch.cat([torch.zeros(1, device=x.device), alpha_lin.bias.detach().float()])
-        s = ops.dense([(x, w, 0)], 2, bias=bias)[0]
-        return s[:, 0], s[:, 1]
+    def _transforms(self, x: Tensor, specs):
+        """All Linear applications of one forward in TWO launches.  specs = [(lin, first input column, alpha_lin)]:
+        feature k is h_k = lin(x[:, c0:c0+in]) and its attention scores are s_src = h_k . a_j, s_dst = h_k . a_i + c
+        with (a_j, a_i, c) = alpha_lin (SNEAConv.py:137-142: Linear(2*out -> 1) on [h_j || h_i]).  Both are linear in
+        x, so (i) the h_k are the column blocks of one transform with block-structured weights and (ii) all score
+        pairs are the columns of a second, narrow transform of x (zero-padded to 16 columns for the tensor-core
+        kernel) whose weights are W^T a and whose bias carries b . a (+ c)."""
+        fi, fo, dev = self.in_dim, self.out_dim, x.device
+        k = len(specs)
+        w_all = x.new_zeros((x.size(1), k * fo), dtype=torch.float32)
+        b_all = torch.zeros(k * fo, device=dev)
+        width = 16 if 2 * k <= 16 else 32
+        sw = torch.zeros((x.size(1), width), device=dev)
+        sb = torch.zeros(width, device=dev)
+        for i, (lin, c0, alpha_lin) in enumerate(specs):
+            wt = lin.weight.detach().t().float()                                   # [in, out]
+            w_all[c0:c0 + fi, i * fo:(i + 1) * fo] = wt
+            a = alpha_lin.weight.detach().view(2, fo).t().float()                  # [out, 2]: (a_j, a_i)
+            sw[c0:c0 + fi, 2 * i:2 * i + 2] = wt @ a
+            if lin.bias is not None:
+                b_all[i * fo:(i + 1) * fo] = lin.bias.detach().float()
+                sb[2 * i:2 * i + 2] = lin.bias.detach().float() @ a
+            sb[2 * i + 1] += alpha_lin.bias.detach().float().view(())
+        h_all = ops.dense([(x, w_all, 0)], k * fo, bias=b_all)[0]
+        s_all = ops.dense([(x, sw, 0)], width, bias=sb)[0]
+        hs = [h_all[:, i * fo:(i + 1) * fo] for i in range(k)]
+        ss = [(s_all[:, 2 * i].contiguous(), s_all[:, 2 * i + 1].contiguous()) for i in range(k)]
+        return hs, ss
 
-    def _attend(self, plans, xs, alpha_lin) -> Tensor:
-        sc = [self._scores(x, alpha_lin) for x in xs]
-        y, _ = ops.edge_softmax(plans, [s[0] for s in sc], [s[1] for s in sc], act="tanh", xd=xs)
+    def _attend(self, plans, hs, ss) -> Tensor:
+        y, _ = ops.edge_softmax(plans, [s[0] for s in ss], [s[1] for s in ss], act="tanh", xd=hs)
         return y
-
-    def _lin(self, lin: torch.nn.Linear, x: Tensor) -> Tensor:
-        return ops.dense([(x, lin.weight.detach().t(), 0)], self.out_dim, bias=lin.bias)[0]
 
     def forward(self, x: Union[Tensor, Tuple[Tensor, Tensor]], pos_edge_index: Tensor,
                 neg_edge_index: Tensor) -> Tensor:
@@ -80,16 +98,18 @@ class SNEAConv(torch.nn.Module):
             raise NotImplementedError("SNEAConv kernels take a single feature tensor")
         _plan.require_cuda(x, "x")
         n = x.size(0)
-        if self.first_aggr:
-            h_b, h_u = self._lin(self.lin_b, x), self._lin(self.lin_u, x)
-            out_b = self._attend([self._plan_for(pos_edge_index, n, True)], [h_b], self.alpha_b)
-            out_u = self._attend([self._plan_for(neg_edge_index, n, True)], [h_u], self.alpha_u)
-        else:
-            fi = self.in_dim
-            h_b, h_u = x[:, :fi], x[:, fi:]
-            plans = [self._plan_for(pos_edge_index, n, True), self._plan_for(neg_edge_index, n, False)]
-            out_b = self._attend(plans, [self._lin(self.lin_b, h_b), self._lin(self.lin_b, h_u)], self.alpha_b)
-            out_u = self._attend(plans, [self._lin(self.lin_u, h_u), self._lin(self.lin_u, h_b)], self.alpha_u)
+        with torch.no_grad():
+            if self.first_aggr:
+                hs, ss = self._transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_u, 0, self.alpha_u)])
+                out_b = self._attend([self._plan_for(pos_edge_index, n, True)], hs[:1], ss[:1])
+                out_u = self._attend([self._plan_for(neg_edge_index, n, True)], hs[1:], ss[1:])
+            else:
+                fi = self.in_dim                       # x = [h_b | h_u]
+                hs, ss = self._transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_b, fi, self.alpha_b),
+                                              (self.lin_u, fi, self.alpha_u), (self.lin_u, 0, self.alpha_u)])
+                plans = [self._plan_for(pos_edge_index, n, True), self._plan_for(neg_edge_index, n, False)]
+                out_b = self._attend(plans, hs[:2], ss[:2])
+                out_u = self._attend(plans, hs[2:], ss[2:])
         return torch.cat([out_b, out_u], dim=-1)
 
     def __repr__(self) -> str:

@@ -88,6 +88,24 @@ with torch.no_grad():
          alg_gbs=b1 / ms1 / 1e6, frac=b1 / ms1 / 1e6 / PEAK, kernels_ms=breakdown(lambda: c1(x, pos, neg)))
     emit(config="C4 SGCNConv layer 2 2M/40M/(32|32) fp32", ms=ms2, edges_per_s=nnz / ms2 * 1e3, alg_gb=b1 / 1e9,
          alg_gbs=b1 / ms2 / 1e6, frac=b1 / ms2 / 1e6 / PEAK, kernels_ms=breakdown(lambda: c2(z1, pos, neg)))
+    # SNEAConv (rows a8): same SSBM graph, 64 -> 32|32 first layer and (32|32) -> 32|32 deep layer
+    s1 = nn.SNEAConv(64, 32, first_aggr=True).to(dev)
+    s2 = nn.SNEAConv(32, 32, first_aggr=False).to(dev)
+    zs = s1(x, pos, neg)
+    s2(zs, pos, neg)
+    for nm, fn in (("SNEAConv layer 1 2M/40M/64 fp32", lambda: s1(x, pos, neg)),
+                   ("SNEAConv layer 2 2M/40M/(32|32) fp32", lambda: s2(zs, pos, neg))):
+        ms_ = timeit(fn)
+        emit(config=nm, ms=ms_, edges_per_s=nnz / ms_ * 1e3, kernels_ms=breakdown(fn))
+    del s1, s2, zs
+    # SDRLayer (row a9): 4 GATConv over the pos/neg in/out lists of the same graph + MLP, 64 -> 64
+    sdr = nn.SDRLayer(64, 64, [pos, pos.flip(0), neg, neg.flip(0)]).to(dev)
+    sdr(x)
+    ms_ = timeit(lambda: sdr(x))
+    emit(config="SDRLayer 4 x GATConv 2M/2x40M/64 fp32", ms=ms_, edges_per_s=2 * nnz / ms_ * 1e3,
+         kernels_ms=breakdown(lambda: sdr(x)))
+    del sdr
+    torch.cuda.empty_cache()
     # C4 as a model: SGCN(in=64, out=64, 2 layers), tanh fused into each layer's transform
     es = torch.cat([torch.cat([pos.t(), torch.ones(pos.size(1), 1, dtype=torch.long, device=dev)], 1),
                     torch.cat([neg.t(), -torch.ones(neg.size(1), 1, dtype=torch.long, device=dev)], 1)], 0)
