@@ -325,6 +325,15 @@ typedef struct pgsd_attn_args {
 
 PGSD_API int pgsd_edge_softmax(const pgsd_attn_args* args, pgsd_stream_t stream);
 
+/* GATConv aggregation with the edge softmax inside (PyG GATConv, heads = 1, as used by nn/signed/SDGNN.py:35-61 and
+ * nn/signed/SiGAT.py:59-64):  y[i] = sum_e alpha_e h[col_e] (+ bias) (+ beta * z[i]) over the entries of row i,
+ * alpha = softmax_i(leaky_relu(s_src[col_e] + s_dst[i])) with PyG's 1e-16 in the denominator.  fp32, feat a
+ * multiple of 4 (<= 128), 16-byte aligned rows; z may alias y (accumulating epilogue). */
+PGSD_API int pgsd_gat_aggregate(const int32_t* row_ptr, const int32_t* col, const float* s_src,
+                                  const float* s_dst, float negative_slope, const float* h, int64_t ldh,
+                                  int32_t feat, int64_t n_rows, const float* bias, const float* z,
+                                  int64_t ldz, float beta, float* y, int64_t ldy, pgsd_stream_t stream);
+
 /* Weight / bias gradient of y = X W (backward pass):
  *   dw[k, n] += sum_r x[r, k] * g[r, n];   db[n] += sum_r g[r, n]   (db may be NULL)
  * x: [n_rows, k], g: [n_rows, n] (fp32 or bf16), dw/db fp32 accumulated with atomics: the

@@ -90,6 +90,7 @@ _PROTOTYPES = {
     "pgsd_build_magnetic_rows_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_double,
                                                   C.c_int, _f32, _vp, _vp, _vp, _vp]),
     "pgsd_signed_triangle_counts": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i64, _i64, _vp, _vp]),
+    "pgsd_gat_aggregate": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _i64, _i32, _i64, _vp, _vp, _i64, _f32, _vp, _i64, _vp]),
     "pgsd_magnetic_q_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
                                        _vp, _i64, _vp, _i64, C.c_double, _vp, _vp]),
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),

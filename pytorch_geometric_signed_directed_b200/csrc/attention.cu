@@ -120,9 +120,179 @@ __global__ void __launch_bounds__(256) edge_softmax_kernel(const AttnParams p) {
   }
 }
 
+// ---- GATConv aggregation with the softmax inside (SDRLayer / SiGAT) -----------------------
+//   y[i] = sum_e alpha_e h[j_e] (+ bias) (+ beta z[i]),   alpha_e = exp(t_e - max_i) / (sum_e' exp(t_e' - max_i) + 1e-16),
+//   t_e = leaky_relu(s_src[j_e] + s_dst[i])
+// One LPR-lane group per destination row, like the aggregation kernels of spmm.cu, but the per-entry weight is
+// computed on the fly from two scalar gathers and normalised at the END of the row (running maximum, rescaled
+// partial sums): the separate softmax launch, the alpha array and its re-read disappear.
+struct GatParams {
+  int64_t n_rows;
+  int32_t feat, lpr_active;
+  float slope, beta;
+  const int32_t* row_ptr;
+  const int32_t* col;
+  const float* s_src;
+  const float* s_dst;
+  const float* h;
+  int64_t ldh;
+  const float* bias;
+  const float* z;
+  int64_t ldz;
+  float* y;
+  int64_t ldy;
+};
+
+// Software pipeline as in spmm_groups_kernel: while the feature rows of the current batch are being gathered,
+// the column indices and then the scores of the NEXT batch (same row, or the first batch of the group's next
+// row, whose row_ptr pair / s_dst were fetched one row ahead) are already in flight -- without it the chain
+// row_ptr -> col -> s_src -> exp -> gathers is exposed once per row and the kernel is no faster than the
+// softmax + aggregation pair it replaces (measured, session 39).
+template <int LPR>
+__global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int G = 32 / LPR, U = 4;
+  const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+  const bool lane_active = l < p.lpr_active;
+  const int64_t stride = int64_t(gridDim.x) * 8 * G;
+  const float* hb = p.h + l * 4;
+
+  auto load_row = [&](int64_t r, int& b, int& e, float& sd) {
+    b = e = 0, sd = 0.f;
+    if (r < p.n_rows) b = __ldg(p.row_ptr + r), e = __ldg(p.row_ptr + r + 1), sd = __ldg(p.s_dst + r);
+  };
+  auto score = [&](int c, float sd) {
+    const float v = __ldg(p.s_src + c) + sd;
+    return v > 0.f ? v : p.slope * v;
+  };
+
+  int64_t row = (int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5)) * G + g;
+  int b, e, nb, ne;
+  float sd, nsd;
+  load_row(row, b, e, sd);
+  int64_t nrow = row + stride;
+  load_row(nrow, nb, ne, nsd);
+  int kb = b;
+  int c = 0;
+  float t = -INFINITY;
+  if (kb + l < e) c = __ldg(p.col + kb + l), t = score(c, sd);
+
+  float m = -INFINITY, lsum = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  while (__any_sync(FULL, row < p.n_rows)) {
+    const int cnt = min(LPR, e - kb);                       // <= 0: empty / finished row
+    const bool more = kb + LPR < e;
+    // next batch: issue its column-index load now
+    const int nk = (more ? kb + LPR : nb) + l;
+    const int nend = more ? e : ne;
+    const float nsdv = more ? sd : nsd;
+    const bool nvalid = nk < nend;
+    const int nc = nvalid ? __ldg(p.col + nk) : 0;
+
+    // softmax statistics of the current batch
+    float bm = t;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(FULL, bm, o, LPR));
+    const float mn = fmaxf(m, bm);
+    const float sc = (m == -INFINITY) ? 0.f : expf(m - mn);
+    acc.x *= sc, acc.y *= sc, acc.z *= sc, acc.w *= sc, lsum *= sc;
+    m = mn;
+    const float pw = (l < cnt) ? expf(t - mn) : 0.f;
+    float ps = pw;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ps += __shfl_xor_sync(FULL, ps, o, LPR);
+    lsum += ps;
+
+    float nt = -INFINITY;
+    for (int j = 0; __any_sync(FULL, j < cnt); j += U) {
+      float4 d[U];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = j + u;
+        const int cc = __shfl_sync(FULL, c, idx & (LPR - 1), LPR);
+        const float ww = __shfl_sync(FULL, pw, idx & (LPR - 1), LPR);
+        const bool ok = idx < cnt && lane_active;
+        w[u] = ok ? ww : 0.f;
+        if (ok) d[u] = __ldg(reinterpret_cast<const float4*>(hb + int64_t(cc) * p.ldh));
+        else d[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc.x = fmaf(w[u], d[u].x, acc.x), acc.y = fmaf(w[u], d[u].y, acc.y);
+        acc.z = fmaf(w[u], d[u].z, acc.z), acc.w = fmaf(w[u], d[u].w, acc.w);
+      }
+    }
+    // The next batch's scores go out LAST: they depend on nc, and a dependent load in the middle of the gather
+    // sequence stalls the in-order warp before the remaining gathers are issued (2.0 ms per launch instead of
+    // 1.46, session 39); here nc has arrived behind the gathers and only the score latency is exposed.
+    if (nvalid) nt = score(nc, nsdv);
+
+    if (more) {
+      kb += LPR;
+    } else {
+      if (row < p.n_rows && lane_active) {
+        const float inv = 1.0f / (lsum + 1e-16f);
+        float4 o = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        if (p.bias) {
+          const float4 bs = __ldg(reinterpret_cast<const float4*>(p.bias + l * 4));
+          o.x += bs.x, o.y += bs.y, o.z += bs.z, o.w += bs.w;
+        }
+        if (p.z) {
+          const float4 zz = *reinterpret_cast<const float4*>(p.z + row * p.ldz + l * 4);
+          o.x = fmaf(p.beta, zz.x, o.x), o.y = fmaf(p.beta, zz.y, o.y), o.z = fmaf(p.beta, zz.z, o.z),
+          o.w = fmaf(p.beta, zz.w, o.w);
+        }
+        *reinterpret_cast<float4*>(p.y + row * p.ldy + l * 4) = o;
+      }
+      m = -INFINITY, lsum = 0.f, acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      row = nrow, b = nb, e = ne, sd = nsd, kb = nb;
+      nrow += stride;
+      load_row(nrow, nb, ne, nsd);
+    }
+    c = nc, t = nt;
+    __syncwarp();
+  }
+}
+
 }  // namespace pgsd
 
 using namespace pgsd;
+
+extern "C" int pgsd_gat_aggregate(const int32_t* row_ptr, const int32_t* col, const float* s_src, const float* s_dst,
+                                  float negative_slope, const float* h, int64_t ldh, int32_t feat, int64_t n_rows,
+                                  const float* bias, const float* z, int64_t ldz, float beta, float* y, int64_t ldy,
+                                  pgsd_stream_t stream) {
+  PGSD_REQUIRE(n_rows >= 0 && feat >= 0, "gat_aggregate: negative size");
+  if (n_rows == 0 || feat == 0) return PGSD_OK;
+  PGSD_REQUIRE(row_ptr && s_src && s_dst && h && y, "gat_aggregate: null pointer");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  PGSD_REQUIRE(feat % 4 == 0 && feat <= 128, "gat_aggregate: feat must be a multiple of 4, at most 128 (got %d)", feat);
+  PGSD_REQUIRE(al16(h) && al16(y) && ldh % 4 == 0 && ldy % 4 == 0 && (bias == nullptr || al16(bias)) &&
+                   (z == nullptr || (al16(z) && ldz % 4 == 0)),
+               "gat_aggregate: rows must be 16-byte aligned");
+  GatParams p{};
+  p.n_rows = n_rows, p.feat = feat, p.lpr_active = feat / 4, p.slope = negative_slope, p.beta = beta;
+  p.row_ptr = row_ptr, p.col = col, p.s_src = s_src, p.s_dst = s_dst, p.h = h, p.ldh = ldh, p.bias = bias;
+  p.z = z, p.ldz = ldz, p.y = y, p.ldy = ldy;
+  int lpr = 1;
+  while (lpr < p.lpr_active) lpr <<= 1;
+  int64_t grid = ceil_div<int64_t>(n_rows, 8 * (32 / lpr));
+  if (grid > int64_t(sm_count()) * 5) grid = int64_t(sm_count()) * 5;   // one wave: 48 registers -> 5 CTAs per SM
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (lpr) {
+    case 1: gat_aggregate_kernel<1><<<unsigned(grid), 256, 0, st>>>(p); break;
+    case 2: gat_aggregate_kernel<2><<<unsigned(grid), 256, 0, st>>>(p); break;
+    case 4: gat_aggregate_kernel<4><<<unsigned(grid), 256, 0, st>>>(p); break;
+    case 8: gat_aggregate_kernel<8><<<unsigned(grid), 256, 0, st>>>(p); break;
+    case 16: gat_aggregate_kernel<16><<<unsigned(grid), 256, 0, st>>>(p); break;
+    default: gat_aggregate_kernel<32><<<unsigned(grid), 256, 0, st>>>(p); break;
+  }
+  PGSD_LAUNCH_CHECK("gat_aggregate_kernel");
+  return PGSD_OK;
+}
+
 
 extern "C" int pgsd_edge_softmax(const pgsd_attn_args* a, pgsd_stream_t stream) {
   PGSD_REQUIRE(a != nullptr, "edge_softmax: args is null");

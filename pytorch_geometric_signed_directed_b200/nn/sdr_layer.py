@@ -79,6 +79,12 @@ class GATConv(torch.nn.Module):
         `accumulate_into`: running sum the result is ADDED to in the aggregation epilogue (no bias then; used
         when the layer that follows is linear and has been folded into h, see SDRLayer.forward)."""
         p = self._plan_for(edge_index, h.size(0))
+        if ops.gat_aggregate_supported(h, out, accumulate_into) and (self.bias is None or self.out_channels % 4 == 0):
+            # softmax inside the aggregation kernel: no alpha array, one launch
+            if accumulate_into is not None:
+                return ops.gat_aggregate(p, s_src, s_dst, h, slope=self.negative_slope, z=accumulate_into, beta=1.0,
+                                         out=accumulate_into)
+            return ops.gat_aggregate(p, s_src, s_dst, h, slope=self.negative_slope, bias=self.bias, out=out)
         _, alphas = ops.edge_softmax([p], [s_src], [s_dst], act="leaky_relu", slope=self.negative_slope,
                                      want_alpha=True)
         weighted = CSRPlan(p.n_dst, p.n_src, p.nnz, p.num_input_edges, p.row_ptr, p.col, [alphas[0]], [None], [0.0])

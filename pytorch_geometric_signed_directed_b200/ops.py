@@ -253,6 +253,44 @@ def edge_softmax(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Seque
     return y, alphas
 
 
+# 1: GATConv aggregates with the softmax inside one kernel (pgsd_gat_aggregate); 0 (default): edge_softmax +
+# spmm.  The one-kernel route is parity-green but not faster yet: 1.46 ms per 22M-entry launch without software
+# pipelining (= the two launches it replaces, 0.39 + 1.08 ms), 1.78 ms with the next batch's column / score
+# prefetch (the dependent score gather costs more than it hides) -- profiles/r01_configs_attention_s39.jsonl.
+GAT_FUSED = int(os.environ.get("PGSD_GAT_FUSED", "0"))
+
+
+def gat_aggregate_supported(h: Tensor, out: Optional[Tensor] = None, z: Optional[Tensor] = None) -> bool:
+    ok = lambda t: t is None or (t.dtype == torch.float32 and t.stride(1) == 1 and t.data_ptr() % 16 == 0
+                                 and t.stride(0) % 4 == 0)
+    return bool(GAT_FUSED) and h.dim() == 2 and h.size(1) % 4 == 0 and h.size(1) <= 128 and ok(h) and ok(out) and ok(z)
+
+
+def gat_aggregate(plan: CSRPlan, s_src: Tensor, s_dst: Tensor, h: Tensor, *, slope: float = 0.2,
+                  bias: Optional[Tensor] = None, z: Optional[Tensor] = None, beta: float = 1.0,
+                  out: Optional[Tensor] = None) -> Tensor:
+    """y = softmax-weighted sum of h over the incoming entries (+ bias) (+ beta * z)  (`pgsd_gat_aggregate`)."""
+    global LAUNCHES
+    require_cuda(h, "h")
+    dev, n, f = h.device, plan.n_dst, h.size(1)
+    ss = s_src.detach().float().contiguous().view(-1)
+    sd = s_dst.detach().float().contiguous().view(-1)
+    if ss.numel() < plan.n_src or sd.numel() < plan.n_dst:
+        raise ValueError("gat_aggregate: score vectors shorter than the plan's node ranges")
+    y = out if out is not None else torch.empty((n, f), dtype=torch.float32, device=dev)
+    b = None if bias is None else bias.detach().float().contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(dev), _Timed("gat_aggregate", dev):
+        _lib.check(lib.pgsd_gat_aggregate(plan.row_ptr.data_ptr(), plan.col.data_ptr(), ss.data_ptr(), sd.data_ptr(),
+                                          float(slope), h.data_ptr(), h.stride(0), f, n,
+                                          None if b is None else b.data_ptr(),
+                                          None if z is None else z.data_ptr(), 0 if z is None else z.stride(0),
+                                          float(beta), y.data_ptr(), y.stride(0),
+                                          torch.cuda.current_stream(dev).cuda_stream), "pgsd_gat_aggregate")
+    LAUNCHES += 1
+    return y
+
+
 def xtg_accumulate(x: Tensor, g: Tensor, dw: Tensor, db: Optional[Tensor] = None) -> None:
     """dw[k, n] += sum_r x[r, k] g[r, n]; db[n] += sum_r g[r, n]  (`pgsd_xtg_accumulate`)."""
     global LAUNCHES

@@ -836,3 +836,35 @@ def test_uncached_layer_reuses_its_plan_only_for_identical_tensors():
     ref.load_state_dict(conv.state_dict())
     r = ref(x, x, ei, ew, lambda_max=torch.tensor(1.5))
     assert torch.equal(conv(x, x, ei, ew, lambda_max=torch.tensor(1.5))[0], r[0])
+
+
+@pytest.mark.parametrize("n,e,c", [(4000, 60_000, 64), (3000, 20_000, 12), (2000, 30_000, 128), (500, 0, 8)])
+def test_gat_aggregation_with_inkernel_softmax(n, e, c):
+    """`pgsd_gat_aggregate` (softmax inside the aggregation kernel) against the two-kernel route (edge softmax ->
+    alpha array -> weighted aggregation) and against the oracle's GATConv; also the accumulating epilogue."""
+    g = torch.Generator().manual_seed(n + c)
+    ei = torch.randint(0, n - 7, (2, e), generator=g)
+    if e:
+        ei[1, :600] = 3                                                  # one long row (several batches per group)
+    x = torch.randn(n, c, generator=g)
+    gat = nn.GATConv(c, c).to(DEV)
+    with torch.no_grad():
+        gat.bias.uniform_(-0.3, 0.3)
+    ref = port.gat_conv(x, ei, gat.lin.weight.detach().cpu(), gat.att_src.detach().cpu().view(-1),
+                        gat.att_dst.detach().cpu().view(-1), gat.bias.detach().cpu())
+    xd, eid = x.to(DEV), ei.to(DEV)
+    old = ops.GAT_FUSED
+    try:
+        ops.GAT_FUSED = 1
+        fused = gat(xd, eid)
+        acc = torch.randn(n, c, generator=g).to(DEV)
+        acc0 = acc.clone()
+        hs, ss = nn.sdr_layer.gat_transforms(xd, [gat])
+        gat.aggregate(hs[0], ss[0][0], ss[0][1], eid, accumulate_into=acc)
+        ops.GAT_FUSED = 0
+        two = gat(xd, eid)
+    finally:
+        ops.GAT_FUSED = old
+    assert_close_rel(fused, ref, 1e-5, "fused vs oracle")
+    assert_close_rel(fused, two, 2e-6, "fused vs two-kernel route")
+    assert_close_rel(acc - acc0, fused - gat.bias.detach(), 2e-6, "accumulating epilogue")
