@@ -119,3 +119,51 @@ def test_synthetic_generators_follow_the_reference_distributions():
     # both directions stored
     assert torch.equal(torch.sort(pos[0] * 2000 + pos[1]).values, torch.sort(pos[1] * 2000 + pos[0]).values)
     assert synthetic.meta_graph_cyclic(3, 0.1)[0, 1] == pytest.approx(0.9)
+
+
+def test_argument_validation_of_the_newer_entry_points():
+    """Entry points added after the first C-ABI batch reject bad arguments before touching the device."""
+    lib = _lib.load()
+    one = C.c_int64(0)
+    buf = (C.c_float * 64)()
+    ibuf = (C.c_int32 * 8)()
+    # pgsd_gat_aggregate: feature width must be a multiple of 4, rows 16-byte aligned
+    rc = lib.pgsd_gat_aggregate(ibuf, ibuf, buf, buf, 0.2, buf, 3, 3, 2, None, None, 0, 0.0, buf, 3, None)
+    assert rc == 1 and b"multiple of 4" in lib.pgsd_last_error()
+    rc = lib.pgsd_gat_aggregate(None, ibuf, buf, buf, 0.2, buf, 4, 4, 2, None, None, 0, 0.0, buf, 4, None)
+    assert rc == 1 and b"null" in lib.pgsd_last_error()
+    assert lib.pgsd_gat_aggregate(None, None, None, None, 0.2, None, 4, 4, 0, None, None, 0, 0.0, None, 4, None) == 0
+    # pgsd_signed_triangle_counts: null list table
+    rc = lib.pgsd_signed_triangle_counts(None, None, ibuf, ibuf, 5, 10, ibuf, None)
+    assert rc == 1 and b"null" in lib.pgsd_last_error()
+    assert lib.pgsd_signed_triangle_counts(None, None, None, None, 0, 10, None, None) == 0      # no edges: no-op
+    # row-range builder: the range must lie inside [0, num_nodes]
+    rc = lib.pgsd_build_magnetic_rows_begin(ibuf, ibuf, None, 1, 10, 7, 3, 0, ibuf, ibuf, buf, buf, buf,
+                                            C.byref(one), buf, 1 << 20, None)
+    assert rc != 0 and b"row range" in lib.pgsd_last_error()
+    rc = lib.pgsd_build_magnetic_rows_finish(ibuf, ibuf, buf, buf, buf, 10, 4, 12, 0.25, 1, 2.0, buf, buf, buf, None)
+    assert rc != 0 and b"row range" in lib.pgsd_last_error()
+    assert lib.pgsd_build_magnetic_rows_finish(None, None, None, None, None, 10, 4, 4, 0.25, 1, 2.0, None, None, None,
+                                               None) == 0                                         # empty shard
+
+
+def test_new_model_wrappers_keep_the_reference_contracts():
+    from pytorch_geometric_signed_directed_b200 import distributed as pgd
+    m = nn.DiGCN_Inception_Block_node_classification(7, 16, 4, dropout=0.5)
+    assert sorted(k for k, _ in m.named_parameters())[:3] == ["ib1.conv1.bias", "ib1.conv1.weight", "ib1.conv2.bias"]
+    assert m.ib3.conv1.weight.shape == (16, 4) and m.ib1.ln.weight.shape == (16, 7)
+    es = torch.tensor([[0, 1, 1], [1, 2, -1], [2, 0, 1]])
+    with pytest.raises(NotImplementedError, match="init_emb"):
+        nn.SGCN(3, es)
+    with pytest.raises(NotImplementedError, match="init_emb"):
+        nn.SDGNN(3, es)
+    with pytest.raises(NotImplementedError, match="init_emb"):
+        nn.SiGAT(3, es)
+    with pytest.raises(PgsdError, match="no CPU path"):
+        nn.SDGNN(3, es, in_dim=4, out_dim=4, init_emb=torch.randn(3, 4))       # motif mining needs the device
+    sg = nn.SGCN(3, es, in_dim=4, out_dim=4, init_emb=torch.randn(3, 4))
+    assert sg.pos_edge_index.tolist() == [[0, 2], [1, 0]] and sg.neg_edge_index.tolist() == [[1], [2]]
+    assert [n_ for n_, _ in sg.named_parameters()][:2] == ["x", "conv1.lin_b.weight"]
+    with pytest.raises(NotImplementedError):
+        sg.loss()
+    assert pgd.halo_fraction([torch.arange(2, dtype=torch.int32)] * 2, [0, 4, 8], 0) == 1.0
