@@ -34,23 +34,11 @@ __device__ __forceinline__ float attn_act(float v, int act, float slope) {
   if (act == 0) return tanhf(v);
   return v > 0.f ? v : slope * v;   // leaky_relu
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float warp_add(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // One LPR-lane group per destination row (rows have ~10-20 entries: a whole warp per row leaves most lanes
-// idle), ONE pass over the entries for the softmax statistics: every lane keeps a running maximum and the
-// exponent sums relative to it (rescaled when the maximum moves), the group merges the (max, sums) triples
-// with shuffles.  Mode A needs nothing else; mode B revisits the entries once to write alpha.  The first
-// version of this kernel used a warp per row and re-gathered / re-evaluated every entry in three passes
-// (0.75 ms per 20M entries; this one: see profiles/README.md).
+// idle).  Every entry is gathered and activated ONCE: the first CACHE entries per lane and type stay in registers
+// between the maximum pass and the sum pass (longer rows re-evaluate the rest).  The first version of this kernel
+// used a warp per row and re-gathered / re-evaluated every entry in three passes (0.75 ms per 20M entries); a
+// grouped version with online rescaling was issue-bound on its expf calls (0.36-0.41 ms, ncu session 41).
 template <int LPR>
 __global__ void __launch_bounds__(256) edge_softmax_kernel(const AttnParams p) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -71,31 +59,57 @@ __global__ void __launch_bounds__(256) edge_softmax_kernel(const AttnParams p) {
         b[t] = __ldg(p.row_ptr[t] + row), e[t] = __ldg(p.row_ptr[t] + row + 1);
         sd[t] = __ldg(p.s_dst[t] + row);
       }
-    float m = -INFINITY, sum[2] = {0.f, 0.f};
-    for (int t = 0; t < p.n_types; ++t)
-      for (int k = b[t] + l; k < e[t]; k += LPR) {
-        const float v = attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope);
-        if (v > m) {
-          const float sc = expf(m - v);          // exp(-inf) = 0 on the first entry
-          sum[0] *= sc, sum[1] *= sc, m = v;
-        }
-        sum[t] += expf(v - m);
+    // pass 1: activations of this lane's entries (the first CACHE per type stay in registers), group maximum.
+    // No exponentials here: ncu showed the first grouped version issue-bound (68 % issue-active at 19 % DRAM)
+    // on the expf calls of its online rescaling and of the shuffle merge, not on the gathers.
+    constexpr int CACHE = 2;
+    float cv[2][CACHE];
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {                       // fixed bound: cv[][] must stay in registers
+      if (t >= p.n_types) continue;
+#pragma unroll
+      for (int i = 0; i < CACHE; ++i) {
+        const int k = b[t] + l + i * LPR;
+        cv[t][i] = -INFINITY;
+        if (k < e[t]) cv[t][i] = attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope);
+        m = fmaxf(m, cv[t][i]);
       }
+      for (int k = b[t] + l + CACHE * LPR; k < e[t]; k += LPR)            // long rows: not cached
+        m = fmaxf(m, attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope));
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o, LPR));
+    // pass 2: exponent sums per type (one expf per entry), group sums
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (t >= p.n_types) continue;
+#pragma unroll
+      for (int i = 0; i < CACHE; ++i)
+        if (cv[t][i] != -INFINITY) sum[t] += expf(cv[t][i] - m);
+      for (int k = b[t] + l + CACHE * LPR; k < e[t]; k += LPR)
+        sum[t] += expf(attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope) - m);
+    }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) {
-      const float m2 = __shfl_xor_sync(FULL, m, o, LPR);
-      const float a0 = __shfl_xor_sync(FULL, sum[0], o, LPR), a1 = __shfl_xor_sync(FULL, sum[1], o, LPR);
-      const float mn = fmaxf(m, m2);
-      const float f1 = (m == -INFINITY) ? 0.f : expf(m - mn), f2 = (m2 == -INFINITY) ? 0.f : expf(m2 - mn);
-      sum[0] = sum[0] * f1 + a0 * f2, sum[1] = sum[1] * f1 + a1 * f2, m = mn;
+      sum[0] += __shfl_xor_sync(FULL, sum[0], o, LPR);
+      sum[1] += __shfl_xor_sync(FULL, sum[1], o, LPR);
     }
     const float inv = 1.0f / (sum[0] + sum[1] + 1e-16f);
     // mode B: per-entry alpha
-    for (int t = 0; t < p.n_types; ++t)
-      if (p.alpha_out[t] != nullptr)
-        for (int k = b[t] + l; k < e[t]; k += LPR)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (t < p.n_types && p.alpha_out[t] != nullptr) {
+#pragma unroll
+        for (int i = 0; i < CACHE; ++i) {
+          const int k = b[t] + l + i * LPR;
+          if (k < e[t]) p.alpha_out[t][k] = expf(cv[t][i] - m) * inv;
+        }
+        for (int k = b[t] + l + CACHE * LPR; k < e[t]; k += LPR)
           p.alpha_out[t][k] =
               expf(attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope) - m) * inv;
+      }
     // mode A: y[i] = xd0[i] * P + xd1[i] * N
     if (p.y != nullptr && live) {
       const float w0 = sum[0] * inv, w1 = sum[1] * inv;       // an isolated row: 0 * 1e16 = 0
