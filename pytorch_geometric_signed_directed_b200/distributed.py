@@ -258,6 +258,16 @@ class SymmetricPullExchange:
         return works
 
 
+def _distinct_operands(xs: Sequence[Tensor]) -> int:
+    """1 when both operators read ONE tensor (x_real is x_imag, how the reference's example calls the first layer of
+    every MagNet model): the shard then travels once, and the block launches see the same pointer twice, which the
+    aggregation kernel turns into one gather per entry."""
+    if len(xs) == 2 and xs[0].data_ptr() == xs[1].data_ptr() and xs[0].shape == xs[1].shape \
+            and xs[0].stride() == xs[1].stride():
+        return 1
+    return len(xs)
+
+
 def _default_aggregate(block: CSRPlan, xs, op_ids, alpha, beta, zs, out):
     return ops.spmm(block, xs, op_ids, alpha=alpha, beta=beta, zs=zs, out=out)
 
@@ -342,9 +352,10 @@ class ShardedAggregator:
             return self._gather_then_single(xs, op_ids, f, alpha, beta, zs)
         if self.mode == "halo":
             return self._halo_step(xs, op_ids, f, alpha, beta, zs)
-        # interleave the operands: one [n_local, n_ops*F] send buffer
-        pull = self._pull_exchange(xs[0], n_ops * f)
-        views = lambda buf: [buf[:, k * f:(k + 1) * f] for k in range(n_ops)]
+        # interleave the DISTINCT operands: one [n_local, n_cols*F] send buffer
+        n_cols = _distinct_operands(xs)
+        pull = self._pull_exchange(xs[0], n_cols * f)
+        views = lambda buf: [buf[:, (k % n_cols) * f:(k % n_cols + 1) * f] for k in range(n_ops)]
         trace = TRACE is not None and xs[0].is_cuda
         mark = (lambda name: TRACE.append((name, _now_event()))) if trace else (lambda name: None)
         mark("start")
@@ -353,11 +364,11 @@ class ShardedAggregator:
         # the first shard lands at 1.9 ms instead of 1.4 ms.)
         if pull is not None:
             send = pull.send_buffer(self.n_local)
-            for k in range(n_ops):
+            for k in range(n_cols):
                 send[:, k * f:(k + 1) * f].copy_(xs[k])
         else:
-            send = xs[0].contiguous() if n_ops == 1 else torch.cat(list(xs), dim=1)
-        recv = self._buffers(send, n_ops * f)
+            send = xs[0].contiguous() if n_cols == 1 else torch.cat(list(xs), dim=1)
+        recv = self._buffers(send, n_cols * f)
         if self.world == 1:
             works = []
         elif pull is not None:
@@ -402,15 +413,16 @@ ShardedAggregator._gather_then_single = _gather_then_single
 def _halo_step(self, xs, op_ids, f, alpha, beta, zs):
     """pack -> all_to_all (async) | own-column block -> wait -> remote-column block (+=)."""
     n_ops, hx = len(xs), self.halo
-    key = ("halo", xs[0].dtype, xs[0].device, n_ops * f)
+    n_cols = _distinct_operands(xs)
+    key = ("halo", xs[0].dtype, xs[0].device, n_cols * f)
     if self._recv is None or self._recv[0] != key:
-        mk = lambda rows: torch.empty((max(rows, 1), n_ops * f), dtype=xs[0].dtype, device=xs[0].device)
+        mk = lambda rows: torch.empty((max(rows, 1), n_cols * f), dtype=xs[0].dtype, device=xs[0].device)
         self._recv = (key, (mk(hx.n_send), mk(hx.n_recv)))
     send, recv = self._recv[1]
     gather = self.gather_fn or ops.gather_rows
     if hx.n_send:
         vec = (f * xs[0].element_size()) % 16 == 0 or self.gather_fn is not None
-        for k in range(n_ops):                     # halo pack: the rows the peers asked for
+        for k in range(n_cols):                    # halo pack: the rows the peers asked for
             dst = send[:hx.n_send, k * f:(k + 1) * f]
             if vec and xs[k].data_ptr() % 16 == 0 and (xs[k].stride(0) * xs[k].element_size()) % 16 == 0:
                 gather(xs[k], hx.serve, out=dst)
@@ -420,7 +432,7 @@ def _halo_step(self, xs, op_ids, f, alpha, beta, zs):
     y = self.aggregate_fn(self.own_block, list(xs), op_ids, alpha, beta, zs, None)
     work.wait()                                    # NCCL: the current stream waits; gloo: the host blocks
     if self.halo_block.nnz:
-        views = [recv[:, k * f:(k + 1) * f] for k in range(n_ops)]
+        views = [recv[:, (k % n_cols) * f:(k % n_cols + 1) * f] for k in range(n_ops)]
         y = self.aggregate_fn(self.halo_block, views, op_ids, alpha, 1.0, y, y)
     return y
 

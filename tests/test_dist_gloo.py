@@ -73,6 +73,13 @@ def _worker(rank, world, port_no, n, e, f):
         for k in range(2):
             assert torch.allclose(t1[k], ref[k][lo:hi], atol=1e-5), f"rank {rank} op {k}"
             assert torch.allclose(tg[k], ref[k][lo:hi], atol=1e-5), f"rank {rank} gather-mode op {k}"
+        # one tensor for both operators: the shard travels once (half-width buffers), same result
+        ref_s = _torch_aggregate(full, [xr, xr], (0, 1), 1.0, 0.0, None, None)
+        xs_loc = xr[lo:hi]
+        ts = agg([xs_loc, xs_loc])
+        assert agg._recv[0][-1] == f                       # exchange width F, not 2F
+        for k in range(2):
+            assert torch.allclose(ts[k], ref_s[k][lo:hi], atol=1e-5), f"rank {rank} shared op {k}"
         # Chebyshev step: T2 = 2 L T1 - T0 with a second exchange
         ref2 = _torch_aggregate(full, ref, (0, 1), 2.0, -1.0, [xr, xi], None)
         t2 = agg(t1, alpha=2.0, beta=-1.0, zs=[xr[lo:hi], xi[lo:hi]])
@@ -127,6 +134,12 @@ def _halo_worker(rank, world, port_no, n, e, f, band, long_range):
         t1 = agg([xr[lo:hi], xi[lo:hi]])
         for k in range(2):
             assert torch.allclose(t1[k], ref[k][lo:hi], atol=1e-5), f"rank {rank} op {k}"
+        # one tensor for both operators: halo rows are packed and exchanged once
+        ref_s = _torch_aggregate(full, [xr, xr], (0, 1), 1.0, 0.0, None, None)
+        xs_loc = xr[lo:hi]
+        ts = agg([xs_loc, xs_loc])
+        for k in range(2):
+            assert torch.allclose(ts[k], ref_s[k][lo:hi], atol=1e-5), f"rank {rank} shared op {k}"
         ref2 = _torch_aggregate(full, ref, (0, 1), 2.0, -1.0, [xr, xi], None)
         t2 = agg(t1, alpha=2.0, beta=-1.0, zs=[xr[lo:hi], xi[lo:hi]])
         t2b = agg(t1, alpha=2.0, beta=-1.0, zs=[xr[lo:hi], xi[lo:hi]])          # buffers are reused
