@@ -313,8 +313,12 @@ class ShardedAggregator:
         self.n_ops = len(local_plan.val)
         self.ring = RingExchange(rank, world, group)
         self.aggregate_fn = aggregate_fn
-        self._recv = None
-        self._pull = None
+        # exchange objects and buffers are cached PER (dtype, width): a model alternates between widths (first
+        # layer: one shared operand, later layers: two) and must not re-rendezvous symmetric memory every call
+        self._recv_cache = {}
+        self._pull_cache = {}
+        self._recv = None          # (key, buffers) of the most recent call
+        self._pull = None          # (key, exchange) of the most recent call
 
     def _pull_exchange(self, like: Tensor, width: int):
         """Copy-engine exchange over symmetric peer memory when it can be set up (CUDA tensors,
@@ -322,7 +326,7 @@ class ShardedAggregator:
         if self.world == 1 or not like.is_cuda or os.environ.get("PGSD_EXCHANGE", "pull") == "nccl":
             return None
         key = (like.dtype, width)
-        if self._pull is None or self._pull[0] != key:
+        if key not in self._pull_cache:
             ex = None
             try:
                 rows_max = max(self.bounds[b + 1] - self.bounds[b] for b in range(self.world))
@@ -332,16 +336,17 @@ class ShardedAggregator:
                 if self.rank == 0:
                     print(f"[pgsd] symmetric-memory exchange unavailable ({type(exc).__name__}: {exc}); "
                           "using the NCCL send/recv ring", file=sys.stderr, flush=True)
-            self._pull = (key, ex)
+            self._pull_cache[key] = ex
+        self._pull = (key, self._pull_cache[key])
         return self._pull[1]
 
     def _buffers(self, like: Tensor, width: int):
         key = (like.dtype, like.device, width)
-        if self._recv is None or self._recv[0] != key:
-            bufs = [None if b == self.rank else
-                    torch.empty((self.bounds[b + 1] - self.bounds[b], width), dtype=like.dtype,
-                                device=like.device) for b in range(self.world)]
-            self._recv = (key, bufs)
+        if key not in self._recv_cache:
+            self._recv_cache[key] = [None if b == self.rank else
+                                     torch.empty((self.bounds[b + 1] - self.bounds[b], width), dtype=like.dtype,
+                                                 device=like.device) for b in range(self.world)]
+        self._recv = (key, self._recv_cache[key])
         return self._recv[1]
 
     def __call__(self, xs: Sequence[Tensor], alpha: float = 1.0, beta: float = 0.0,
@@ -393,8 +398,9 @@ class ShardedAggregator:
 def _gather_then_single(self, xs, op_ids, f, alpha, beta, zs):
     n_ops, lo, hi = len(xs), self.bounds[self.rank], self.bounds[self.rank + 1]
     key = ("full", xs[0].dtype, xs[0].device, n_ops * f)
-    if self._recv is None or self._recv[0] != key:
-        self._recv = (key, torch.empty((self.bounds[-1], n_ops * f), dtype=xs[0].dtype, device=xs[0].device))
+    if key not in self._recv_cache:
+        self._recv_cache[key] = torch.empty((self.bounds[-1], n_ops * f), dtype=xs[0].dtype, device=xs[0].device)
+    self._recv = (key, self._recv_cache[key])
     full = self._recv[1]
     own = full[lo:hi]
     for k in range(n_ops):
@@ -415,9 +421,10 @@ def _halo_step(self, xs, op_ids, f, alpha, beta, zs):
     n_ops, hx = len(xs), self.halo
     n_cols = _distinct_operands(xs)
     key = ("halo", xs[0].dtype, xs[0].device, n_cols * f)
-    if self._recv is None or self._recv[0] != key:
+    if key not in self._recv_cache:
         mk = lambda rows: torch.empty((max(rows, 1), n_cols * f), dtype=xs[0].dtype, device=xs[0].device)
-        self._recv = (key, (mk(hx.n_send), mk(hx.n_recv)))
+        self._recv_cache[key] = (mk(hx.n_send), mk(hx.n_recv))
+    self._recv = (key, self._recv_cache[key])
     send, recv = self._recv[1]
     gather = self.gather_fn or ops.gather_rows
     if hx.n_send:

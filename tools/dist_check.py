@@ -48,6 +48,19 @@ def check(gname, want_mode, ei):
             ok &= good
             print(f"[rank {rank}] {gname} mode={sh.agg.mode} K={K} out_{nm}: max err {err:.3e} "
                   f"(scale {scale:.3e}) {'OK' if good else 'FAIL'}", flush=True)
+        # one tensor for both parts (the reference example's call): the shard travels once, then back to two
+        # tensors -- exchange objects of both widths stay cached
+        xloc = x_real[lo:hi].contiguous()
+        sr, si = sh(xloc, xloc)
+        fr, fi = conv(x_real, x_real, ei)
+        out_r2, _ = sh(x_real[lo:hi].contiguous(), x_imag[lo:hi].contiguous())
+        torch.cuda.synchronize()
+        for got, ref, nm in ((sr, fr[lo:hi], "shared real"), (si, fi[lo:hi], "shared imag"), (out_r2, full_r[lo:hi], "real again")):
+            err, scale = (got - ref).abs().max().item(), ref.abs().max().item()
+            good = err <= 2e-6 * scale
+            ok &= good
+            if not good or rank == 0:
+                print(f"[rank {rank}] {gname} K={K} {nm}: max err {err:.3e} {'OK' if good else 'FAIL'}", flush=True)
     return ok
 
 
