@@ -139,3 +139,83 @@ def test_row_normalised_and_mean_aggregations_dense():
     ref = m @ (xd @ w.double().numpy()) + b.double().numpy()
     got = port.digcn_conv(x, ei, ew, w, b).double().numpy()
     assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_dimpa_and_dgcn_dense():
+    """DIMPA (nn/directed/DIMPA.py:32-59): feat_s = sum_h w_s[h] P^h x_s with P = D^-1 (A + tau I) row-normalised over
+    the remaining self-loops, feat_t the same with A^T.  DGCNConv (nn/directed/DGCNConv.py:38-103 + PyG gcn_norm):
+    out = D^-1/2 (A^T + I) D^-1/2 x with D the in-degree of (A + I) -- aggregation at edge_index[1]."""
+    g = torch.Generator().manual_seed(9)
+    n, e, f, hop = 60, 420, 5, 3
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei = ei[:, ei[0] != ei[1]]                                    # loop-free (the loop rules are checked above)
+    ew = torch.rand(ei.size(1), generator=g) + 0.2
+    xs = torch.rand(n, f, generator=g) * 2 - 1
+    xt = torch.rand(n, f, generator=g) * 2 - 1
+    w_s, w_t = torch.rand(hop + 1, 1, generator=g), torch.rand(hop + 1, 1, generator=g)
+    a = np.zeros((n, n))
+    np.add.at(a, (ei[0].numpy(), ei[1].numpy()), ew.double().numpy())
+
+    def rw(m):
+        m = m + 0.5 * np.eye(n)
+        return m / m.sum(1, keepdims=True)
+    ps, pt = rw(a), rw(a.T)
+    fs, ft = w_s[0].item() * xs.double().numpy(), w_t[0].item() * xt.double().numpy()
+    cs, ct = xs.double().numpy(), xt.double().numpy()
+    for h in range(1, hop + 1):
+        cs, ct = ps @ cs, pt @ ct
+        fs, ft = fs + w_s[h].item() * cs, ft + w_t[h].item() * ct
+    ref = np.concatenate([fs, ft], 1)
+    got = port.dimpa(xs, xt, ei, ew, w_s, w_t, hop, 0.5).double().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    # DGCNConv
+    ah = a + np.eye(n)
+    deg = ah.sum(0)                                               # weighted in-degree (target = edge_index[1])
+    dis = deg ** -0.5
+    ref = (dis[:, None] * ah.T * dis[None, :]) @ xs.double().numpy()
+    got = port.dgcn_conv(xs, ei, ew).double().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_attention_layers_dense():
+    """GATConv (heads = 1): out_i = sum_j softmax_j(leaky_relu(a_s . h_j + a_d . h_i)) h_j + b over j in N_in(i) + {i};
+    SNEAConv first layer (nn/signed/SNEAConv.py:81-146): out_i = h_i * sum_j alpha_ij = h_i wherever node i has an
+    incoming entry (the message is the TARGET's feature, quirk Q7, and alpha sums to one), else 0."""
+    g = torch.Generator().manual_seed(13)
+    n, e, c = 50, 300, 6
+    ei = torch.randint(0, n - 2, (2, e), generator=g)
+    x = torch.randn(n, c, generator=g)
+    lin_w = torch.randn(c, c, generator=g) / c ** 0.5
+    a_s, a_d, b = torch.randn(c, generator=g), torch.randn(c, generator=g), torch.randn(c, generator=g)
+    h = x.double().numpy() @ lin_w.double().numpy().T
+    adj = np.zeros((n, n), dtype=bool)                            # adj[i, j]: j -> i
+    keep = ei[0] != ei[1]
+    adj[ei[1][keep].numpy(), ei[0][keep].numpy()] = True
+    mult = np.zeros((n, n))                                        # duplicate edges count twice in the softmax
+    np.add.at(mult, (ei[1][keep].numpy(), ei[0][keep].numpy()), 1.0)
+    mult += np.eye(n)
+    s = (h @ a_s.double().numpy())[None, :] + (h @ a_d.double().numpy())[:, None]
+    s = np.where(s > 0, s, 0.2 * s)
+    w = mult * np.exp(s - s.max())
+    alpha = w / w.sum(1, keepdims=True)
+    ref = alpha @ h + b.double().numpy()
+    got = port.gat_conv(x, ei, lin_w, a_s, a_d, b).double().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    # SNEAConv, first layer
+    out = 4
+    pos, neg = ei[:, :150], ei[:, 150:]
+    wb, wu = torch.randn(out, c, generator=g), torch.randn(out, c, generator=g)
+    bb, bu = torch.randn(out, generator=g), torch.randn(out, generator=g)
+    ab_w, au_w = torch.randn(1, 2 * out, generator=g), torch.randn(1, 2 * out, generator=g)
+    ab_b, au_b = torch.randn(1, generator=g), torch.randn(1, generator=g)
+    got = port.snea_conv(x, pos, neg, wb, bb, wu, bu, ab_w, ab_b, au_w, au_b, first_aggr=True).double().numpy()
+    for half, (edges, w_, b_) in enumerate(((pos, wb, bb), (neg, wu, bu))):
+        hh = x.double().numpy() @ w_.double().numpy().T + b_.double().numpy()
+        k = edges[:, edges[0] != edges[1]]
+        m = int(k.max()) + 1 if k.numel() else 0                  # self-loops re-added for nodes 0..max id only
+        has_in = np.zeros(n, dtype=bool)
+        has_in[:m] = True
+        has_in[k[1].numpy()] = True
+        ref = np.where(has_in[:, None], hh, 0.0)
+        blk = got[:, half * out:(half + 1) * out]
+        assert np.abs(blk - ref).max() <= 2e-6 * max(np.abs(ref).max(), 1e-30)
