@@ -170,6 +170,10 @@ PGSD_API int pgsd_build_magnetic_rows_finish(const int32_t* row_ptr, const int32
  *   nn/general/conv_base.py:111-117.
  * x/z/y are row-major with leading dimensions in ELEMENTS so column slices of wider
  * buffers can be aggregated/written in place (SGCNConv.py:109-119 half-width slices).
+ * n_ops = 2 with x[0] == x[1] and ldx[0] == ldx[1] (fp32; how examples/magnet_node.py:61-62
+ * calls the first layer: X_real and X_img are one tensor) gathers every neighbour row ONCE for
+ * both operators; results are bit-identical to the two-gather evaluation.  z[k] may alias
+ * y[k] (accumulating epilogue: every row is read and written by the same lanes).
  * ---------------------------------------------------------------------------------- */
 typedef struct pgsd_spmm_args {
   int64_t n_rows;            /* destination rows                                      */
@@ -192,7 +196,8 @@ typedef struct pgsd_spmm_args {
   const float* bias;         /* [F] or NULL                                           */
   int32_t variant;           /* 0 = library default; bits 0-3 loads in flight (2/4/8), 0x10 /
                                 0x20 prefer 128- / 256-bit gathers, 0x80 warp-per-row kernel
-                                instead of the default group-per-row kernel                 */
+                                instead of the default group-per-row kernel, 0x400 gather twice
+                                even when both operators read one tensor (A/B timing)        */
   int32_t diag_row_offset;   /* x row holding destination row 0 (diag term only): lets x span a
                                 larger node range than the plan's rows (row-sharded plans)  */
   float op_scale[2];         /* per-operator multiplier of alpha (0 is read as 1): -1 on the
@@ -250,7 +255,10 @@ typedef struct pgsd_dense_args {
   int32_t variant;           /* 0 = auto: TMA-fed warp-specialised tcgen05 kernel, else the
                                 register-staged tcgen05 kernel, else FFMA; 1 = FFMA; 2 / 4 / 8 =
                                 register-staged tcgen05 (synchronous / warp-specialised / deep
-                                prefetch); 16 = require the TMA-fed kernel                  */
+                                prefetch); 16 = require the TMA-fed kernel (experiment knobs of that
+                                kernel ride in the upper bits: 8-11 lo slots, 12-15 landing stages,
+                                16-18 timing-only knock-outs, 20-22 converter groups, 24-25 epilogue
+                                staging layout; 0 everywhere = measured defaults)            */
 } pgsd_dense_args;
 
 PGSD_API int pgsd_dense_transform(const pgsd_dense_args* args, pgsd_stream_t stream);
