@@ -170,7 +170,7 @@ def test_node_bounds_and_ring_schedule():
     assert [ring.source_of_round(s) for s in (1, 2, 3)] == [0, 3, 2]
 
 
-@pytest.mark.parametrize("world,long_range", [(2, 0.0), (3, 0.0), (2, 0.2)])
+@pytest.mark.parametrize("world,long_range", [(2, 0.0), (3, 0.0), (4, 0.0), (2, 0.2)])
 def test_halo_exchange_on_a_naturally_sharding_graph(world, long_range):
     """Locality-ordered graph: thin halo -> `auto` picks the all-to-all halo path; with 20 % long-range
     edges the halo is most of the matrix and `auto` must fall back to the ring all-gather."""
@@ -208,3 +208,24 @@ def _route_worker(rank, world, port_no, n, e):
 @pytest.mark.parametrize("world", [2, 3])
 def test_edge_routing_for_the_distributed_build(world):
     mp.spawn(_route_worker, args=(world, _free_port(), 101, 3000), nprocs=world, join=True)
+
+
+def test_locality_graph_generator_properties():
+    from pytorch_geometric_signed_directed_b200 import synthetic
+    n, band = 5000, 40
+    ei = synthetic.locality_edges(n, 60_000, band, 0.0, seed=2)
+    assert ei.dtype == torch.long and ei.shape[0] == 2
+    assert int(ei.min()) >= 0 and int(ei.max()) < n
+    assert bool((ei[0] != ei[1]).all())                                   # no self-loops
+    assert bool(((ei[0] - ei[1]).abs() <= band).all())                    # banded
+    key = ei[0] * n + ei[1]
+    assert key.unique().numel() == key.numel()                            # no duplicates
+    far = synthetic.locality_edges(n, 60_000, band, 0.3, seed=2)
+    assert float(((far[0] - far[1]).abs() > band).float().mean()) > 0.2   # long-range share lands anywhere
+    # a 1-D node-range split of the banded graph needs only a thin band of each neighbour shard
+    bounds = pgd.node_bounds(n, 4)
+    lo, hi = bounds[1], bounds[2]
+    rows = (ei[1] >= lo) & (ei[1] < hi)                                   # entries aggregated by rank 1 (dst rows)
+    src = ei[0][rows]
+    remote = src[(src < lo) | (src >= hi)]
+    assert remote.unique().numel() <= 2 * band
