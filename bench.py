@@ -12,12 +12,14 @@ the whole graph.  metric = input edges aggregated per second = E_input / t_step.
             H2D of x_real/x_imag and D2H of out_real/out_imag inside the timed region.
   roofline: dominant kernel = pgsd_spmm_csr; algorithmic bytes / its CUDA-event duration measured
             inside the timed region, against MEASURED_PEAKS.json's hbm_gbs.
-  cpu_baseline: oracle/port.py (the reference's CPU op sequence) on a bounded 1/8-scale sample.
+  cpu_baseline: oracle/port.py (the reference's CPU op sequence) on the same 1M/20M graph, a few forwards.
 N > 1 ("weak" scaling): the graph grows to N*1M nodes / N*20M edges, destination rows are
-sharded by node range, every rank builds only its rows of the operator, and feature shards are pulled over
-NVLink by the copy engines (symmetric peer memory; NCCL send/recv ring as fallback), pipelined with the
-per-shard column-block aggregation (pytorch_geometric_signed_directed_b200/distributed.py).
-`--impl reference` times the CPU port only (rank 0), same metric/config.
+sharded by node range, every rank builds only its rows of the operator, and feature shards are pushed
+over NVLink into the peers' receive planes by one kernel (pgsd_shard_push: symmetric peer memory, per-slice
+flags), overlapped with the aggregation of the own-column block and of every landed slice
+(pytorch_geometric_signed_directed_b200/distributed.py).  Extra keys: parity_check (rank 0's rows of the
+timed path against the oracle), halo_path (a locality-ordered graph: all-to-all of halo rows instead).
+`--impl reference` times the CPU port only (rank 0) on the whole 1M/20M graph, same metric.
 """
 from __future__ import annotations
 
@@ -143,59 +145,96 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------ CPU baseline
 
-def cpu_reference_run(steps: int, warmup: int, scale_div: int = 8):
-    """The reference's CPU op sequence (oracle/port.py: index_select -> mul -> scatter_add_, the
-    four Chebyshev chains, 4(K+1) matmuls) on the host cores, on a bounded sample: a DSBM graph
-    with the same mean degree and 1/scale_div of the nodes/edges of the per-GPU workload.
-    torch's CPU scatter_add_ does not scale to very wide hosts, so the thread count is chosen
-    among {all cores, 32, 16, 8} by one untimed forward each (the fastest wins) -- the baseline
-    gets the best setting the host offers."""
-    from oracle import port
+def _cpu_inputs(n, e):
     from pytorch_geometric_signed_directed_b200 import synthetic
-    cores = os.cpu_count() or 1
-    n, e = N_PER_GPU // scale_div, E_PER_GPU // scale_div
     ei, _ = synthetic.dsbm_edges(n, 3, num_edges=e, eta=0.1, size_ratio=1.5, seed=0)
     g = torch.Generator().manual_seed(0)
     xr = torch.rand(n, FEAT, generator=g) * 2 - 1
     xi = torch.rand(n, FEAT, generator=g) * 2 - 1
     w = torch.rand(2, FEAT, FEAT, generator=g) - 0.5
-    b = torch.zeros(FEAT)
+    return ei, xr, xi, w, torch.zeros(FEAT)
 
-    def fwd():
-        t0 = time.perf_counter()
-        port.magnet_conv(xr, xi, ei, None, w, b, 0.25, "sym", cached_result=cached)
-        return time.perf_counter() - t0
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 150.0):
+    """The reference's CPU op sequence (oracle/port.py: index_select -> mul -> scatter_add_, the four
+    Chebyshev chains, 4(K+1) matmuls; MagNetConv.py:185-249 op for op) on the host cores, on the
+    benchmark's OWN per-GPU graph: DSBM 1M nodes / 20M edges / 64 features, cached operator (steady
+    state of cached=True), under torch.no_grad().  torch's CPU scatter_add_ does not scale to very wide
+    hosts, so the thread count is first chosen among {all cores, 32, 16, 8} on a 1/8-size graph of the
+    same mean degree (seconds; the fastest wins) -- the baseline gets the best setting the host offers.
+    `steps` timed forwards after `warmup` untimed ones, cut short so that the timed part stays within
+    budget_s (at least 3 timed forwards); the count actually run is returned."""
+    from oracle import port
+    cores = os.cpu_count() or 1
     with torch.no_grad():
-        cached = port.magnet_norm(ei, None, n, 0.25, "sym", 2.0)       # cached=True steady state
+        ei, xr, xi, w, b = _cpu_inputs(N_PER_GPU // 8, E_PER_GPU // 8)
+        cached = port.magnet_norm(ei, None, xr.size(0), 0.25, "sym", 2.0)
         trial = {}
         for th in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
             torch.set_num_threads(th)
-            fwd()
-            trial[th] = fwd()
+            port.magnet_conv(xr, xi, ei, None, w, b, 0.25, "sym", cached_result=cached)
+            t0 = time.perf_counter()
+            port.magnet_conv(xr, xi, ei, None, w, b, 0.25, "sym", cached_result=cached)
+            trial[th] = time.perf_counter() - t0
         best = min(trial, key=trial.get)
         torch.set_num_threads(best)
-        for _ in range(max(0, warmup - 1)):
+        small = {"nodes": xr.size(0), "edges": ei.size(1), "s_per_forward": trial[best],
+                 "value": ei.size(1) / trial[best]}
+        del ei, xr, xi, cached
+
+        ei, xr, xi, w, b = _cpu_inputs(N_PER_GPU, E_PER_GPU)
+        t0 = time.perf_counter()
+        cached = port.magnet_norm(ei, None, xr.size(0), 0.25, "sym", 2.0)       # operator build (cold part)
+        build_s = time.perf_counter() - t0
+
+        def fwd():
+            t0 = time.perf_counter()
+            port.magnet_conv(xr, xi, ei, None, w, b, 0.25, "sym", cached_result=cached)
+            return time.perf_counter() - t0
+
+        first = fwd()                                       # untimed warm-up no. 1 (also sizes the run)
+        n_timed = max(3, min(steps, int(budget_s / max(first, 1e-3))))
+        n_warm = max(0, min(warmup - 1, int(0.25 * budget_s / max(first, 1e-3))))
+        for _ in range(n_warm):
             fwd()
-        times = [fwd() for _ in range(steps)]
+        times = [fwd() for _ in range(n_timed)]
     t = sum(times) / len(times)
-    return {"value": ei.size(1) / t, "unit": UNIT, "cores": best, "host_cores": cores, "kind": "port",
-            "thread_trials_s": {str(k): round(v, 3) for k, v in trial.items()},
-            "sample": f"DSBM {n} nodes / {ei.size(1)} edges / {FEAT} feat (1/{scale_div} of the per-GPU "
-                      f"workload, same mean degree), cached operator, {len(times)} timed forwards, "
-                      f"{t:.3f} s each, {best} threads (best of {sorted(trial)})"}, t
+    return {"value": ei.size(1) / t, "unit": UNIT, "cores": best, "host_cores": cores, "cpu_model": _cpu_model(),
+            "kind": "port", "nodes": xr.size(0), "edges": ei.size(1), "timed_forwards": n_timed,
+            "warmup_forwards": n_warm + 1, "s_per_forward": t, "cold_s": build_s + first,
+            "operator_build_s": build_s,
+            "thread_trials_s_on_eighth_size_graph": {str(k): round(v, 3) for k, v in trial.items()},
+            "eighth_size_sample": small,
+            "sample": f"the whole per-GPU workload: DSBM {xr.size(0)} nodes / {ei.size(1)} edges / {FEAT} feat, cached "
+                      f"operator, {n_timed} timed forwards of {t:.2f} s after {n_warm + 1} warm-ups, {best} threads "
+                      f"(best of {sorted(trial)} on a 1/8-size graph); cold call (operator build + first forward) "
+                      f"{build_s + first:.1f} s"}, t, n_timed, n_warm + 1
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    base, t = cpu_reference_run(steps, warmup)
+    base, t, n_timed, n_warm = cpu_reference_run(args.steps, args.warmup)
+    cfg = bench_config(args.gpus)
+    if args.gpus > 1:
+        cfg["reference_ran"] = ("ONE rank's share of the weak-scaled workload (1M nodes / 20M edges): the reference is "
+                                "single-process, its CPU path does not use the other GPUs' hosts, and the "
+                                f"{args.gpus}M-node graph needs ~{27 * args.gpus} GB of edge-level temporaries")
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3,
+        "n_gpus": args.gpus, "steps": n_timed, "warmup": n_warm, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": bench_config(args.gpus),
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,13 +248,66 @@ def bench_config(n_gpus):
                         f"64->64 features, fp32 (BASELINE configs[1] layer shape)",
             "nodes_per_gpu": N_PER_GPU, "edges_per_gpu": E_PER_GPU, "feat": FEAT,
             "parallelism": "single GPU" if n_gpus == 1 else
-                           f"node-range row shards x{n_gpus}; feature shards all-gathered over NVLink (copy-engine pulls "
-                           f"from symmetric peer memory, NCCL send/recv ring as fallback), pipelined with per-shard "
-                           f"column-block aggregation; operator built per rank (row-range build + degree all-gather)",
+                           f"node-range row shards x{n_gpus}; feature shards all-gathered over NVLink by the shard-push "
+                           f"kernel (each rank stores its rows into every peer's receive planes in symmetric memory, "
+                           f"slice by slice with flags), overlapped with the aggregation of the own-column block and "
+                           f"of every landed slice; operator built per rank (row-range build + degree all-gather)",
             "l2": "inputs larger than L2 (x_real+x_imag 512 MB, plan 0.5 GB vs 126 MB L2); no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+
+def parity_check(rank, world, dev, ei_cpu, n_total, x_real, x_imag, outs, conv, row_lo, n_check=2000):
+    """In-line correctness evidence for the line being printed: n_check destination rows of rank 0's
+    outputs against the oracle (port.magnet_norm_rows builds those rows of the operator from the edge
+    list on the CPU, port.magnet_conv_rows runs the reference's op sequence on them).  Collective: every
+    rank contributes its feature shard; only rank 0 computes and returns the dict."""
+    import torch.distributed as dist
+    if world > 1:
+        full = []
+        for x in (x_real, x_imag):
+            buf = torch.empty((n_total, x.size(1)), dtype=x.dtype, device=dev)
+            dist.all_gather_into_tensor(buf, x.contiguous())
+            full.append(buf.cpu() if rank == 0 else None)
+            del buf
+    else:
+        full = [x_real.cpu(), x_imag.cpu()]
+    if rank != 0:
+        return None
+    from oracle import port
+    t0 = time.time()
+    threads = torch.get_num_threads()
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    g = torch.Generator().manual_seed(99)
+    n_local = outs[0].size(0)
+    rows_local = torch.randperm(n_local, generator=g)[:n_check].sort().values
+    rows = rows_local + row_lo
+    with torch.no_grad():
+        cached = port.magnet_norm_rows(rows, ei_cpu, None, n_total, 0.25, "sym", 2.0)
+        ref = port.magnet_conv_rows(rows, full[0], full[1], cached, conv.weight.detach().cpu(),
+                                    conv.bias.detach().cpu())
+    torch.set_num_threads(threads)
+    worst = 0.0
+    for got, want in zip(outs, ref):
+        got = got[rows_local.to(dev)].cpu()
+        worst = max(worst, float((got - want).abs().max() / want.abs().max()))
+    return {"max_rel_err": worst, "rows": int(rows.numel()), "tolerance": 1e-5, "ok": bool(worst <= 1e-5),
+            "against": "oracle/port.py: magnet_norm_rows (operator rows from the edge list) + magnet_conv_rows",
+            "seconds": round(time.time() - t0, 1)}
+
+
+def time_steps(step, steps, warmup, barrier):
+    for _ in range(warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1) / steps
+
 
 def run_gpu_arm(args, rank, world):
     import torch.distributed as dist
@@ -260,6 +352,7 @@ def run_gpu_arm(args, rank, world):
                 return sharded(x_real, x_imag)
         nnz, n_rows = sharded.local_nnz, n_local
         exchange_mode = sharded.agg.mode
+    ei_cpu = ei.cpu() if rank == 0 else None
     if world > 1:
         del ei
     torch.cuda.synchronize()
@@ -298,8 +391,43 @@ def run_gpu_arm(args, rank, world):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_ms.item())
 
+    # ---- in-line parity check of the path that was just timed (rank 0's rows against the oracle)
+    if world > 1:
+        sharded.agg.check()
+    with torch.no_grad():
+        outs = step()
+    parity = parity_check(rank, world, dev, ei_cpu, n_total, x_real, x_imag, outs, conv,
+                          0 if world == 1 else sharded.bounds[rank])
+    del outs
+
     # ---- end-to-end: host (pinned) features in, host (pinned) outputs back, every step
     e2e = None
+    if world > 1:
+        # every rank uploads its shard from pinned host memory, runs the sharded forward and downloads its
+        # rows of the outputs; max over ranks
+        hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
+        ho_r = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
+        ho_i = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
+        dx_r, dx_i = torch.empty_like(x_real), torch.empty_like(x_imag)
+
+        @torch.no_grad()
+        def e2e_step_sharded():
+            dx_r.copy_(hx_r, non_blocking=True)
+            dx_i.copy_(hx_i, non_blocking=True)
+            o_r, o_i = sharded(dx_r, dx_i)
+            ho_r.copy_(o_r, non_blocking=True)
+            ho_i.copy_(o_i, non_blocking=True)
+
+        n_e2e = max(3, min(args.steps, 10))
+        t_e2e = torch.tensor([time_steps(e2e_step_sharded, n_e2e, 2, barrier)], device=dev)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t_e2e.item())
+        e2e = {"value": e_input / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 2 * n_local * FEAT * 4 * world, "d2h_bytes_per_step": 2 * n_local * FEAT * 4 * world,
+               "steps": n_e2e, "note": "per rank: pinned host shard of x_real/x_imag -> H2D -> sharded forward (push "
+                                       "exchange + aggregation + transform) -> D2H of its output rows, every step; "
+                                       "serial on each rank's stream, max over ranks; bytes are summed over ranks"}
+        del hx_r, hx_i, ho_r, ho_i, dx_r, dx_i
     if world == 1:
         hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
         ho_r = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
@@ -430,6 +558,31 @@ def run_gpu_arm(args, rank, world):
         shared = {"ms_per_step": sh_ms, "value": e_input / (sh_ms * 1e-3), "unit": UNIT, "spmm_ms": sh_spmm,
                   "algorithmic_bytes": b_sh, "note": "x_real is x_imag (same tensor object): one gather per entry"}
 
+    # ---- halo path (extra key, never the headline): a graph whose edge list shards naturally -- node ids with
+    # locality (|i - j| <= 50k), the same 1M nodes / 20M edges per rank -- takes the all-to-all of packed halo
+    # rows instead of the all-gather; timed and parity-checked the same way
+    halo = None
+    if world > 1 and not args.no_halo:
+        ei2 = synthetic.locality_edges(n_total, e_total, 50_000, 0.0, seed=1, device=dev)
+        sh2 = pgd.ShardedMagNetConv(conv, n_total, rank, world).build(ei2)
+        e2_input = ei2.size(1)
+        ei2_cpu = ei2.cpu() if rank == 0 else None
+        del ei2
+
+        def halo_step():
+            with torch.no_grad():
+                return sh2(x_real, x_imag)
+
+        t_h = torch.tensor([time_steps(halo_step, args.steps, args.warmup, barrier)], device=dev)
+        dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
+        par2 = parity_check(rank, world, dev, ei2_cpu, n_total, x_real, x_imag, halo_step(), conv, sh2.bounds[rank])
+        halo = {"ms_per_step": float(t_h.item()), "value": e2_input / (float(t_h.item()) * 1e-3), "unit": UNIT,
+                "mode": sh2.agg.mode, "halo_fraction": getattr(sh2.agg, "halo_fraction", None),
+                "halo_rows_received_rank0": sh2.agg.halo.n_recv if sh2.agg.halo else None,
+                "edges_total": e2_input, "parity_check": par2,
+                "graph": "synthetic.locality_edges: |i - j| <= 50k, 1M nodes / 20M edges per rank, unit weights"}
+        del sh2
+
     if rank != 0:
         return
 
@@ -474,24 +627,34 @@ def run_gpu_arm(args, rank, world):
 
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        log("timing the CPU baseline (oracle port) on the host cores ...")
-        cpu_base, _ = cpu_reference_run(2, 1)
+        log("timing the CPU baseline (oracle port, whole 1M/20M graph) on the host cores ...")
+        cpu_base = cpu_reference_run(3, 1, budget_s=45.0)[0]
 
     line = {
         "metric": METRIC, "value": e_input / (ms_per_step * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": bench_config(world),
-        "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "parity_check": parity, "gpu_launches": launches,
         "clocks": clocks, "edges_total": e_input, "nnz_per_rank": nnz,
         "cold_ms_per_step": cold_ms,   # cached=False: plan build + forward (reference: ~48 s on CPU)
         "uncached_same_tensors_ms_per_step": uncached_same_tensors_ms,   # cached=False, identical edge tensors again
         "shared_input": shared,
     }
     if world > 1:
-        pull = sharded.agg._pull[1] if sharded.agg._pull else None
-        line["exchange"] = {"mode": exchange_mode, "transport": "symmetric-memory copy-engine pull" if pull is not None
-                            else "nccl send/recv ring", "halo_fraction": getattr(sharded.agg, "halo_fraction", None)}
+        agg = sharded.agg
+        push = agg._push[1] if agg._push else None
+        pull = agg._pull[1] if agg._pull else None
+        if push is not None:
+            transport = {"name": "shard-push kernel over symmetric peer memory (pgsd_shard_push)",
+                         "engine": "bulk-copy (TMA)" if push.engine == 1 else "LSU", "ctas": push.n_ctas,
+                         "slices": [round(c, 3) for c in agg.stage_cum], "multicast": bool(push.mc_ptr),
+                         "nvlink_bytes_in_per_rank": (world - 1) * n_local * FEAT * 4 * 2}
+        else:
+            transport = "symmetric-memory copy-engine pull" if pull is not None else "nccl send/recv ring"
+        line["exchange"] = {"mode": exchange_mode, "transport": transport,
+                            "halo_fraction": getattr(agg, "halo_fraction", None)}
+        line["halo_path"] = halo
     if shared:
         shared["frac"] = shared["algorithmic_bytes"] / (shared["ms_per_step"] * 1e-3) / 1e9 / peak
     emit_json(line)
@@ -504,6 +667,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-halo", action="store_true", help="N > 1: skip the extra halo-path measurement")
     args = ap.parse_args()
     protect_stdout()
     args.warmup = max(args.warmup, 3)
@@ -518,7 +682,8 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", "29511",
                    os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-                   "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+                   "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else []) \
+                  + (["--no-halo"] if args.no_halo else [])
             sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     run_gpu_arm(args, rank, world)

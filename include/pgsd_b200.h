@@ -212,7 +212,8 @@ typedef struct pgsd_spmm_args {
   int32_t n_long_rows;
   int32_t long_row_threshold;
   int32_t long_chunk;
-  int32_t reserved;
+  int32_t grid_reserve;      /* resident-CTA slots to leave free for a kernel running beside this
+                                one (the shard-push collective of the row-sharded path); 0 = none */
 } pgsd_spmm_args;
 
 PGSD_API int pgsd_spmm_csr(const pgsd_spmm_args* args, pgsd_stream_t stream);
@@ -405,6 +406,61 @@ PGSD_API int pgsd_ppr_stationary(const int32_t* row_ptr_dst, const int32_t* col_
 PGSD_API int pgsd_gather_rows(const void* x, int64_t ldx, const int32_t* index, int64_t n_index,
                      int32_t feat, int32_t dtype, void* out, int64_t ldo,
                      pgsd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Shard push: the all-gather of the node-range sharded path as ONE kernel over
+ * NVLink peer memory -- no reference counterpart (the reference is single-device).
+ * Rank `rank` owns `n_rows` feature rows of 1 or 2 matrices (x_real, x_imag).  Every 16-byte
+ * piece is read ONCE from local HBM and stored to every peer's receive buffer (peer-mapped
+ * addresses, e.g. torch symmetric memory) straight from registers, so sending costs one read
+ * of the shard instead of world-1.  The rows travel in `n_slices` row slices (slice s = rows
+ * [slice_row[s], slice_row[s+1])); when a slice is complete on all peers (per-CTA
+ * fence.sys, device-scope arrival counter, last CTA), the word flag[p][s] on peer p is set to
+ * `seq` with a system-scope release store.  The consumer orders its reads behind the flags with
+ * pgsd_wait_flags on its own stream (a kernel boundary then separates the wait from the
+ * non-coherent gathers of the aggregation).  `seq` must grow from call to call (wrap-around safe
+ * comparison); `counters` is n_slices zeroed words of LOCAL scratch that the kernel leaves zeroed.
+ * mc_dst != NULL: one multimem.st per piece to an NVSwitch multicast address instead of world-1
+ * unicast stores (the switch replicates to every rank, including the sender).
+ * The kernel is meant to run beside the aggregation on its own high-priority stream:
+ * it occupies n_ctas resident-CTA slots for the whole exchange, which the aggregation launches
+ * leave free through pgsd_spmm_args.grid_reserve.
+ * ---------------------------------------------------------------------------------- */
+#define PGSD_MAX_RANKS 16
+#define PGSD_MAX_SLICES 16
+typedef struct pgsd_push_args {
+  int32_t world, rank;
+  int32_t n_tensors;                 /* 1 or 2                                                   */
+  int32_t row_bytes;                 /* bytes of one feature row, multiple of 16                 */
+  int64_t n_rows;                    /* rows of the local shard                                  */
+  const void* src[2];                /* local rows, 16-byte aligned                              */
+  int64_t ld_src_bytes[2];
+  void* dst[2][PGSD_MAX_RANKS];      /* dst[t][p]: where row 0 of THIS rank's shard lands on rank p */
+  int64_t ld_dst_bytes[2];
+  void* mc_dst[2];                   /* multicast alias of dst (same offset on every rank) or NULL */
+  int32_t n_slices;
+  int32_t n_ctas;                    /* grid size (0 = 16)                                       */
+  int64_t slice_row[PGSD_MAX_SLICES + 1];
+  uint32_t* flag[PGSD_MAX_RANKS];    /* flag[p][s] on rank p for source = this rank              */
+  uint32_t* counters;                /* [n_slices] local scratch, zero on entry and on exit      */
+  uint32_t seq;
+  int32_t include_self;              /* 1: also store to dst[t][rank] and set flag[rank]          */
+  int32_t engine;                    /* 0: LSU kernel (any row stride, multicast); 1: bulk-copy (TMA) kernel --
+                                        cp.async.bulk global->shared->peer, contiguous rows only, else falls
+                                        back to 0                                                   */
+  int32_t chunk_bytes, stages;       /* engine 1: tile size (0 = 16384) and ring depth (0 = 4)    */
+  int32_t reserved;
+} pgsd_push_args;
+
+PGSD_API size_t pgsd_sizeof_push_args(void);
+PGSD_API int pgsd_shard_push(const pgsd_push_args* args, pgsd_stream_t stream);
+
+/* Stream-ordered wait: returns (on the stream) once flags[index_host[i]] has reached `seq` for all
+ * i < n (n <= 64), polling with ld.acquire.sys.  After timeout_ns the kernel gives up, writes 1 to
+ * *status (device int32, may be NULL) and lets the stream continue -- the caller checks status at
+ * the end of the step instead of hanging the GPU. */
+PGSD_API int pgsd_wait_flags(const uint32_t* flags, const int32_t* index_host, int32_t n, uint32_t seq,
+                             uint64_t timeout_ns, int32_t* status, pgsd_stream_t stream);
 
 /* Signed-triangle motif counts (SDGNN / SiGAT preprocessing; replaces the Python set loops of
  * nn/signed/SDGNN.py:153-254 get_features()/build_adj_lists() and nn/signed/SiGAT.py:93-186).

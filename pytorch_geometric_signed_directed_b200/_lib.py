@@ -31,7 +31,7 @@ class SpmmArgs(C.Structure):
         ("bias", _vp), ("variant", _i32), ("diag_row_offset", _i32),
         ("op_scale", _f32 * 2),
         ("long_rows", _vp), ("long_chunk_ptr", _vp), ("n_long_rows", _i32),
-        ("long_row_threshold", _i32), ("long_chunk", _i32), ("reserved", _i32),
+        ("long_row_threshold", _i32), ("long_chunk", _i32), ("grid_reserve", _i32),
     ]
 
 
@@ -56,6 +56,20 @@ class MagnetFusedArgs(C.Structure):
         ("w", _vp * 2), ("ldw_k", _i64 * 2), ("ldw_n", _i64 * 2),
         ("bias", _vp), ("y", _vp * 2), ("ldy", _i64 * 2),
         ("relu_mode", _i32), ("variant", _i32),
+    ]
+
+
+MAX_RANKS, MAX_SLICES = 16, 16
+
+
+class PushArgs(C.Structure):
+    _fields_ = [
+        ("world", _i32), ("rank", _i32), ("n_tensors", _i32), ("row_bytes", _i32), ("n_rows", _i64),
+        ("src", _vp * 2), ("ld_src_bytes", _i64 * 2),
+        ("dst", (_vp * MAX_RANKS) * 2), ("ld_dst_bytes", _i64 * 2), ("mc_dst", _vp * 2),
+        ("n_slices", _i32), ("n_ctas", _i32), ("slice_row", _i64 * (MAX_SLICES + 1)),
+        ("flag", _vp * MAX_RANKS), ("counters", _vp), ("seq", C.c_uint32), ("include_self", _i32),
+        ("engine", _i32), ("chunk_bytes", _i32), ("stages", _i32), ("reserved", _i32),
     ]
 
 
@@ -105,6 +119,9 @@ _PROTOTYPES = {
     "pgsd_gram_expand": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pgsd_ppr_stationary": (C.c_int, [_vp, _vp, _vp, _i64, C.c_double, _i32, _vp, _vp, _vp]),
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "pgsd_sizeof_push_args": (C.c_size_t, []),
+    "pgsd_shard_push": (C.c_int, [C.POINTER(PushArgs), _vp]),
+    "pgsd_wait_flags": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.c_uint32, C.c_uint64, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
@@ -136,6 +153,8 @@ def load() -> C.CDLL:
             raise PgsdError("ctypes struct mirror out of sync with include/pgsd_b200.h; rebuild")
         if lib.pgsd_sizeof_magnet_fused_args() != C.sizeof(MagnetFusedArgs):
             raise PgsdError("ctypes mirror of pgsd_magnet_fused_args out of sync with include/pgsd_b200.h; rebuild")
+        if lib.pgsd_sizeof_push_args() != C.sizeof(PushArgs):
+            raise PgsdError("ctypes mirror of pgsd_push_args out of sync with include/pgsd_b200.h; rebuild")
         _lib = lib
     return _lib
 

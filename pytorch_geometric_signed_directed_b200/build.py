@@ -22,7 +22,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libpgsd_b200.so")
 STAMP = os.path.join(OUT_DIR, "libpgsd_b200.sha256")
 
-SOURCES = ["spmm.cu", "plan_build.cu", "dense.cu", "dense_tc.cu", "dense_tma.cu", "magnet_fused.cu", "attention.cu", "grad.cu", "preprocess.cu", "motif.cu"]
+SOURCES = ["spmm.cu", "plan_build.cu", "dense.cu", "dense_tc.cu", "dense_tma.cu", "magnet_fused.cu", "attention.cu", "grad.cu", "preprocess.cu", "motif.cu", "exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -45,6 +45,7 @@ struct SpmmParams {
   int long_thr;        // rows longer than this are aggregated by spmm_long_rows_kernel (0 = off)
   int keep_policy;     // L2 policy of the feature gathers: 0 evict_last (default), 1 normal, 2 evict_first
   int shared_x;        // n_ops == 2 and both operators read the same matrix: gather once
+  int grid_reserve;    // resident-CTA slots left free for a collective kernel running beside this launch
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -556,7 +557,7 @@ static int launch_groups(const SpmmParams& p, cudaStream_t st) {
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
   if (occ < 1) occ = 1;
   int64_t need = ceil_div<int64_t>(p.n_rows, (THREADS / 32) * G);
-  int64_t grid = int64_t(sm_count()) * occ;
+  int64_t grid = int64_t(sm_count()) * occ - p.grid_reserve;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   kern<<<dim3((unsigned)grid), dim3(THREADS), 0, st>>>(p);
@@ -575,7 +576,7 @@ static int launch_rows(const SpmmParams& p, cudaStream_t st) {
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
   if (occ < 1) occ = 1;
   int64_t need = ceil_div<int64_t>(p.n_rows, THREADS / 32);
-  int64_t grid = int64_t(sm_count()) * occ;
+  int64_t grid = int64_t(sm_count()) * occ - p.grid_reserve;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   kern<<<dim3((unsigned)grid), dim3(THREADS), 0, st>>>(p);
@@ -673,6 +674,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   p.beta = a->beta;
   p.bias = a->bias;
   p.diag_row_offset = a->diag_row_offset;
+  p.grid_reserve = a->grid_reserve > 0 ? a->grid_reserve : 0;
   for (int k = 0; k < 2; ++k) p.alpha_op[k] = a->alpha * (a->op_scale[k] == 0.f ? 1.f : a->op_scale[k]);
   bool vec16 = (int64_t(a->feat) * es) % 16 == 0;
   bool vec32 = (int64_t(a->feat) * es) % 32 == 0;

@@ -98,6 +98,90 @@ def split_columns_by_owner(local: CSRPlan, bounds: Sequence[int], own_rank: int)
     return blocks
 
 
+def stage_fractions(spec=None, world: int = 2) -> List[float]:
+    """Cumulative row fractions of the slices a shard travels in (push exchange).  `spec` / PGSD_PUSH_SLICES is
+    a count (equal slices) or a comma list of weights.  Default: a small model of the step -- the own-column
+    block takes t_agg / world, the exchange (world-1) shard times, every extra launch re-reads the outputs:
+      * exchange-bound (8 ranks): the aggregation always waits for rows, so the slices only have to keep the
+        LAST block (aggregated after the whole exchange) small: six slices shrinking towards the end;
+      * aggregation-bound (2-4 ranks): as few launches as possible -- each slice ends where the exchange will
+        be when the previous block finishes (2 ranks: one slice, the whole peer shard is there in time)."""
+    if spec is None:
+        spec = os.environ.get("PGSD_PUSH_SLICES", "")
+    spec = str(spec)
+    if spec and spec != "auto":
+        w = [float(t) for t in spec.split(",") if t.strip()] if "," in spec else [1.0] * max(1, int(spec))
+        tot, acc, cum = sum(w), 0.0, [0.0]
+        for v in w:
+            acc += v
+            cum.append(acc / tot)
+        cum[-1] = 1.0
+        return cum
+    t_agg, t_shard, t_launch, k_max = 3.0, 0.75, 0.15, 6           # ms, north-star shapes on B200 / NVLink 5
+    t_x, t_rem, t = (world - 1) * t_shard, t_agg * (world - 1) / world, t_agg / world
+    if t_x >= 1.3 * (t_rem + k_max * t_launch):
+        w = [0.22, 0.20, 0.18, 0.16, 0.14, 0.10]
+        return stage_fractions(",".join(str(v) for v in w))
+    cum = [0.0]
+    while cum[-1] < 1.0:
+        f = 1.0 if len(cum) == k_max else min(1.0, max(t / t_x, cum[-1] + 0.05))
+        if 1.0 - f < 0.08:
+            f = 1.0
+        t = max(t, f * t_x) + (f - cum[-1]) * t_rem + t_launch
+        cum.append(f)
+    return cum
+
+
+def slice_rows(n_rows: int, cum: Sequence[float]) -> List[int]:
+    """Row boundaries of the slices of an n_rows shard (same formula on the sender and on every receiver)."""
+    out = [min(n_rows, int(round(c * n_rows))) for c in cum]
+    out[0], out[-1] = 0, n_rows
+    for i in range(1, len(out)):
+        out[i] = max(out[i], out[i - 1])
+    return out
+
+
+def split_columns_by_stage(local: CSRPlan, bounds: Sequence[int], own_rank: int, cum: Sequence[float]) -> List[CSRPlan]:
+    """Blocks of the push exchange: block 0 = entries whose column this rank owns (columns re-based to the shard,
+    carries the diagonal); block s >= 1 = entries whose column lies in slice s-1 of ANY peer's shard, columns kept
+    GLOBAL (they index the [n_total, F] receive planes).  Entry order inside a row is preserved."""
+    dev = local.row_ptr.device
+    n_rows, world = local.n_dst, len(bounds) - 1
+    n_stage = len(cum) - 1
+    counts = (local.row_ptr[1:] - local.row_ptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), counts)
+    col = local.col.long()
+    b_t = torch.tensor(list(bounds), device=dev, dtype=torch.long)
+    owner = torch.bucketize(col, b_t[1:], right=True)
+    # per-owner slice boundaries in GLOBAL row numbers: [world, n_stage + 1]
+    cuts = torch.tensor([[bounds[b] + r for r in slice_rows(bounds[b + 1] - bounds[b], cum)] for b in range(world)],
+                        device=dev, dtype=torch.long)
+    stage = torch.ones_like(col)
+    for k in range(1, n_stage):                      # stage = 1 + number of interior cuts at or below col
+        stage += (col >= cuts[owner, k]).long()
+    stage[owner == own_rank] = 0
+    order = torch.sort(stage * n_rows + rows, stable=True).indices
+    stage_s, rows_s, col_s = stage[order], rows[order], col[order]
+    per_stage = torch.bincount(stage_s, minlength=n_stage + 1).tolist()
+    blocks, start = [], 0
+    lo = bounds[own_rank]
+    for k in range(n_stage + 1):
+        m = per_stage[k]
+        sl = slice(start, start + m)
+        rp = torch.zeros(n_rows + 1, dtype=torch.int32, device=dev)
+        if m:
+            rp[1:] = torch.cumsum(torch.bincount(rows_s[sl], minlength=n_rows), 0).int()
+        vals = [None if v is None else v[order[sl]].contiguous() for v in local.val]
+        own = k == 0
+        diags = [d if own else None for d in local.diag]
+        dconst = [c if own else 0.0 for c in local.diag_const]
+        cols = (col_s[sl] - lo) if own else col_s[sl]
+        blocks.append(CSRPlan(n_rows, (bounds[own_rank + 1] - lo) if own else bounds[-1], m, local.num_input_edges,
+                              rp, cols.int().contiguous(), vals, diags, dconst))
+        start += m
+    return blocks
+
+
 def split_local_and_halo(local: CSRPlan, bounds: Sequence[int], own_rank: int):
     """(own_block, halo_block, need): own_block keeps the entries whose column this rank owns
     (columns re-based to the shard, carries the diagonal); halo_block keeps the others with the
@@ -258,6 +342,90 @@ class SymmetricPullExchange:
         return works
 
 
+class PushExchange:
+    """All-gather by `pgsd_shard_push` (csrc/exchange.cu): every rank stores its rows straight into the peers'
+    [n_total, F] receive planes (symmetric memory, peer-mapped over NVSwitch), one read of the shard for all
+    peers, in row slices published by per-slice flags.  Receive planes and flags are double-buffered by step
+    parity: a peer can be at most one step ahead (it cannot finish step t+1 without this rank's step-t+1 rows,
+    which are pushed only after this rank's step-t kernels), so no per-step barrier is needed."""
+
+    def __init__(self, rank: int, world: int, bounds: Sequence[int], n_planes: int, feat: int, dtype, device,
+                 cum: Sequence[float], group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world, self.bounds = rank, world, list(bounds)
+        self.n_planes, self.feat, self.dtype = n_planes, feat, dtype
+        grp = group if group is not None else dist.group.WORLD
+        n_total = self.bounds[-1]
+        self.row_bytes = feat * torch.empty((), dtype=dtype).element_size()
+        self.plane_bytes = n_total * self.row_bytes
+        self.parity_bytes = n_planes * self.plane_bytes
+        self.buf = symm_mem.empty((2 * n_planes * n_total, feat), dtype=dtype, device=device)
+        self.flags = symm_mem.empty((2 * _MAX_RANKS * _MAX_SLICES,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
+        self.fhdl = symm_mem.rendezvous(self.flags, grp)
+        dist.barrier(group=group)                      # every rank's flags are zero before anyone pushes
+        o_b, o_f = int(getattr(self.hdl, "offset", 0) or 0), int(getattr(self.fhdl, "offset", 0) or 0)
+        self.buf_ptrs = [int(p) + o_b for p in self.hdl.buffer_ptrs]
+        self.flag_ptrs = [int(p) + o_f for p in self.fhdl.buffer_ptrs]
+        if self.buf_ptrs[rank] != self.buf.data_ptr() or self.flag_ptrs[rank] != self.flags.data_ptr():
+            raise RuntimeError("symmetric-memory handle does not describe the tensor it was created from")
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        mc = mc + o_b if mc else 0
+        self.mc_ptr = mc if (mc and os.environ.get("PGSD_PUSH_MC", "0") == "1") else 0
+        self.counters = torch.zeros(_MAX_SLICES, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.slices = slice_rows(self.bounds[rank + 1] - self.bounds[rank], cum)
+        self.n_slices = len(self.slices) - 1
+        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "16"))
+        # engine 1 = bulk-copy (TMA) kernel, 0 = LSU kernel; PGSD_PUSH_TILE = "<chunk bytes>x<stages>"
+        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "1"))
+        tile = os.environ.get("PGSD_PUSH_TILE", "16384x4").split("x")
+        self.chunk_bytes, self.stages = int(tile[0]), int(tile[1])
+        prio = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
+        self.stream = torch.cuda.Stream(device=device, priority=prio)
+        self.seq = 0
+        self.done = torch.cuda.Event()
+        self.planes = [[self.buf[(par * n_planes + t) * n_total:(par * n_planes + t + 1) * n_total]
+                        for t in range(n_planes)] for par in range(2)]
+
+    def push(self, xs: Sequence[Tensor]) -> int:
+        """Starts the push of this step's rows on the exchange stream (ordered behind the current stream, where
+        xs were produced); returns the step's sequence number."""
+        self.seq += 1
+        par, lo = self.seq & 1, self.bounds[self.rank]
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        off = lambda t: par * self.parity_bytes + t * self.plane_bytes + lo * self.row_bytes
+        dst = [[self.buf_ptrs[p] + off(t) for p in range(self.world)] for t in range(self.n_planes)]
+        fl = [self.flag_ptrs[p] + 4 * ((par * _MAX_RANKS + self.rank) * _MAX_SLICES) for p in range(self.world)]
+        mc = [self.mc_ptr + off(t) for t in range(self.n_planes)] if self.mc_ptr else None
+        ops.shard_push(list(xs), dst, self.row_bytes, self.rank, self.world, self.slices, fl, self.counters,
+                       self.seq, n_ctas=self.n_ctas, mc_ptrs=mc, include_self=bool(mc), stream=self.stream,
+                       engine=self.engine, chunk_bytes=self.chunk_bytes, stages=self.stages)
+        self.done.record(self.stream)
+        return self.seq
+
+    def wait_slice(self, s: int, seq: int) -> None:
+        """The current stream waits until slice s of every peer's shard of step `seq` has landed here."""
+        par = seq & 1
+        idx = [(par * _MAX_RANKS + b) * _MAX_SLICES + s for b in range(self.world) if b != self.rank]
+        ops.wait_flags(self.flags, idx, seq, self.status, float(os.environ.get("PGSD_WAIT_TIMEOUT_S", "5")))
+
+    def finish(self) -> None:
+        """The current stream waits for this rank's own push (the source rows may then be reused)."""
+        torch.cuda.current_stream().wait_event(self.done)
+
+    def check(self) -> None:
+        if int(self.status.item()) != 0:
+            raise RuntimeError("push exchange: a slice did not arrive within the time-out (peer died or "
+                               "the ranks disagree on the number of steps)")
+
+
+_MAX_RANKS, _MAX_SLICES = 16, 16
+
+
 def _distinct_operands(xs: Sequence[Tensor]) -> int:
     """1 when both operators read ONE tensor (x_real is x_imag, how the reference's example calls the first layer of
     every MagNet model): the shard then travels once, and the block launches see the same pointer twice, which the
@@ -308,7 +476,18 @@ class ShardedAggregator:
         self.local_plan = CSRPlan(local_plan.n_dst, local_plan.n_src, local_plan.nnz, local_plan.num_input_edges,
                                   local_plan.row_ptr, local_plan.col, local_plan.val, local_plan.diag,
                                   local_plan.diag_const, {**local_plan.meta, "diag_row_offset": self.bounds[rank]})
-        self.blocks = split_columns_by_owner(local_plan, bounds, rank) if self.mode == "ring" else None
+        # ring mode on CUDA with an NCCL group: the push exchange (one kernel over peer memory, stage blocks);
+        # otherwise (gloo CPU tests, PGSD_EXCHANGE=pull|nccl) per-owner blocks + copy-engine pulls / send-recv
+        self.transport = os.environ.get("PGSD_EXCHANGE", "push")
+        self.use_push = (self.mode == "ring" and world > 1 and world <= _MAX_RANKS and local_plan.row_ptr.is_cuda
+                         and self.transport == "push" and aggregate_fn is _default_aggregate)
+        self.stage_cum = stage_fractions(world=world) if self.use_push else None
+        self.stage_blocks = (split_columns_by_stage(local_plan, bounds, rank, self.stage_cum)
+                             if self.use_push else None)
+        self._push_cache = {}
+        self._push = None
+        self.blocks = (split_columns_by_owner(local_plan, bounds, rank)
+                       if self.mode == "ring" and not self.use_push else None)
         self.n_local = local_plan.n_dst
         self.n_ops = len(local_plan.val)
         self.ring = RingExchange(rank, world, group)
@@ -357,8 +536,12 @@ class ShardedAggregator:
             return self._gather_then_single(xs, op_ids, f, alpha, beta, zs)
         if self.mode == "halo":
             return self._halo_step(xs, op_ids, f, alpha, beta, zs)
-        # interleave the DISTINCT operands: one [n_local, n_cols*F] send buffer
         n_cols = _distinct_operands(xs)
+        if self.use_push:
+            ex = self._push_exchange(xs[0], n_cols, f)
+            if ex is not None:
+                return self._push_step(ex, xs, op_ids, n_cols, alpha, beta, zs)
+        # interleave the DISTINCT operands: one [n_local, n_cols*F] send buffer
         pull = self._pull_exchange(xs[0], n_cols * f)
         views = lambda buf: [buf[:, (k % n_cols) * f:(k % n_cols + 1) * f] for k in range(n_ops)]
         trace = TRACE is not None and xs[0].is_cuda
@@ -393,6 +576,67 @@ class ShardedAggregator:
             y = self.aggregate_fn(self.blocks[src], views(recv[src]), op_ids, alpha, 1.0, y, y)
             mark(f"block{src} done")
         return y
+
+
+def _push_exchange(self, like: Tensor, n_cols: int, f: int):
+    key = (like.dtype, n_cols, f)
+    if key not in self._push_cache:
+        ex = None
+        if (f * like.element_size()) % 16 == 0:
+            try:
+                ex = PushExchange(self.rank, self.world, self.bounds, n_cols, f, like.dtype, like.device,
+                                  self.stage_cum, self.ring.group)
+            except Exception as exc:                      # noqa: BLE001 - fall back, but say so
+                if self.rank == 0:
+                    print(f"[pgsd] push exchange unavailable ({type(exc).__name__}: {exc}); "
+                          "using copy-engine pulls / NCCL", file=sys.stderr, flush=True)
+        if ex is None and self.blocks is None:
+            self.blocks = split_columns_by_owner(self.local_plan, self.bounds, self.rank)
+        self._push_cache[key] = ex
+    self._push = (key, self._push_cache[key])
+    return self._push[1]
+
+
+def _push_step(self, ex, xs, op_ids, n_cols, alpha, beta, zs):
+    """push (exchange stream) | own block -> for every slice: wait its flags -> stage block (+=)."""
+    n_ops = len(xs)
+    trace = TRACE is not None
+    mark = (lambda name: TRACE.append((name, _now_event()))) if trace else (lambda name: None)
+    mark("start")
+    srcs = [xs[k] for k in range(n_cols)]
+    for k in range(n_cols):
+        x = srcs[k]
+        if x.stride(1) != 1 or x.data_ptr() % 16 or (x.stride(0) * x.element_size()) % 16:
+            srcs[k] = x.contiguous()
+    seq = ex.push(srcs)
+    reserve = ex.n_ctas
+    own = [srcs[k % n_cols] for k in range(n_ops)]
+    y = ops.spmm(self.stage_blocks[0], own, op_ids, alpha=alpha, beta=beta, zs=zs, grid_reserve=reserve)
+    mark("own block done")
+    planes = ex.planes[seq & 1]
+    views = [planes[k % n_cols] for k in range(n_ops)]
+    for s in range(ex.n_slices):
+        ex.wait_slice(s, seq)
+        mark(f"slice{s} landed")
+        blk = self.stage_blocks[s + 1]
+        if blk.nnz == 0:
+            continue
+        y = ops.spmm(blk, views, op_ids, alpha=alpha, beta=1.0, zs=y, out=y, grid_reserve=reserve)
+        mark(f"stage{s + 1} done")
+    ex.finish()
+    return y
+
+
+def _check(self):
+    """Raises if a flag wait of the push exchange timed out (one device->host sync; call outside timed loops)."""
+    for ex in self._push_cache.values():
+        if ex is not None:
+            ex.check()
+
+
+ShardedAggregator.check = _check
+ShardedAggregator._push_exchange = _push_exchange
+ShardedAggregator._push_step = _push_step
 
 
 def _gather_then_single(self, xs, op_ids, f, alpha, beta, zs):

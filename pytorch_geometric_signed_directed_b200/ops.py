@@ -74,10 +74,12 @@ def _rows2d(t: Tensor, name: str) -> Tensor:
 def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean: bool = False,
          alpha: float = 1.0, beta: float = 0.0, zs: Optional[Sequence[Tensor]] = None,
          bias: Optional[Tensor] = None, out: Optional[Sequence[Tensor]] = None,
-         variant: Optional[int] = None, op_scale: Optional[Sequence[float]] = None) -> List[Tensor]:
+         variant: Optional[int] = None, op_scale: Optional[Sequence[float]] = None,
+         grid_reserve: int = 0) -> List[Tensor]:
     """y_k = alpha * (diag_k x_k[r] + sum val_k x_k[col]) (/len if mean) + beta * z_k + bias
     for the plan operators listed in `ops` (1 or 2 of them), one kernel launch.
-    xs/zs/out may be column slices of wider row-major buffers."""
+    xs/zs/out may be column slices of wider row-major buffers.  grid_reserve = resident-CTA slots
+    left free for a collective kernel running beside this launch (`shard_push`)."""
     global LAUNCHES
     n_ops = len(ops)
     assert n_ops in (1, 2) and len(xs) == n_ops
@@ -90,6 +92,7 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
     a.alpha, a.beta = float(alpha), float(beta)
     a.variant = SPMM_VARIANT if variant is None else variant
     a.diag_row_offset = int(plan.meta.get("diag_row_offset", 0))
+    a.grid_reserve = int(grid_reserve)
     if op_scale is not None:
         for k, sc in enumerate(op_scale):
             a.op_scale[k] = float(sc)
@@ -207,6 +210,63 @@ def gather_rows(x: Tensor, index: Tensor, out: Optional[Tensor] = None) -> Tenso
                    "pgsd_gather_rows")
     LAUNCHES += 1
     return out
+
+
+def shard_push(srcs: Sequence[Tensor], dst_ptrs: Sequence[Sequence[int]], ld_dst_bytes: int, rank: int, world: int,
+               slice_row: Sequence[int], flag_ptrs: Sequence[int], counters: Tensor, seq: int, *,
+               n_ctas: int = 16, mc_ptrs: Optional[Sequence[int]] = None, include_self: bool = False,
+               stream: Optional[torch.cuda.Stream] = None, engine: int = 0, chunk_bytes: int = 0,
+               stages: int = 0) -> None:
+    """All-gather push over NVLink peer memory (`pgsd_shard_push`): every 16-byte piece of the local rows
+    `srcs[t]` is read once and stored to dst_ptrs[t][p] (+ row * ld_dst_bytes) on every peer p; slice s =
+    rows [slice_row[s], slice_row[s+1]) is published by writing `seq` to flag_ptrs[p][s] on every peer."""
+    global LAUNCHES
+    srcs = [_rows2d(x.detach(), "src") for x in srcs]
+    dev = srcs[0].device
+    a = _lib.PushArgs()
+    a.world, a.rank, a.n_tensors = world, rank, len(srcs)
+    a.row_bytes = srcs[0].size(1) * srcs[0].element_size()
+    a.n_rows = srcs[0].size(0)
+    for t, x in enumerate(srcs):
+        if x.shape != srcs[0].shape or x.dtype != srcs[0].dtype:
+            raise ValueError("shard_push: tensors must share shape and dtype")
+        a.src[t], a.ld_src_bytes[t] = x.data_ptr(), x.stride(0) * x.element_size()
+        a.ld_dst_bytes[t] = int(ld_dst_bytes)
+        for p_ in range(world):
+            a.dst[t][p_] = dst_ptrs[t][p_] or None
+        if mc_ptrs is not None:
+            a.mc_dst[t] = mc_ptrs[t]
+    a.n_slices, a.n_ctas = len(slice_row) - 1, int(n_ctas)
+    if a.n_slices > _lib.MAX_SLICES:
+        raise ValueError(f"shard_push: at most {_lib.MAX_SLICES} slices")
+    for s_, r in enumerate(slice_row):
+        a.slice_row[s_] = int(r)
+    for p_ in range(world):
+        a.flag[p_] = flag_ptrs[p_] or None
+    a.counters, a.seq, a.include_self = counters.data_ptr(), seq & 0xffffffff, int(include_self)
+    a.engine, a.chunk_bytes, a.stages = int(engine), int(chunk_bytes), int(stages)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.pgsd_shard_push(C.byref(a), st.cuda_stream), "pgsd_shard_push")
+    LAUNCHES += 1
+
+
+def wait_flags(flags: Tensor, index: Sequence[int], seq: int, status: Optional[Tensor] = None,
+               timeout_s: float = 5.0) -> None:
+    """The current stream waits until flags[i] >= seq for every i in `index` (`pgsd_wait_flags`); after
+    timeout_s the wait gives up and sets status[0] = 1 instead of hanging the GPU."""
+    global LAUNCHES
+    if not index:
+        return
+    dev = flags.device
+    arr = (C.c_int32 * len(index))(*[int(i) for i in index])
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.pgsd_wait_flags(flags.data_ptr(), arr, len(index), seq & 0xffffffff, int(timeout_s * 1e9),
+                                       None if status is None else status.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream), "pgsd_wait_flags")
+    LAUNCHES += 1
 
 
 def edge_softmax(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Sequence[Tensor], *,

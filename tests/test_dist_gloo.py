@@ -229,3 +229,41 @@ def test_locality_graph_generator_properties():
     src = ei[0][rows]
     remote = src[(src < lo) | (src >= hi)]
     assert remote.unique().numel() <= 2 * band
+
+
+def test_stage_split_covers_the_shard_and_matches_the_slices():
+    """Push exchange, host side: the stage blocks partition a row shard's entries (block 0 = own columns,
+    block s = columns in slice s-1 of any peer's shard, GLOBAL numbering), slices use one formula on sender
+    and receiver, and block-wise accumulation reproduces the unsharded aggregation."""
+    n, e, f, world = 1003, 9000, 8, 3
+    g = torch.Generator().manual_seed(5)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    xr = torch.rand(n, f, generator=g) * 2 - 1
+    xi = torch.rand(n, f, generator=g) * 2 - 1
+    full = _plan_from_oracle(ei, n)
+    bounds = pgd.node_bounds(n, world)
+    ref = _torch_aggregate(full, [xr, xi], (0, 1), 1.0, 0.0, None, None)
+    for spec in (None, 1, 3, 5):
+        cum = pgd.stage_fractions(spec)
+        assert cum[0] == 0.0 and cum[-1] == 1.0 and all(b >= a for a, b in zip(cum, cum[1:]))
+        for rank in range(world):
+            lo, hi = bounds[rank], bounds[rank + 1]
+            local = pgd.split_rows(full, lo, hi)
+            blocks = pgd.split_columns_by_stage(local, bounds, rank, cum)
+            assert len(blocks) == len(cum) and sum(b.nnz for b in blocks) == local.nnz
+            assert blocks[0].n_src == hi - lo and all(b.n_src == n for b in blocks[1:])
+            cuts = {b: pgd.slice_rows(bounds[b + 1] - bounds[b], cum) for b in range(world)}
+            for s, blk in enumerate(blocks[1:]):
+                c = blk.col.long()
+                own = (c >= lo) & (c < hi)
+                assert not bool(own.any())
+                for b in range(world):
+                    inb = c[(c >= bounds[b]) & (c < bounds[b + 1])] - bounds[b]
+                    if inb.numel():
+                        assert int(inb.min()) >= cuts[b][s] and int(inb.max()) < cuts[b][s + 1]
+            # own block reads the local rows, the stage blocks the global planes; (+=) over the blocks
+            y = _torch_aggregate(blocks[0], [xr[lo:hi], xi[lo:hi]], (0, 1), 1.0, 0.0, None, None)
+            for blk in blocks[1:]:
+                y = _torch_aggregate(blk, [xr, xi], (0, 1), 1.0, 1.0, y, None)
+            for k in range(2):
+                assert torch.allclose(y[k], ref[k][lo:hi], atol=1e-5)

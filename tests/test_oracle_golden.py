@@ -248,3 +248,37 @@ def test_sdgnn_and_sigat_forward_port():
     z = port.sigat_forward(s["x"], lists, _gat_params(s, "", 38), s["mlp_layer__0__weight"], s["mlp_layer__0__bias"],
                            s["mlp_layer__2__weight"], s["mlp_layer__2__bias"])
     assert_close_rel(z, s["out"], 1e-5)
+
+
+@pytest.mark.parametrize("norm,lam", [("sym", 2.0), (None, 3.7)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_row_restricted_operator_matches_the_full_oracle(norm, lam, weighted):
+    """`port.magnet_norm_rows` (used by the full-size parity checks and bench.py's in-line parity_check) keeps
+    exactly the entries of `port.magnet_norm` whose target is in `rows` -- indices bit-exact and in the same
+    order, values to fp32 rounding (its degree is the same sum in another association)."""
+    g = torch.Generator().manual_seed(11)
+    n, e, f = 700, 6000, 8
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[:, :40] = ei[:, 40:80]                      # duplicates
+    ei[:, 80:120] = ei[:, 120:160].flip(0)         # reciprocal pairs
+    ei[1, 160:170] = ei[0, 160:170]                # self-loops
+    w = torch.rand(e, generator=g) + 0.1 if weighted else None
+    rows = torch.randperm(n, generator=g)[:64]
+    full = port.magnet_norm(ei, w, n, 0.2, norm, lam)
+    sub = port.magnet_norm_rows(rows, ei, w, n, 0.2, norm, lam)
+    nnz = full[1].size(1) - n
+    sel = torch.zeros(n, dtype=torch.bool)
+    sel[rows] = True
+    keep = sel[full[1][1, :nnz]]
+    m = int(keep.sum())
+    assert torch.equal(full[1][:, :nnz][:, keep], sub[1][:, :m])
+    assert torch.equal(sub[1][:, m:], torch.stack([rows, rows]))
+    for k in (2, 3):
+        ref = full[k][:nnz][keep]
+        assert (ref - sub[k][:m]).abs().max() <= 1e-6 * ref.abs().max().clamp(min=1e-30)
+    xr, xi = torch.rand(n, f, generator=g), torch.rand(n, f, generator=g)
+    wt, b = torch.rand(2, f, f, generator=g) - 0.5, torch.rand(f, generator=g)
+    o_full = port.magnet_conv(xr, xi, ei, w, wt, b, 0.2, norm, lam)
+    o_rows = port.magnet_conv_rows(rows, xr, xi, sub, wt, b)
+    for a, r in zip(o_full, o_rows):
+        assert (a[rows] - r).abs().max() <= 2e-6 * a.abs().max()

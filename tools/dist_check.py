@@ -40,6 +40,7 @@ def check(gname, want_mode, ei):
         for it in range(3):                                   # repeated calls reuse the buffers
             out_r, out_i = sh(x_real[lo:hi].contiguous(), x_imag[lo:hi].contiguous())
         torch.cuda.synchronize()
+        sh.agg.check()
         ok &= sh.agg.mode == want_mode
         for got, ref, nm in ((out_r, full_r[lo:hi], "real"), (out_i, full_i[lo:hi], "imag")):
             err = (got - ref).abs().max().item()
