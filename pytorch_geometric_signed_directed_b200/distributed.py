@@ -378,9 +378,9 @@ class PushExchange:
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.slices = slice_rows(self.bounds[rank + 1] - self.bounds[rank], cum)
         self.n_slices = len(self.slices) - 1
-        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "16"))
+        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "32"))
         # engine 1 = bulk-copy (TMA) kernel, 0 = LSU kernel; PGSD_PUSH_TILE = "<chunk bytes>x<stages>"
-        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "1"))
+        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "0"))
         tile = os.environ.get("PGSD_PUSH_TILE", "16384x4").split("x")
         self.chunk_bytes, self.stages = int(tile[0]), int(tile[1])
         prio = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1

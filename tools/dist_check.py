@@ -115,16 +115,22 @@ if "--trace" in sys.argv and flag.item() == 1:
     with torch.no_grad():
         for _ in range(5):
             sh(xr, xi)
-        for rep in range(2):
+        # (a) one step after a barrier + synchronize; (b) the 4th of 6 back-to-back steps (what bench.py times)
+        for mode in ("isolated", "steady"):
             dist.barrier(); torch.cuda.synchronize()
-            pgd.TRACE = []
-            t0 = pgd._now_event()
-            sh(xr, xi)
-            t1 = pgd._now_event()
+            n_run, traced = (1, 0) if mode == "isolated" else (6, 3)
+            for i in range(n_run):
+                if i == traced:
+                    pgd.TRACE = []
+                    t0 = pgd._now_event()
+                sh(xr, xi)
+                if i == traced:
+                    t1 = pgd._now_event()
+                    tr, pgd.TRACE = pgd.TRACE, None
             torch.cuda.synchronize()
-            tr, pgd.TRACE = pgd.TRACE, None
-            if rank in (0, world - 1) and rep == 1:
+            sh.agg.check()
+            if rank in (0, world - 1):
                 line = " | ".join(f"{nm} {t0.elapsed_time(ev):.2f}" for nm, ev in tr)
-                print(f"[rank {rank}] TRACE ms from step start: {line} | step end {t0.elapsed_time(t1):.2f}", flush=True)
+                print(f"[rank {rank}] TRACE {mode} ms from step start: {line} | step end {t0.elapsed_time(t1):.2f}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)

@@ -96,8 +96,7 @@ out({"what": "aggregation alone", "spmm_ms": round(a.elapsed_time(b) / 5, 3)})
 
 # ---- shard-push kernel: (label, engine, multicast, CTAs, tile)
 variants = [("lsu", 0, 0, 16, "16384x4"), ("lsu", 0, 0, 32, "16384x4"), ("lsu", 0, 0, 48, "16384x4"),
-            ("tma", 1, 0, 8, "16384x4"), ("tma", 1, 0, 16, "16384x4"), ("tma", 1, 0, 32, "16384x4"),
-            ("tma", 1, 0, 16, "32768x4"), ("tma", 1, 0, 16, "16384x8"), ("tma", 1, 0, 32, "8192x8"),
+            ("tma", 1, 0, 16, "16384x4"), ("tma", 1, 0, 32, "16384x4"), ("tma", 1, 0, 16, "32768x4"),
             ("lsu-mc", 0, 1, 32, "16384x4")]
 if os.environ.get("PROBE_VARIANTS"):
     keep = set(os.environ["PROBE_VARIANTS"].split(","))
@@ -141,7 +140,7 @@ for mc_name, engine, mc, ctas, tile in variants:
     torch.cuda.empty_cache()
 
 # ---- copy-engine pulls (round-1 transport)
-for streams in (1, 7):
+for streams in (1,):
     os.environ["PGSD_COPY_STREAMS"] = str(streams)
     pe = pgd.SymmetricPullExchange(rank, world, N, 2 * F, torch.float32, dev)
     recv = [None if b == rank else torch.empty((N, 2 * F), device=dev) for b in range(world)]
