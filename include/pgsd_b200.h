@@ -197,7 +197,10 @@ typedef struct pgsd_spmm_args {
   int32_t variant;           /* 0 = library default; bits 0-3 loads in flight (2/4/8), 0x10 /
                                 0x20 prefer 128- / 256-bit gathers, 0x80 warp-per-row kernel
                                 instead of the default group-per-row kernel, 0x400 gather twice
-                                even when both operators read one tensor (A/B timing)        */
+                                even when both operators read one tensor (A/B timing); bits 12-14:
+                                preferred shared-memory carve-out of the launch in steps of 14 % of
+                                the SM's 228 KB (0 = driver default), so that a kernel which needs
+                                shared memory (bulk-copy shard push) can be co-resident            */
   int32_t diag_row_offset;   /* x row holding destination row 0 (diag term only): lets x span a
                                 larger node range than the plan's rows (row-sharded plans)  */
   float op_scale[2];         /* per-operator multiplier of alpha (0 is read as 1): -1 on the
@@ -439,7 +442,7 @@ typedef struct pgsd_push_args {
   int64_t ld_dst_bytes[2];
   void* mc_dst[2];                   /* multicast alias of dst (same offset on every rank) or NULL */
   int32_t n_slices;
-  int32_t n_ctas;                    /* grid size (0 = 16)                                       */
+  int32_t n_ctas;                    /* grid size in 256-thread CTAs (0 = 64); engine 1: 32-thread CTAs */
   int64_t slice_row[PGSD_MAX_SLICES + 1];
   uint32_t* flag[PGSD_MAX_RANKS];    /* flag[p][s] on rank p for source = this rank              */
   uint32_t* counters;                /* [n_slices] local scratch, zero on entry and on exit      */

@@ -55,9 +55,12 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 
-// U pieces in flight per thread; MC = multicast stores.
-template <int U, bool MC>
-__global__ void __launch_bounds__(512) shard_push_kernel(const __grid_constant__ PushParams p) {
+// U pieces in flight per thread; MC = multicast stores; CONTIG = rows are contiguous on both sides (offset = piece
+// index * 16, no row / column split and no per-piece offset registers).  256 threads x <= 80 registers: one CTA
+// fits into the register space ONE aggregation CTA (256 threads x 80 registers) leaves free, which is what
+// pgsd_spmm_args.grid_reserve counts.
+template <int U, bool MC, bool CONTIG>
+__global__ void __launch_bounds__(256) shard_push_kernel(const __grid_constant__ PushParams p) {
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int n_peers = p.include_self ? p.world : p.world - 1;
@@ -71,31 +74,57 @@ __global__ void __launch_bounds__(512) shard_push_kernel(const __grid_constant__
       const int64_t dst_off0 = r0 * p.ld_dst[t];
       for (int64_t i = tid; i < total; i += nthreads * U) {
         float4 v[U];
-        int64_t off[U];
+        if constexpr (CONTIG) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int64_t idx = i + int64_t(u) * nthreads;
-          off[u] = -1;
-          if (idx < total) {
-            int64_t row, c;
-            if (p.cpr_shift >= 0) row = idx >> p.cpr_shift, c = idx & (p.cpr - 1);
-            else row = idx / p.cpr, c = idx - row * p.cpr;
-            v[u] = ld_once_v4(src + row * p.ld_src[t] + c * 16);
-            off[u] = dst_off0 + row * p.ld_dst[t] + c * 16;
+          for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + int64_t(u) * nthreads;
+            if (idx < total) v[u] = ld_once_v4(src + idx * 16);
           }
-        }
-        if constexpr (MC) {
+          if constexpr (MC) {
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (off[u] >= 0) st_multicast_v4(p.mc_dst[t] + off[u], v[u]);
+            for (int u = 0; u < U; ++u) {
+              const int64_t idx = i + int64_t(u) * nthreads;
+              if (idx < total) st_multicast_v4(p.mc_dst[t] + dst_off0 + idx * 16, v[u]);
+            }
+          } else {
+            for (int q = 0; q < n_peers; ++q) {
+              int d = p.rank + first + q;            // staggered: rank r starts with peer r+1
+              if (d >= p.world) d -= p.world;
+              char* base = p.dst[t][d] + dst_off0;
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const int64_t idx = i + int64_t(u) * nthreads;
+                if (idx < total) st_peer_v4(base + idx * 16, v[u]);
+              }
+            }
+          }
         } else {
-          for (int q = 0; q < n_peers; ++q) {
-            int d = p.rank + first + q;            // staggered: rank r starts with peer r+1
-            if (d >= p.world) d -= p.world;
-            char* base = p.dst[t][d];
+          int64_t off[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + int64_t(u) * nthreads;
+            off[u] = -1;
+            if (idx < total) {
+              int64_t row, c;
+              if (p.cpr_shift >= 0) row = idx >> p.cpr_shift, c = idx & (p.cpr - 1);
+              else row = idx / p.cpr, c = idx - row * p.cpr;
+              v[u] = ld_once_v4(src + row * p.ld_src[t] + c * 16);
+              off[u] = dst_off0 + row * p.ld_dst[t] + c * 16;
+            }
+          }
+          if constexpr (MC) {
 #pragma unroll
             for (int u = 0; u < U; ++u)
-              if (off[u] >= 0) st_peer_v4(base + off[u], v[u]);
+              if (off[u] >= 0) st_multicast_v4(p.mc_dst[t] + off[u], v[u]);
+          } else {
+            for (int q = 0; q < n_peers; ++q) {
+              int d = p.rank + first + q;
+              if (d >= p.world) d -= p.world;
+              char* base = p.dst[t][d];
+#pragma unroll
+              for (int u = 0; u < U; ++u)
+                if (off[u] >= 0) st_peer_v4(base + off[u], v[u]);
+            }
           }
         }
       }
@@ -282,8 +311,8 @@ extern "C" int pgsd_shard_push(const pgsd_push_args* a, pgsd_stream_t stream) {
     p.flag[r] = a->flag[r];
     PGSD_REQUIRE((r == a->rank && !a->include_self) || p.flag[r] != nullptr, "shard_push: flag[%d] is null", r);
   }
-  int grid = a->n_ctas > 0 ? a->n_ctas : 16;
-  if (grid > sm_count()) grid = sm_count();   // every CTA must be resident: the slices end on a grid-wide count
+  int grid = a->n_ctas > 0 ? a->n_ctas : 64;
+  if (grid > 2 * sm_count()) grid = 2 * sm_count();   // every CTA must be resident: the slices end on a grid-wide count
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // engine: 1 = bulk-copy (TMA) kernel, needs contiguous rows on both sides and unicast; 0 = LSU kernel
   bool contiguous = true;
@@ -304,8 +333,10 @@ extern "C" int pgsd_shard_push(const pgsd_push_args* a, pgsd_stream_t stream) {
     PGSD_LAUNCH_CHECK("shard_push_tma_kernel");
     return PGSD_OK;
   }
-  if (mc) shard_push_kernel<8, true><<<grid, 512, 0, st>>>(p);
-  else shard_push_kernel<4, false><<<grid, 512, 0, st>>>(p);
+  if (mc && contiguous) shard_push_kernel<4, true, true><<<grid, 256, 0, st>>>(p);
+  else if (mc) shard_push_kernel<4, true, false><<<grid, 256, 0, st>>>(p);
+  else if (contiguous) shard_push_kernel<8, false, true><<<grid, 256, 0, st>>>(p);
+  else shard_push_kernel<4, false, false><<<grid, 256, 0, st>>>(p);
   PGSD_LAUNCH_CHECK("shard_push_kernel");
   return PGSD_OK;
 }

@@ -46,6 +46,7 @@ struct SpmmParams {
   int keep_policy;     // L2 policy of the feature gathers: 0 evict_last (default), 1 normal, 2 evict_first
   int shared_x;        // n_ops == 2 and both operators read the same matrix: gather once
   int grid_reserve;    // resident-CTA slots left free for a collective kernel running beside this launch
+  int smem_carveout;   // preferred shared-memory carve-out in percent (0 = driver default); see launch_groups
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -553,6 +554,15 @@ static int launch_groups(const SpmmParams& p, cudaStream_t st) {
   constexpr int MINB = (NX * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
   constexpr int G = 32 / LPR;
   auto kern = spmm_groups_kernel<W, LPR, NOPS, NX, U, BF16, THREADS, MINB>;
+  // The kernel itself uses no shared memory, so the driver configures its SMs with the smallest carve-out; a
+  // kernel that needs shared memory (the bulk-copy shard push, 64 KB per CTA) then cannot become resident on
+  // those SMs before they drain.  The sharded path asks for a carve-out that leaves room for it.
+  static int carveout_set = -1;
+  if (p.smem_carveout != carveout_set && (p.smem_carveout > 0 || carveout_set > 0)) {
+    PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   p.smem_carveout > 0 ? p.smem_carveout : cudaSharedmemCarveoutDefault));
+    carveout_set = p.smem_carveout;
+  }
   int occ = 0;
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
   if (occ < 1) occ = 1;
@@ -710,6 +720,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   // every row length tried (2.91 vs 3.18 ms at 40 entries/row, 2-3x at 5 entries/row)
   p.use_groups = (a->variant & 0x80) == 0;
   p.keep_policy = (a->variant >> 8) & 3;   // experiment knob (bits 8-9), 128-bit gather path only
+  p.smem_carveout = ((a->variant >> 12) & 7) * 14;   // bits 12-14: preferred shared-memory carve-out, 14 % steps
   const bool can256 = vec32 && row_bytes <= 32 * 32;
   const bool can128 = vec16 && row_bytes <= 32 * 16;
   // one tensor passed as both operands (variant bit 10 switches the sharing off, for A/B timing)

@@ -378,11 +378,12 @@ class PushExchange:
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.slices = slice_rows(self.bounds[rank + 1] - self.bounds[rank], cum)
         self.n_slices = len(self.slices) - 1
-        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "32"))
+        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "64"))
         # engine 1 = bulk-copy (TMA) kernel, 0 = LSU kernel; PGSD_PUSH_TILE = "<chunk bytes>x<stages>"
         self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "0"))
         tile = os.environ.get("PGSD_PUSH_TILE", "16384x4").split("x")
         self.chunk_bytes, self.stages = int(tile[0]), int(tile[1])
+        self.spmm_carveout = int(os.environ.get("PGSD_PUSH_CARVEOUT", "3"))      # x 14 % of 228 KB
         prio = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
         self.stream = torch.cuda.Stream(device=device, priority=prio)
         self.seq = 0
@@ -610,8 +611,11 @@ def _push_step(self, ex, xs, op_ids, n_cols, alpha, beta, zs):
             srcs[k] = x.contiguous()
     seq = ex.push(srcs)
     reserve = ex.n_ctas
+    # bulk-copy engine: its CTAs need shared memory, so the aggregation asks for a carve-out that leaves room
+    variant = ops.SPMM_VARIANT | ((ex.spmm_carveout & 7) << 12) if ex.engine == 1 else None
     own = [srcs[k % n_cols] for k in range(n_ops)]
-    y = ops.spmm(self.stage_blocks[0], own, op_ids, alpha=alpha, beta=beta, zs=zs, grid_reserve=reserve)
+    y = ops.spmm(self.stage_blocks[0], own, op_ids, alpha=alpha, beta=beta, zs=zs, grid_reserve=reserve,
+                 variant=variant)
     mark("own block done")
     planes = ex.planes[seq & 1]
     views = [planes[k % n_cols] for k in range(n_ops)]
@@ -621,7 +625,7 @@ def _push_step(self, ex, xs, op_ids, n_cols, alpha, beta, zs):
         blk = self.stage_blocks[s + 1]
         if blk.nnz == 0:
             continue
-        y = ops.spmm(blk, views, op_ids, alpha=alpha, beta=1.0, zs=y, out=y, grid_reserve=reserve)
+        y = ops.spmm(blk, views, op_ids, alpha=alpha, beta=1.0, zs=y, out=y, grid_reserve=reserve, variant=variant)
         mark(f"stage{s + 1} done")
     ex.finish()
     return y

@@ -48,7 +48,7 @@ def max_over_ranks(v):
 load_stream = torch.cuda.Stream(device=dev)
 
 
-def run(name, start_exchange, wait_exchange, with_load, reserve=0, reps=4):
+def run(name, start_exchange, wait_exchange, with_load, reserve=0, reps=4, variant=None, load_first=False):
     """start_exchange() launches the transfer ordered behind the current stream; wait_exchange() makes the
     current stream wait for everything THIS rank receives."""
     times, loads = [], []
@@ -58,14 +58,17 @@ def run(name, start_exchange, wait_exchange, with_load, reserve=0, reps=4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        start_exchange()
+        if not load_first:
+            start_exchange()
         if with_load:
             load_stream.wait_event(e0)
             with torch.cuda.stream(load_stream):
                 l0.record()
                 for _ in range(3):
-                    ops.spmm(load_plan, [xr, xi], (0, 1), grid_reserve=reserve)
+                    ops.spmm(load_plan, [xr, xi], (0, 1), grid_reserve=reserve, variant=variant)
                 l1.record()
+        if load_first:
+            start_exchange()
         wait_exchange()
         e1.record()
         torch.cuda.synchronize()
@@ -75,7 +78,7 @@ def run(name, start_exchange, wait_exchange, with_load, reserve=0, reps=4):
             if with_load:
                 loads.append(l0.elapsed_time(l1) / 3)
     t = max_over_ranks(sorted(times)[len(times) // 2])
-    rec = {"transport": name, "load": with_load, "world": world, "ms": round(t, 3),
+    rec = {"transport": name, "load": with_load, "load_first": load_first, "world": world, "ms": round(t, 3),
            "ingress_gbs": round(bytes_in / t / 1e6, 1)}
     if with_load:
         rec["spmm_ms_beside"] = round(max_over_ranks(sorted(loads)[len(loads) // 2]), 3)
@@ -93,11 +96,20 @@ for _ in range(5):
 b.record()
 torch.cuda.synchronize()
 out({"what": "aggregation alone", "spmm_ms": round(a.elapsed_time(b) / 5, 3)})
+for code in (1, 2, 3, 4, 5, 6):       # preferred shared-memory carve-out of the aggregation launch
+    for _ in range(2):
+        ops.spmm(load_plan, [xr, xi], (0, 1), variant=code << 12)
+    a.record()
+    for _ in range(5):
+        ops.spmm(load_plan, [xr, xi], (0, 1), variant=code << 12)
+    b.record()
+    torch.cuda.synchronize()
+    out({"what": f"aggregation alone, smem carve-out {14 * code} %", "spmm_ms": round(a.elapsed_time(b) / 5, 3)})
 
 # ---- shard-push kernel: (label, engine, multicast, CTAs, tile)
-variants = [("lsu", 0, 0, 16, "16384x4"), ("lsu", 0, 0, 32, "16384x4"), ("lsu", 0, 0, 48, "16384x4"),
+variants = [("lsu", 0, 0, 32, "16384x4"), ("lsu", 0, 0, 64, "16384x4"), ("lsu", 0, 0, 96, "16384x4"),
             ("tma", 1, 0, 16, "16384x4"), ("tma", 1, 0, 32, "16384x4"), ("tma", 1, 0, 16, "32768x4"),
-            ("lsu-mc", 0, 1, 32, "16384x4")]
+            ("lsu-mc", 0, 1, 64, "16384x4")]
 if os.environ.get("PROBE_VARIANTS"):
     keep = set(os.environ["PROBE_VARIANTS"].split(","))
     variants = [v for v in variants if f"{v[0]}-{v[3]}-{v[4]}" in keep]
@@ -126,8 +138,12 @@ for mc_name, engine, mc, ctas, tile in variants:
             ex.wait_slice(s, state["seq"])
         ex.finish()
 
-    for with_load in (False, True):
-        run(f"push-{mc_name}-{ctas}", start, wait, with_load, reserve=ctas)
+    var = (3 << 12) if engine == 1 else None
+    run(f"push-{mc_name}-{ctas}", start, wait, False)
+    run(f"push-{mc_name}-{ctas}", start, wait, True, reserve=ctas, variant=var)
+    # the aggregation is enqueued BEFORE the push (what a steady-state loop can look like): the push CTAs must
+    # still find room beside the resident aggregation CTAs (grid_reserve / shared-memory carve-out)
+    run(f"push-{mc_name}-{ctas}", start, wait, True, reserve=ctas, variant=var, load_first=True)
     ex.check()
     # data check once per variant: plane rows of peer b must equal what b generated (same generator recipe)
     par = state["seq"] & 1
