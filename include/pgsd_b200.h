@@ -445,7 +445,7 @@ typedef struct pgsd_push_args {
   int32_t n_ctas;                    /* grid size in 256-thread CTAs (0 = 64); engine 1: 32-thread CTAs */
   int64_t slice_row[PGSD_MAX_SLICES + 1];
   uint32_t* flag[PGSD_MAX_RANKS];    /* flag[p][s] on rank p for source = this rank              */
-  uint32_t* counters;                /* [n_slices] local scratch, zero on entry and on exit      */
+  uint32_t* counters;                /* [PGSD_MAX_SLICES + 1] local scratch, zero on entry and on exit */
   uint32_t seq;
   int32_t include_self;              /* 1: also store to dst[t][rank] and set flag[rank]          */
   int32_t engine;                    /* 0: LSU kernel (any row stride, multicast); 1: bulk-copy (TMA) kernel --
@@ -453,6 +453,9 @@ typedef struct pgsd_push_args {
                                         back to 0                                                   */
   int32_t chunk_bytes, stages;       /* engine 1: tile size (0 = 16384) and ring depth (0 = 4)    */
   int32_t reserved;
+  uint32_t* started;                 /* LOCAL word set to seq once every CTA of the push is resident, or NULL:
+                                        pgsd_wait_flags on it before launching the SM-filling aggregation, so
+                                        the push always gets its SM slots (and shared memory) first          */
 } pgsd_push_args;
 
 PGSD_API size_t pgsd_sizeof_push_args(void);

@@ -70,6 +70,7 @@ class PushArgs(C.Structure):
         ("n_slices", _i32), ("n_ctas", _i32), ("slice_row", _i64 * (MAX_SLICES + 1)),
         ("flag", _vp * MAX_RANKS), ("counters", _vp), ("seq", C.c_uint32), ("include_self", _i32),
         ("engine", _i32), ("chunk_bytes", _i32), ("stages", _i32), ("reserved", _i32),
+        ("started", _vp),
     ]
 
 

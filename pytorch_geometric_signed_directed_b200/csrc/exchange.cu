@@ -24,7 +24,20 @@ struct PushParams {
   int64_t slice_row[PGSD_MAX_SLICES + 1];
   uint32_t* flag[PGSD_MAX_RANKS];
   uint32_t* counters;
+  uint32_t* started;   // local word set to seq once every CTA of the push is resident (NULL = off)
 };
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v);
+// Every CTA checks in when it starts; the last one publishes `started`.  The consumer stream waits for it before
+// it launches the (persistent, SM-filling) aggregation, so the push CTAs always get their SM slots first.
+__device__ __forceinline__ void announce_start(const PushParams& p) {
+  if (p.started == nullptr || threadIdx.x != 0) return;
+  const unsigned old = atomicAdd(p.counters + PGSD_MAX_SLICES, 1u);
+  if (old == gridDim.x - 1) {
+    p.counters[PGSD_MAX_SLICES] = 0;
+    st_release_sys_u32(p.started, p.seq);
+  }
+}
 
 __device__ __forceinline__ float4 ld_once_v4(const void* p) {
   float4 r;
@@ -61,6 +74,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // pgsd_spmm_args.grid_reserve counts.
 template <int U, bool MC, bool CONTIG>
 __global__ void __launch_bounds__(256) shard_push_kernel(const __grid_constant__ PushParams p) {
+  announce_start(p);
   const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
   const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int n_peers = p.include_self ? p.world : p.world - 1;
@@ -175,6 +189,7 @@ __global__ void __launch_bounds__(32) shard_push_tma_kernel(const __grid_constan
                                                             const int stages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (threadIdx.x != 0) return;
+  announce_start(p);
   const uint32_t tiles = tc::smem_u32(smem_raw);
   const uint32_t bars = tiles + uint32_t(stages) * uint32_t(chunk);
   for (int i = 0; i < stages; ++i) tc::mbar_init(bars + 8 * i, 1);
@@ -287,6 +302,7 @@ extern "C" int pgsd_shard_push(const pgsd_push_args* a, pgsd_stream_t stream) {
     if ((1 << s) == p.cpr) p.cpr_shift = s;
   p.seq = a->seq;
   p.counters = a->counters;
+  p.started = a->started;
   const bool mc = a->mc_dst[0] != nullptr;
   for (int t = 0; t < a->n_tensors; ++t) {
     PGSD_REQUIRE(a->src[t] != nullptr && reinterpret_cast<uintptr_t>(a->src[t]) % 16 == 0 && a->ld_src_bytes[t] % 16 == 0 &&

@@ -374,16 +374,17 @@ class PushExchange:
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         mc = mc + o_b if mc else 0
         self.mc_ptr = mc if (mc and os.environ.get("PGSD_PUSH_MC", "0") == "1") else 0
-        self.counters = torch.zeros(_MAX_SLICES, dtype=torch.int32, device=device)
+        self.counters = torch.zeros(_MAX_SLICES + 1, dtype=torch.int32, device=device)
+        self.started = torch.zeros(1, dtype=torch.int32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.slices = slice_rows(self.bounds[rank + 1] - self.bounds[rank], cum)
         self.n_slices = len(self.slices) - 1
-        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "64"))
+        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "32"))
         # engine 1 = bulk-copy (TMA) kernel, 0 = LSU kernel; PGSD_PUSH_TILE = "<chunk bytes>x<stages>"
-        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "0"))
+        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "1"))
         tile = os.environ.get("PGSD_PUSH_TILE", "16384x4").split("x")
         self.chunk_bytes, self.stages = int(tile[0]), int(tile[1])
-        self.spmm_carveout = int(os.environ.get("PGSD_PUSH_CARVEOUT", "3"))      # x 14 % of 228 KB
+        self.spmm_carveout = int(os.environ.get("PGSD_PUSH_CARVEOUT", "0"))      # x 14 % of 228 KB
         prio = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
         self.stream = torch.cuda.Stream(device=device, priority=prio)
         self.seq = 0
@@ -404,8 +405,11 @@ class PushExchange:
         mc = [self.mc_ptr + off(t) for t in range(self.n_planes)] if self.mc_ptr else None
         ops.shard_push(list(xs), dst, self.row_bytes, self.rank, self.world, self.slices, fl, self.counters,
                        self.seq, n_ctas=self.n_ctas, mc_ptrs=mc, include_self=bool(mc), stream=self.stream,
-                       engine=self.engine, chunk_bytes=self.chunk_bytes, stages=self.stages)
+                       engine=self.engine, chunk_bytes=self.chunk_bytes, stages=self.stages,
+                       started_ptr=self.started.data_ptr())
         self.done.record(self.stream)
+        # the aggregation launches fill every SM: let the push CTAs become resident first
+        ops.wait_flags(self.started, [0], self.seq, self.status, float(os.environ.get("PGSD_WAIT_TIMEOUT_S", "5")))
         return self.seq
 
     def wait_slice(self, s: int, seq: int) -> None:
@@ -610,9 +614,10 @@ def _push_step(self, ex, xs, op_ids, n_cols, alpha, beta, zs):
         if x.stride(1) != 1 or x.data_ptr() % 16 or (x.stride(0) * x.element_size()) % 16:
             srcs[k] = x.contiguous()
     seq = ex.push(srcs)
-    reserve = ex.n_ctas
-    # bulk-copy engine: its CTAs need shared memory, so the aggregation asks for a carve-out that leaves room
-    variant = ops.SPMM_VARIANT | ((ex.spmm_carveout & 7) << 12) if ex.engine == 1 else None
+    # LSU engine: one 256-thread push CTA takes the register space of one aggregation CTA; the bulk-copy engine's
+    # 32-thread CTAs fit beside a full set of aggregation CTAs (they are resident first, see PushExchange.push)
+    reserve = ex.n_ctas if ex.engine == 0 else 0
+    variant = ops.SPMM_VARIANT | ((ex.spmm_carveout & 7) << 12) if (ex.engine == 1 and ex.spmm_carveout) else None
     own = [srcs[k % n_cols] for k in range(n_ops)]
     y = ops.spmm(self.stage_blocks[0], own, op_ids, alpha=alpha, beta=beta, zs=zs, grid_reserve=reserve,
                  variant=variant)
@@ -791,6 +796,7 @@ class ShardedMagNetConv:
                                               allgather_deg=lambda d: allgather_rows(d, self.bounds, self.group))
             local.meta = {}
         self.local_nnz = local.nnz
+        self.local_plan = local
         self.agg = ShardedAggregator(local, self.bounds, self.rank, self.world, self.group)
         return self
 

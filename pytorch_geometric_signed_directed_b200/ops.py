@@ -216,7 +216,7 @@ def shard_push(srcs: Sequence[Tensor], dst_ptrs: Sequence[Sequence[int]], ld_dst
                slice_row: Sequence[int], flag_ptrs: Sequence[int], counters: Tensor, seq: int, *,
                n_ctas: int = 16, mc_ptrs: Optional[Sequence[int]] = None, include_self: bool = False,
                stream: Optional[torch.cuda.Stream] = None, engine: int = 0, chunk_bytes: int = 0,
-               stages: int = 0) -> None:
+               stages: int = 0, started_ptr: int = 0) -> None:
     """All-gather push over NVLink peer memory (`pgsd_shard_push`): every 16-byte piece of the local rows
     `srcs[t]` is read once and stored to dst_ptrs[t][p] (+ row * ld_dst_bytes) on every peer p; slice s =
     rows [slice_row[s], slice_row[s+1]) is published by writing `seq` to flag_ptrs[p][s] on every peer."""
@@ -245,6 +245,7 @@ def shard_push(srcs: Sequence[Tensor], dst_ptrs: Sequence[Sequence[int]], ld_dst
         a.flag[p_] = flag_ptrs[p_] or None
     a.counters, a.seq, a.include_self = counters.data_ptr(), seq & 0xffffffff, int(include_self)
     a.engine, a.chunk_bytes, a.stages = int(engine), int(chunk_bytes), int(stages)
+    a.started = started_ptr or None
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     lib = _lib.load()
     with torch.cuda.device(dev):

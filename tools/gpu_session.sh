@@ -26,6 +26,11 @@ case "$R" in
     timeout 600 $TR --nproc-per-node $N --master-port 29553 tools/exchange_probe.py "$@" \
       > gpurun_out/probe_n$N.jsonl 2> gpurun_out/probe_n$N.err
     tail -5 gpurun_out/probe_n$N.err; cat gpurun_out/probe_n$N.jsonl ;;
+  sweep)       # sweep N 'cfg' 'cfg' ...: push-exchange knobs on the sharded step (tools/shard_sweep.py)
+    N=$1; shift
+    timeout 900 $TR --nproc-per-node $N --master-port 29554 tools/shard_sweep.py "$@" \
+      > gpurun_out/sweep_n$N.jsonl 2> gpurun_out/sweep_n$N.err
+    tail -3 gpurun_out/sweep_n$N.err; cat gpurun_out/sweep_n$N.jsonl ;;
   configs)     # the other BASELINE configs
     timeout 900 python tools/bench_configs.py "$@" > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
     tail -3 gpurun_out/configs.err; cat gpurun_out/configs.jsonl ;;
@@ -41,5 +46,5 @@ case "$R" in
     python tools/ncu_summary.py gpurun_out/$O.ncu-rep > gpurun_out/${O}_summary.json 2>/dev/null; cat gpurun_out/${O}_summary.json ;;
   seq)         # seq 'recipe args' 'recipe args' ...: several recipes in one call
     for step in "$@"; do bash tools/gpu_session.sh $step; done ;;
-  *) echo "recipes: tests bench dist distbench probe configs launches ncu seq" ;;
+  *) echo "recipes: tests bench dist distbench probe sweep configs launches ncu seq" ;;
 esac
