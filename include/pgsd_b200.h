@@ -461,6 +461,11 @@ typedef struct pgsd_push_args {
 PGSD_API size_t pgsd_sizeof_push_args(void);
 PGSD_API int pgsd_shard_push(const pgsd_push_args* args, pgsd_stream_t stream);
 
+/* Copy-engine variant of the same exchange (no SM involved): a stream-ordered device-to-device / peer copy and a
+ * one-word signal (fence.sys + st.release.sys of `seq`) that is enqueued behind the copies of a slice. */
+PGSD_API int pgsd_peer_copy(void* dst, const void* src, size_t bytes, pgsd_stream_t stream);
+PGSD_API int pgsd_signal_flag(uint32_t* flag, uint32_t seq, pgsd_stream_t stream);
+
 /* Stream-ordered wait: returns (on the stream) once flags[index_host[i]] has reached `seq` for all
  * i < n (n <= 64), polling with ld.acquire.sys.  After timeout_ns the kernel gives up, writes 1 to
  * *status (device int32, may be NULL) and lets the stream continue -- the caller checks status at

@@ -122,6 +122,8 @@ _PROTOTYPES = {
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "pgsd_sizeof_push_args": (C.c_size_t, []),
     "pgsd_shard_push": (C.c_int, [C.POINTER(PushArgs), _vp]),
+    "pgsd_peer_copy": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "pgsd_signal_flag": (C.c_int, [_vp, C.c_uint32, _vp]),
     "pgsd_wait_flags": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.c_uint32, C.c_uint64, _vp, _vp]),
 }
 

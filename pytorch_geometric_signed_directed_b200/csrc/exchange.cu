@@ -357,6 +357,26 @@ extern "C" int pgsd_shard_push(const pgsd_push_args* a, pgsd_stream_t stream) {
   return PGSD_OK;
 }
 
+// ---- copy-engine transport (engine 2 of the Python exchange): plain peer copies + a one-word signal ----------
+__global__ void signal_flags_kernel(uint32_t* flag, uint32_t seq) {
+  __threadfence_system();
+  st_release_sys_u32(flag, seq);
+}
+
+extern "C" int pgsd_peer_copy(void* dst, const void* src, size_t bytes, pgsd_stream_t stream) {
+  if (bytes == 0) return PGSD_OK;
+  PGSD_REQUIRE(dst != nullptr && src != nullptr, "peer_copy: null pointer");
+  PGSD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return PGSD_OK;
+}
+
+extern "C" int pgsd_signal_flag(uint32_t* flag, uint32_t seq, pgsd_stream_t stream) {
+  PGSD_REQUIRE(flag != nullptr, "signal_flag: null pointer");
+  signal_flags_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(flag, seq);
+  PGSD_LAUNCH_CHECK("signal_flags_kernel");
+  return PGSD_OK;
+}
+
 extern "C" int pgsd_wait_flags(const uint32_t* flags, const int32_t* index_host, int32_t n, uint32_t seq,
                                uint64_t timeout_ns, int32_t* status, pgsd_stream_t stream) {
   PGSD_REQUIRE(flags != nullptr && (n == 0 || index_host != nullptr), "wait_flags: null pointer");

@@ -387,6 +387,10 @@ class PushExchange:
         self.spmm_carveout = int(os.environ.get("PGSD_PUSH_CARVEOUT", "0"))      # x 14 % of 228 KB
         prio = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
         self.stream = torch.cuda.Stream(device=device, priority=prio)
+        # engine 2: copy engines -- cudaMemcpyAsync peer copies per (slice, peer) on PGSD_CE_STREAMS streams, each
+        # slice followed by a one-word signal kernel; no SM, no gate
+        self.ce_streams = [torch.cuda.Stream(device=device, priority=prio)
+                           for _ in range(max(1, int(os.environ.get("PGSD_CE_STREAMS", "7"))))] if self.engine == 2 else []
         self.seq = 0
         self.done = torch.cuda.Event()
         self.planes = [[self.buf[(par * n_planes + t) * n_total:(par * n_planes + t + 1) * n_total]
@@ -403,6 +407,25 @@ class PushExchange:
         dst = [[self.buf_ptrs[p] + off(t) for p in range(self.world)] for t in range(self.n_planes)]
         fl = [self.flag_ptrs[p] + 4 * ((par * _MAX_RANKS + self.rank) * _MAX_SLICES) for p in range(self.world)]
         mc = [self.mc_ptr + off(t) for t in range(self.n_planes)] if self.mc_ptr else None
+        if self.engine == 2 and all(x.is_contiguous() for x in xs):
+            lib = ops._lib.load()
+            for st in self.ce_streams:
+                st.wait_stream(cur)
+            for s in range(self.n_slices):
+                r0, r1 = self.slices[s], self.slices[s + 1]
+                for q in range(1, self.world):
+                    p = (self.rank + q) % self.world
+                    st = self.ce_streams[(q - 1) % len(self.ce_streams)].cuda_stream
+                    for t, x in enumerate(xs):
+                        ops._lib.check(lib.pgsd_peer_copy(dst[t][p] + r0 * self.row_bytes,
+                                                          x.data_ptr() + r0 * self.row_bytes,
+                                                          (r1 - r0) * self.row_bytes, st), "pgsd_peer_copy")
+                    ops._lib.check(lib.pgsd_signal_flag(fl[p] + 4 * s, self.seq & 0xffffffff, st), "pgsd_signal_flag")
+            ops.LAUNCHES += self.n_slices * (self.world - 1)
+            for st in self.ce_streams:
+                self.stream.wait_stream(st)
+            self.done.record(self.stream)
+            return self.seq
         ops.shard_push(list(xs), dst, self.row_bytes, self.rank, self.world, self.slices, fl, self.counters,
                        self.seq, n_ctas=self.n_ctas, mc_ptrs=mc, include_self=bool(mc), stream=self.stream,
                        engine=self.engine, chunk_bytes=self.chunk_bytes, stages=self.stages,
@@ -614,6 +637,21 @@ def _push_step(self, ex, xs, op_ids, n_cols, alpha, beta, zs):
         if x.stride(1) != 1 or x.data_ptr() % 16 or (x.stride(0) * x.element_size()) % 16:
             srcs[k] = x.contiguous()
     seq = ex.push(srcs)
+    if trace:
+        # true arrival times, independent of when the aggregation gets round to waiting for a slice
+        obs = getattr(ex, "_observer", None) or torch.cuda.Stream(device=srcs[0].device)
+        ex._observer = obs
+        obs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(obs):
+            for s in range(ex.n_slices):
+                ex.wait_slice(s, seq)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(obs)
+                TRACE.append((f"slice{s} arrived", ev))
+            obs.wait_event(ex.done)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(obs)
+            TRACE.append(("own push done", ev))
     # LSU engine: one 256-thread push CTA takes the register space of one aggregation CTA; the bulk-copy engine's
     # 32-thread CTAs fit beside a full set of aggregation CTAs (they are resident first, see PushExchange.push)
     reserve = ex.n_ctas if ex.engine == 0 else 0

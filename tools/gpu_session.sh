@@ -26,6 +26,10 @@ case "$R" in
     timeout 600 $TR --nproc-per-node $N --master-port 29553 tools/exchange_probe.py "$@" \
       > gpurun_out/probe_n$N.jsonl 2> gpurun_out/probe_n$N.err
     tail -5 gpurun_out/probe_n$N.err; cat gpurun_out/probe_n$N.jsonl ;;
+  interfere)   # 2 GPUs: slowdown of the aggregation beside each kind of NVLink transfer
+    timeout 600 $TR --nproc-per-node 2 --master-port 29555 tools/interference_probe.py "$@" \
+      > gpurun_out/interference.jsonl 2> gpurun_out/interference.err
+    tail -3 gpurun_out/interference.err; cat gpurun_out/interference.jsonl ;;
   sweep)       # sweep N 'cfg' 'cfg' ...: push-exchange knobs on the sharded step (tools/shard_sweep.py)
     N=$1; shift
     timeout 900 $TR --nproc-per-node $N --master-port 29554 tools/shard_sweep.py "$@" \

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pytorch_geometric_signed_directed_b200 import distributed as pgd, nn, synthetic  # noqa: E402
+from pytorch_geometric_signed_directed_b200 import distributed as pgd, nn, ops, synthetic  # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -28,7 +28,7 @@ sh = pgd.ShardedMagNetConv(conv, n_b, rank, world).build(ei)
 del ei
 xr = torch.rand(sh.n_local, f, device=dev) * 2 - 1
 xi = torch.rand(sh.n_local, f, device=dev) * 2 - 1
-KEYS = {"slices": "PGSD_PUSH_SLICES", "ctas": "PGSD_PUSH_CTAS", "engine": "PGSD_PUSH_ENGINE", "tile": "PGSD_PUSH_TILE",
+KEYS = {"cestreams": "PGSD_CE_STREAMS", "slices": "PGSD_PUSH_SLICES", "ctas": "PGSD_PUSH_CTAS", "engine": "PGSD_PUSH_ENGINE", "tile": "PGSD_PUSH_TILE",
         "exchange": "PGSD_EXCHANGE", "mc": "PGSD_PUSH_MC"}
 configs = [a for a in sys.argv[1:] if not a.startswith("--")] or os.environ.get("PGSD_SWEEP", "slices=auto").split()
 trace = "--trace" in sys.argv
@@ -37,9 +37,13 @@ with torch.no_grad():
     for cfg in configs:
         for k in KEYS.values():
             os.environ.pop(k, None)
+        ops.SPMM_VARIANT = 0
         for item in cfg.split(";"):
             k, v = item.split("=", 1)
-            os.environ[KEYS[k]] = v
+            if k == "variant":
+                ops.SPMM_VARIANT = int(v, 0)
+            else:
+                os.environ[KEYS[k]] = v
         sh.agg = pgd.ShardedAggregator(sh.local_plan, sh.bounds, rank, world)
         for _ in range(4):
             sh(xr, xi)
