@@ -646,8 +646,12 @@ def run_gpu_arm(args, rank, world):
         push = agg._push[1] if agg._push else None
         pull = agg._pull[1] if agg._pull else None
         if push is not None:
-            transport = {"name": "shard-push kernel over symmetric peer memory (pgsd_shard_push)",
-                         "engine": "bulk-copy (TMA)" if push.engine == 1 else "LSU", "ctas": push.n_ctas,
+            transport = {"name": "push into the peers' receive planes in symmetric memory, per-slice flags "
+                                 "(pgsd_shard_push / pgsd_peer_copy + pgsd_signal_flag, pgsd_wait_flags)",
+                         "engine": {0: "LSU push kernel", 1: "bulk-copy (TMA) push kernel",
+                                    2: "copy engines (cudaMemcpyAsync peer copies)"}[push.engine],
+                         "ctas": push.n_ctas if push.engine != 2 else 0,
+                         "copy_streams": len(push.ce_streams),
                          "slices": [round(c, 3) for c in agg.stage_cum], "multicast": bool(push.mc_ptr),
                          "nvlink_bytes_in_per_rank": (world - 1) * n_local * FEAT * 4 * 2}
         else:

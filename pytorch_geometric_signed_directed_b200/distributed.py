@@ -100,35 +100,22 @@ def split_columns_by_owner(local: CSRPlan, bounds: Sequence[int], own_rank: int)
 
 def stage_fractions(spec=None, world: int = 2) -> List[float]:
     """Cumulative row fractions of the slices a shard travels in (push exchange).  `spec` / PGSD_PUSH_SLICES is
-    a count (equal slices) or a comma list of weights.  Default: a small model of the step -- the own-column
-    block takes t_agg / world, the exchange (world-1) shard times, every extra launch re-reads the outputs:
-      * exchange-bound (8 ranks): the aggregation always waits for rows, so the slices only have to keep the
-        LAST block (aggregated after the whole exchange) small: six slices shrinking towards the end;
-      * aggregation-bound (2-4 ranks): as few launches as possible -- each slice ends where the exchange will
-        be when the previous block finishes (2 ranks: one slice, the whole peer shard is there in time)."""
+    a count (equal slices) or a comma list of weights.  Defaults are the best of the sweeps on 1M nodes / 20M edges
+    per rank (profiles/r02_sweep_n{2,4,8}_*.jsonl): every extra slice costs one more aggregation launch that re-reads
+    and re-writes the outputs (1 GB), so few slices win while the aggregation is the bottleneck (2 ranks: the whole
+    peer shard lands before the own-column block is done -> one slice; 3-4 ranks: two); at 8 ranks the exchange
+    paces the step and four slices keep the block that runs after the last arrival at a quarter of the remote work."""
     if spec is None:
         spec = os.environ.get("PGSD_PUSH_SLICES", "")
     spec = str(spec)
-    if spec and spec != "auto":
-        w = [float(t) for t in spec.split(",") if t.strip()] if "," in spec else [1.0] * max(1, int(spec))
-        tot, acc, cum = sum(w), 0.0, [0.0]
-        for v in w:
-            acc += v
-            cum.append(acc / tot)
-        cum[-1] = 1.0
-        return cum
-    t_agg, t_shard, t_launch, k_max = 3.0, 0.75, 0.15, 6           # ms, north-star shapes on B200 / NVLink 5
-    t_x, t_rem, t = (world - 1) * t_shard, t_agg * (world - 1) / world, t_agg / world
-    if t_x >= 1.3 * (t_rem + k_max * t_launch):
-        w = [0.22, 0.20, 0.18, 0.16, 0.14, 0.10]
-        return stage_fractions(",".join(str(v) for v in w))
-    cum = [0.0]
-    while cum[-1] < 1.0:
-        f = 1.0 if len(cum) == k_max else min(1.0, max(t / t_x, cum[-1] + 0.05))
-        if 1.0 - f < 0.08:
-            f = 1.0
-        t = max(t, f * t_x) + (f - cum[-1]) * t_rem + t_launch
-        cum.append(f)
+    if not spec or spec == "auto":
+        spec = "1" if world <= 2 else ("2" if world <= 4 else "4")
+    w = [float(t) for t in spec.split(",") if t.strip()] if "," in spec else [1.0] * max(1, int(spec))
+    tot, acc, cum = sum(w), 0.0, [0.0]
+    for v in w:
+        acc += v
+        cum.append(acc / tot)
+    cum[-1] = 1.0
     return cum
 
 
@@ -379,10 +366,14 @@ class PushExchange:
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.slices = slice_rows(self.bounds[rank + 1] - self.bounds[rank], cum)
         self.n_slices = len(self.slices) - 1
-        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "32"))
-        # engine 1 = bulk-copy (TMA) kernel, 0 = LSU kernel; PGSD_PUSH_TILE = "<chunk bytes>x<stages>"
-        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "1"))
-        tile = os.environ.get("PGSD_PUSH_TILE", "16384x4").split("x")
+        # Transport (measured): engine 2 = copy engines (no SM; does not slow the aggregation beside it, but
+        # many small copies to 7 peers top out near 420 GB/s), engine 1 = bulk-copy (TMA) push kernel, engine 0 = LSU
+        # push kernel.  Up to 4 ranks the aggregation is the bottleneck -> copy engines; beyond, the exchange paces the
+        # step -> the push kernel, throttled to 12 CTAs x 4 tiles of 32 KB: as fast as 32 CTAs (NVLink-bound either
+        # way) but it slows the aggregation beside it 1.6x instead of 2.5x.
+        self.engine = int(os.environ.get("PGSD_PUSH_ENGINE", "2" if world <= 4 else "1"))
+        self.n_ctas = int(os.environ.get("PGSD_PUSH_CTAS", "12" if self.engine == 1 else "32"))
+        tile = os.environ.get("PGSD_PUSH_TILE", "32768x4").split("x")
         self.chunk_bytes, self.stages = int(tile[0]), int(tile[1])
         self.spmm_carveout = int(os.environ.get("PGSD_PUSH_CARVEOUT", "0"))      # x 14 % of 228 KB
         prio = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
@@ -390,7 +381,8 @@ class PushExchange:
         # engine 2: copy engines -- cudaMemcpyAsync peer copies per (slice, peer) on PGSD_CE_STREAMS streams, each
         # slice followed by a one-word signal kernel; no SM, no gate
         self.ce_streams = [torch.cuda.Stream(device=device, priority=prio)
-                           for _ in range(max(1, int(os.environ.get("PGSD_CE_STREAMS", "7"))))] if self.engine == 2 else []
+                           for _ in range(max(1, int(os.environ.get("PGSD_CE_STREAMS", str(min(world - 1, 3))))))] \
+            if self.engine == 2 else []
         self.seq = 0
         self.done = torch.cuda.Event()
         self.planes = [[self.buf[(par * n_planes + t) * n_total:(par * n_planes + t + 1) * n_total]

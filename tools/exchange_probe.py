@@ -11,6 +11,8 @@ import json
 import os
 import sys
 
+# one hardware queue per stream of the exchange (copy-engine transport: up to 7 copy streams + compute + push)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch
 import torch.distributed as dist
 

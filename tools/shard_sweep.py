@@ -1,12 +1,14 @@
 """Sweep of the push-exchange knobs on the bench's sharded step (run under torchrun, NCCL): one operator build, then
 for every configuration a fresh ShardedAggregator (stage blocks + exchange) and 10 timed steps; prints one JSON
 line per configuration (max over ranks) and, with --trace, the steady-state timeline of rank 0.
-    configs: "slices=<spec>;ctas=<n>;engine=<0|1>;tile=<bytes>x<stages>" separated by spaces (PGSD_SWEEP env or argv)
+    configs: "slices=<spec>+ctas=<n>+engine=<0|1|2>+tile=<bytes>x<stages>" separated by spaces (PGSD_SWEEP env or argv)
 """
 import json
 import os
 import sys
 
+# one hardware queue per stream of the exchange (copy-engine transport: up to 7 copy streams + compute + push)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch
 import torch.distributed as dist
 
@@ -38,7 +40,7 @@ with torch.no_grad():
         for k in KEYS.values():
             os.environ.pop(k, None)
         ops.SPMM_VARIANT = 0
-        for item in cfg.split(";"):
+        for item in cfg.split("+"):
             k, v = item.split("=", 1)
             if k == "variant":
                 ops.SPMM_VARIANT = int(v, 0)
