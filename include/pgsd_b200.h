@@ -180,7 +180,8 @@ typedef struct pgsd_spmm_args {
   int32_t feat;              /* F: feature columns aggregated                         */
   int32_t n_ops;             /* 1 or 2                                                */
   int32_t dtype;             /* PGSD_F32 or PGSD_BF16 (x, z, y); accumulation is fp32 */
-  int32_t mean;              /* 1: divide by max(row length, 1)                       */
+  int32_t mean;              /* bit 0: divide by max(row length, 1); bit 1: tanh of the finished row
+                                (after beta * z and bias; hub rows excluded)           */
   const int32_t* row_ptr;    /* [n_rows + 1]                                          */
   const int32_t* col;        /* [nnz]                                                 */
   const float* val[2];       /* [nnz] or NULL (implicit 1.0)                          */
@@ -337,6 +338,34 @@ typedef struct pgsd_attn_args {
 
 PGSD_API int pgsd_edge_softmax(const pgsd_attn_args* args, pgsd_stream_t stream);
 
+/* Backward of pgsd_edge_softmax (training through SNEAConv.message, nn/signed/SNEAConv.py:135-146, and through the
+ * attention of PyG GATConv as used by nn/signed/SDGNN.py:35-64).  dL/dalpha arrives per stored entry (dalpha[p],
+ * GAT-style: see pgsd_sddmm_rows) or, when dalpha[p] is NULL, as one coefficient per row (row_coef[p], SNEAConv:
+ * <gy[i], xd_p[i]>).  Writes g_s_dst[p] [n_rows]; ADDS into g_s_src[p] [n_src] (caller zero-initialises; fp32
+ * atomics); type_sum[p] (optional, [n_rows]) receives the per-row sum of alpha over the entries of type p. */
+typedef struct pgsd_attn_bwd_args {
+  int64_t n_rows;
+  int32_t n_types, act;
+  float slope;
+  int32_t reserved;
+  const int32_t* row_ptr[2];
+  const int32_t* col[2];
+  const float* s_src[2];
+  const float* s_dst[2];
+  const float* dalpha[2];
+  const float* row_coef[2];
+  float* g_s_src[2];
+  float* g_s_dst[2];
+  float* type_sum[2];
+} pgsd_attn_bwd_args;
+PGSD_API int pgsd_edge_softmax_backward(const pgsd_attn_bwd_args* args, pgsd_stream_t stream);
+
+/* out[k] = <gy[row(k)], h[col[k]]> for every stored entry k of a CSR plan: dL/dalpha of y[i] = sum_k alpha_k h[col_k]
+ * (sampled dense-dense product).  fp32, feat % 4 == 0 (<= 256), 16-byte aligned rows. */
+PGSD_API int pgsd_sddmm_rows(const int32_t* row_ptr, const int32_t* col, const float* gy, int64_t ldg,
+                             const float* h, int64_t ldh, int64_t n_rows, int32_t feat, float* out,
+                             pgsd_stream_t stream);
+
 /* GATConv aggregation with the edge softmax inside (PyG GATConv, heads = 1, as used by nn/signed/SDGNN.py:35-61 and
  * nn/signed/SiGAT.py:59-64):  y[i] = sum_e alpha_e h[col_e] (+ bias) (+ beta * z[i]) over the entries of row i,
  * alpha = softmax_i(leaky_relu(s_src[col_e] + s_dst[i])) with PyG's 1e-16 in the denominator.  fp32, feat a
@@ -460,6 +489,12 @@ typedef struct pgsd_push_args {
 
 PGSD_API size_t pgsd_sizeof_push_args(void);
 PGSD_API int pgsd_shard_push(const pgsd_push_args* args, pgsd_stream_t stream);
+
+/* Content fingerprint of a device buffer: out2[0] += sum of its 32-bit words, out2[1] += position-weighted sum
+ * (both wrap around; the caller zero-initialises out2).  The Python plan cache compares it before it reuses a plan
+ * for edge tensors whose identity (pointer, shape, version counter) has not changed -- the reference itself
+ * re-normalises on every call (nn/general/conv_base.py:102-108, MagNetConv.py:158-181 with cached=False). */
+PGSD_API int pgsd_fingerprint(const void* data, int64_t n_bytes, uint64_t* out2, pgsd_stream_t stream);
 
 /* Copy-engine variant of the same exchange (no SM involved): a stream-ordered device-to-device / peer copy and a
  * one-word signal (fence.sys + st.release.sys of `seq`) that is enqueued behind the copies of a slice. */

@@ -59,6 +59,15 @@ class MagnetFusedArgs(C.Structure):
     ]
 
 
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", _i64), ("n_types", _i32), ("act", _i32), ("slope", _f32), ("reserved", _i32),
+        ("row_ptr", _vp * 2), ("col", _vp * 2), ("s_src", _vp * 2), ("s_dst", _vp * 2),
+        ("dalpha", _vp * 2), ("row_coef", _vp * 2), ("g_s_src", _vp * 2), ("g_s_dst", _vp * 2),
+        ("type_sum", _vp * 2),
+    ]
+
+
 MAX_RANKS, MAX_SLICES = 16, 16
 
 
@@ -114,6 +123,8 @@ _PROTOTYPES = {
     "pgsd_sizeof_magnet_fused_args": (C.c_size_t, []),
     "pgsd_magnet_layer_fused": (C.c_int, [C.POINTER(MagnetFusedArgs), _vp]),
     "pgsd_edge_softmax": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "pgsd_edge_softmax_backward": (C.c_int, [C.POINTER(AttnBwdArgs), _vp]),
+    "pgsd_sddmm_rows": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "pgsd_xtg_accumulate": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
     "pgsd_coalesce_workspace_bytes": (C.c_int, [_i64, C.POINTER(C.c_size_t)]),
     "pgsd_coo_coalesce": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, C.POINTER(_i64), _vp, C.c_size_t, _vp]),
@@ -122,6 +133,7 @@ _PROTOTYPES = {
     "pgsd_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "pgsd_sizeof_push_args": (C.c_size_t, []),
     "pgsd_shard_push": (C.c_int, [C.POINTER(PushArgs), _vp]),
+    "pgsd_fingerprint": (C.c_int, [_vp, _i64, _vp, _vp]),
     "pgsd_peer_copy": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "pgsd_signal_flag": (C.c_int, [_vp, C.c_uint32, _vp]),
     "pgsd_wait_flags": (C.c_int, [_vp, C.POINTER(_i32), _i32, C.c_uint32, C.c_uint64, _vp, _vp]),

@@ -131,8 +131,18 @@ class _DenseFn(torch.autograd.Function):
         xs, ws = tensors[:n_terms], tensors[n_terms:2 * n_terms]
         bias = tensors[-1] if has_bias else None
         terms = [(x, w, g) for x, w, g in zip(xs, ws, groups)]
-        outs = ops.dense(terms, n_out, bias=bias, combine=combine, relu_mode=relu_mode)
-        ctx.save_for_backward(*xs, *ws, *(outs[:1] if relu_mode else ()))
+        if combine and relu_mode == 1:
+            # complex ReLU (complex_relu.py:21-22): the mask is `real >= 0` of the PRE-activation; it cannot be
+            # recovered from the outputs (real == 0 passes the imaginary part, real < 0 zeroes both), so the
+            # training path keeps it: one transform without the fused mask + one elementwise pass
+            pre = ops.dense(terms, n_out, bias=bias, combine=True, relu_mode=0)
+            mask = pre[0] >= 0
+            outs = [pre[0] * mask, pre[1] * mask]
+            extra = (mask,)
+        else:
+            outs = ops.dense(terms, n_out, bias=bias, combine=combine, relu_mode=relu_mode)
+            extra = tuple(outs[:1]) if relu_mode else ()
+        ctx.save_for_backward(*xs, *ws, *extra)
         ctx.cfg = (n_out, combine, relu_mode, groups, has_bias, n_terms)
         return tuple(outs)
 
@@ -144,11 +154,17 @@ class _DenseFn(torch.autograd.Function):
         g0 = gys[0].contiguous()
         if combine:
             g1 = gys[1].contiguous()
-            if relu_mode:
-                m = (saved[-1] > 0).to(g0.dtype)      # complex ReLU mask (treated as a constant)
+            if relu_mode == 1:
+                m = saved[-1].to(g0.dtype)             # complex ReLU mask of the forward pass
                 g0, g1 = g0 * m, g1 * m
+            elif relu_mode:
+                raise RuntimeError("dense: only the complex ReLU epilogue is differentiable with combine=True")
             gg = [g0 + g1, g1 - g0]                    # dA, dB of out_real = A-B+b, out_imag = A+B+b
         else:
+            if relu_mode == 2:                         # tanh epilogue: d tanh = 1 - out^2
+                g0 = g0 * (1.0 - saved[-1].to(g0.dtype) ** 2)
+            elif relu_mode:
+                raise RuntimeError(f"dense: epilogue {relu_mode} is not differentiable with combine=False")
             gg = [g0]
         dev = g0.device
         gxs, gws = [None] * n_terms, [None] * n_terms
@@ -182,3 +198,101 @@ def dense(terms: Sequence[Tuple[Tensor, Tensor, int]], n_out: int, *, bias: Opti
     groups = tuple(int(t[2]) for t in terms)
     tensors = xs + ws + ([bias] if bias is not None else [])
     return list(_DenseFn.apply(n_out, combine, relu_mode, groups, bias is not None, len(terms), *tensors))
+
+
+# ----------------------------------------------------------------------------- attention layers
+# Training through SNEAConv (nn/signed/SNEAConv.py:135-146) and the GATConv of SDGNN / SiGAT (nn/signed/SDGNN.py:
+# 35-64): the forward kernels are reused; the backward is one segment-softmax-backward kernel
+# (`pgsd_edge_softmax_backward`), and for the GAT-style weighted sum an SDDMM (`pgsd_sddmm_rows`, dL/dalpha) plus the
+# transposed aggregation with the same alpha (`pgsd_spmm_csr` on a transposed pattern cached on the plan).
+
+def transposed_pattern(plan: CSRPlan):
+    """(row_ptr_T, col_T, perm): CSR of the transposed pattern and the permutation that carries a per-entry array
+    of `plan` into its order.  Built once per plan (stable: entries of a transposed row keep destination order)."""
+    cached = getattr(plan, "_tpattern", None)
+    if cached is None:
+        dev = plan.device
+        counts = (plan.row_ptr[1:] - plan.row_ptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(plan.n_dst, device=dev), counts)
+        col = plan.col[:plan.nnz].long()
+        perm = torch.sort(col * plan.n_dst + rows, stable=True).indices
+        rp = torch.zeros(plan.n_src + 1, dtype=torch.int32, device=dev)
+        if plan.nnz:
+            rp[1:] = torch.cumsum(torch.bincount(col, minlength=plan.n_src), 0).int()
+        cached = (rp, rows[perm].int().contiguous(), perm)
+        plan._tpattern = cached
+    return cached
+
+
+class _EdgeSoftmaxSumFn(torch.autograd.Function):
+    """y[i] = sum_t xd_t[i] * (sum of alpha over row i's entries of type t)  -- SNEAConv's aggregation."""
+
+    @staticmethod
+    def forward(ctx, plans, act, slope, n_types, *tensors):
+        s_src, s_dst, xd = tensors[:n_types], tensors[n_types:2 * n_types], tensors[2 * n_types:]
+        y, _ = ops.edge_softmax(plans, list(s_src), list(s_dst), act=act, slope=slope, xd=list(xd))
+        ctx.save_for_backward(*tensors)
+        ctx.cfg = (plans, act, slope, n_types)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        plans, act, slope, n_types = ctx.cfg
+        t = ctx.saved_tensors
+        s_src, s_dst, xd = t[:n_types], t[n_types:2 * n_types], t[2 * n_types:]
+        gy = gy.contiguous()
+        coef = [(gy * x).sum(1) for x in xd]                       # dL/dalpha of every entry of type t in row i
+        g_src, g_dst, sums = ops.edge_softmax_backward(plans, s_src, s_dst, act=act, slope=slope, row_coef=coef,
+                                                       want_type_sum=True)
+        g_xd = [gy * sm.view(-1, 1) for sm in sums]
+        fit = lambda g, like: g[:like.numel()].view(like.shape).to(like.dtype)
+        return (None,) * 4 + tuple(fit(g, s) for g, s in zip(g_src, s_src)) \
+            + tuple(fit(g, s) for g, s in zip(g_dst, s_dst)) + tuple(g_xd)
+
+
+def edge_softmax_sum(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Sequence[Tensor],
+                     xd: Sequence[Tensor], act: str = "tanh", slope: float = 0.2) -> Tensor:
+    tensors = list(s_src) + list(s_dst) + list(xd)
+    if not _needs_grad(tensors):
+        return ops.edge_softmax(plans, list(s_src), list(s_dst), act=act, slope=slope, xd=list(xd))[0]
+    return _EdgeSoftmaxSumFn.apply(list(plans), act, slope, len(plans), *tensors)
+
+
+class _GatAttendFn(torch.autograd.Function):
+    """y = sum_e alpha_e h[col_e] (+ bias),  alpha = softmax_row(leaky_relu(s_src[col] + s_dst[row]))."""
+
+    @staticmethod
+    def forward(ctx, plan, slope, has_bias, s_src, s_dst, h, *rest):
+        bias = rest[0] if has_bias else None
+        _, alphas = ops.edge_softmax([plan], [s_src], [s_dst], act="leaky_relu", slope=slope, want_alpha=True)
+        alpha = alphas[0]
+        weighted = CSRPlan(plan.n_dst, plan.n_src, plan.nnz, plan.num_input_edges, plan.row_ptr, plan.col, [alpha],
+                           [None], [0.0])
+        y = ops.spmm(weighted, [h], (0,), bias=bias)[0]
+        ctx.save_for_backward(s_src, s_dst, h, alpha)
+        ctx.cfg = (plan, slope, has_bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        plan, slope, has_bias = ctx.cfg
+        s_src, s_dst, h, alpha = ctx.saved_tensors
+        gy = gy.contiguous()
+        dalpha = ops.sddmm_rows(plan, gy, h)
+        g_src, g_dst, _ = ops.edge_softmax_backward([plan], [s_src], [s_dst], act="leaky_relu", slope=slope,
+                                                    dalpha=[dalpha])
+        rp_t, col_t, perm = transposed_pattern(plan)
+        tplan = CSRPlan(plan.n_src, plan.n_dst, plan.nnz, plan.num_input_edges, rp_t, col_t, [alpha[perm].contiguous()],
+                        [None], [0.0])
+        g_h = ops.spmm(tplan, [gy], (0,))[0][:h.size(0)].to(h.dtype)
+        fit = lambda g, like: g[:like.numel()].view(like.shape).to(like.dtype)
+        grads = (None, None, None, fit(g_src[0], s_src), fit(g_dst[0], s_dst), g_h)
+        return grads + ((gy.float().sum(0),) if has_bias else ())
+
+
+def gat_attend(plan: CSRPlan, s_src: Tensor, s_dst: Tensor, h: Tensor, slope: float = 0.2,
+               bias: Optional[Tensor] = None) -> Tensor:
+    """Differentiable GAT-style attention aggregation (used on the training path; inference keeps the fused /
+    preallocated routes of nn.GATConv.aggregate)."""
+    tensors = [s_src, s_dst, h] + ([bias] if bias is not None else [])
+    return _GatAttendFn.apply(plan, float(slope), bias is not None, *tensors)

@@ -270,9 +270,177 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(const GatParams p) {
   }
 }
 
+// ---- backward of the segment softmax (training through SNEAConv / GATConv) -----------------------------------
+// Reference: autograd through nn/signed/SNEAConv.py:135-146 and PyG GATConv as used by nn/signed/SDGNN.py:35-64.
+// Per row i the kernel re-evaluates the softmax (max, sums) and then, with dalpha_e = dL/dalpha_e,
+//   D      = sum_e alpha_e dalpha_e
+//   dt_e   = alpha_e (dalpha_e - D)                       (softmax backward; the 1e-16 in the denominator is kept)
+//   dpre_e = dt_e * act'(pre_e)                           (tanh: 1 - t^2;  leaky_relu: 1 or slope)
+//   g_s_src[p][col_e] += dpre_e  (atomics: a source is shared by many rows);   g_s_dst[p][i] = sum_{e of type p} dpre_e
+// dalpha_e comes either per entry (GAT-style: the SDDMM below) or as one coefficient per row and type
+// (SNEAConv: y[i] = xd0[i] S0 + xd1[i] S1 => dalpha_e = <gy[i], xd_type(e)[i]>).  The per-row type sums S_p are written
+// out as well: they are the SNEAConv gradient w.r.t. xd (g_xd_p = gy * S_p).
+struct AttnBwdParams {
+  int64_t n_rows;
+  int32_t n_types, act;
+  float slope;
+  const int32_t* row_ptr[2];
+  const int32_t* col[2];
+  const float* s_src[2];
+  const float* s_dst[2];
+  const float* dalpha[2];     // per entry, or NULL
+  const float* row_coef[2];   // per row, used when dalpha is NULL
+  float* g_s_src[2];
+  float* g_s_dst[2];
+  float* type_sum[2];         // optional S_p per row
+};
+
+template <int LPR>
+__global__ void __launch_bounds__(256) edge_softmax_bwd_kernel(const AttnBwdParams p) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+  const int64_t warp_id = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t stride = int64_t(gridDim.x) * 8 * G;
+  auto gsum = [&](float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, LPR);
+    return v;
+  };
+  for (int64_t base = warp_id * G; base < p.n_rows; base += stride) {
+    const int64_t row = base + g;
+    const bool live = row < p.n_rows;
+    int b[2] = {0, 0}, e[2] = {0, 0};
+    float sd[2] = {0.f, 0.f}, rc[2] = {0.f, 0.f};
+    if (live)
+      for (int t = 0; t < p.n_types; ++t) {
+        b[t] = __ldg(p.row_ptr[t] + row), e[t] = __ldg(p.row_ptr[t] + row + 1);
+        sd[t] = __ldg(p.s_dst[t] + row);
+        if (p.dalpha[t] == nullptr && p.row_coef[t] != nullptr) rc[t] = __ldg(p.row_coef[t] + row);
+      }
+    float m = -INFINITY;
+    for (int t = 0; t < p.n_types; ++t)
+      for (int k = b[t] + l; k < e[t]; k += LPR)
+        m = fmaxf(m, attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope));
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o, LPR));
+    float sum[2] = {0.f, 0.f}, dot = 0.f;
+    for (int t = 0; t < p.n_types; ++t)
+      for (int k = b[t] + l; k < e[t]; k += LPR) {
+        const float ex = expf(attn_act(__ldg(p.s_src[t] + __ldg(p.col[t] + k)) + sd[t], p.act, p.slope) - m);
+        sum[t] += ex;
+        dot += ex * (p.dalpha[t] ? __ldg(p.dalpha[t] + k) : rc[t]);
+      }
+    sum[0] = gsum(sum[0]), sum[1] = gsum(sum[1]), dot = gsum(dot);
+    const float inv = 1.0f / (sum[0] + sum[1] + 1e-16f);
+    const float D = dot * inv;
+    float gd[2] = {0.f, 0.f};
+    for (int t = 0; t < p.n_types; ++t)
+      for (int k = b[t] + l; k < e[t]; k += LPR) {
+        const int c = __ldg(p.col[t] + k);
+        const float pre = __ldg(p.s_src[t] + c) + sd[t];
+        const float a = attn_act(pre, p.act, p.slope);
+        const float alpha = expf(a - m) * inv;
+        const float da = p.dalpha[t] ? __ldg(p.dalpha[t] + k) : rc[t];
+        const float dact = p.act == 0 ? (1.f - a * a) : (pre > 0.f ? 1.f : p.slope);
+        const float dpre = alpha * (da - D) * dact;
+        gd[t] += dpre;
+        atomicAdd(p.g_s_src[t] + c, dpre);
+      }
+    gd[0] = gsum(gd[0]), gd[1] = gsum(gd[1]);
+    if (live && l == 0)
+      for (int t = 0; t < p.n_types; ++t) {
+        p.g_s_dst[t][row] = gd[t];
+        if (p.type_sum[t]) p.type_sum[t][row] = sum[t] * inv;
+      }
+  }
+}
+
+// SDDMM of the GAT-style backward: out[k] = <gy[row(k)], h[col[k]]> for every stored entry k (= dL/dalpha_k of
+// y[i] = sum_k alpha_k h[col_k]).  One 16-lane group per row keeps its slice of gy[row] in registers and gathers the
+// source rows like the aggregation kernels.  feat % 4 == 0, feat <= 256, 16-byte aligned rows.
+__global__ void __launch_bounds__(256) sddmm_rows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                                         const float* __restrict__ gy, int64_t ldg,
+                                                         const float* __restrict__ h, int64_t ldh, int64_t n_rows,
+                                                         int feat, float* __restrict__ out) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int LPR = 16, G = 2, MAXV = 4;
+  const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+  const int64_t stride = int64_t(gridDim.x) * 8 * G;
+  for (int64_t base = (int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5)) * G; base < n_rows; base += stride) {
+    const int64_t row = base + g;
+    const bool live = row < n_rows;
+    int b = 0, e = 0;
+    if (live) b = __ldg(row_ptr + row), e = __ldg(row_ptr + row + 1);
+    float4 gr[MAXV];
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int f = (v * LPR + l) * 4;
+      gr[v] = (live && f < feat) ? __ldg(reinterpret_cast<const float4*>(gy + row * ldg + f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int len = e - b;
+    len = max(len, __shfl_xor_sync(FULL, len, LPR));        // both groups of the warp iterate together
+    for (int k = 0; k < len; ++k) {
+      float acc = 0.f;
+      if (b + k < e) {
+        const float* hr = h + int64_t(__ldg(col + b + k)) * ldh;
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+          const int f = (v * LPR + l) * 4;
+          if (f < feat) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(hr + f));
+            acc = fmaf(gr[v].x, x.x, fmaf(gr[v].y, x.y, fmaf(gr[v].z, x.z, fmaf(gr[v].w, x.w, acc))));
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o, LPR);
+      if (l == 0 && b + k < e) out[b + k] = acc;
+    }
+  }
+}
+
 }  // namespace pgsd
 
 using namespace pgsd;
+
+extern "C" int pgsd_edge_softmax_backward(const pgsd_attn_bwd_args* a, pgsd_stream_t stream) {
+  PGSD_REQUIRE(a != nullptr, "edge_softmax_backward: args is null");
+  PGSD_REQUIRE(a->n_types == 1 || a->n_types == 2, "edge_softmax_backward: n_types must be 1 or 2");
+  PGSD_REQUIRE(a->act == 0 || a->act == 1, "edge_softmax_backward: act must be 0 (tanh) or 1 (leaky_relu)");
+  if (a->n_rows <= 0) return PGSD_OK;
+  AttnBwdParams p{};
+  p.n_rows = a->n_rows, p.n_types = a->n_types, p.act = a->act, p.slope = a->slope;
+  for (int t = 0; t < a->n_types; ++t) {
+    PGSD_REQUIRE(a->row_ptr[t] && a->s_src[t] && a->s_dst[t] && a->g_s_src[t] && a->g_s_dst[t],
+                 "edge_softmax_backward: null pointer (type %d)", t);
+    p.row_ptr[t] = a->row_ptr[t], p.col[t] = a->col[t], p.s_src[t] = a->s_src[t], p.s_dst[t] = a->s_dst[t];
+    p.dalpha[t] = a->dalpha[t], p.row_coef[t] = a->row_coef[t];
+    p.g_s_src[t] = a->g_s_src[t], p.g_s_dst[t] = a->g_s_dst[t], p.type_sum[t] = a->type_sum[t];
+  }
+  constexpr int LPR = 8;
+  int64_t grid = ceil_div<int64_t>(a->n_rows, 8 * (32 / LPR));
+  if (grid > int64_t(sm_count()) * 8) grid = int64_t(sm_count()) * 8;
+  edge_softmax_bwd_kernel<LPR><<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  PGSD_LAUNCH_CHECK("edge_softmax_bwd_kernel");
+  return PGSD_OK;
+}
+
+extern "C" int pgsd_sddmm_rows(const int32_t* row_ptr, const int32_t* col, const float* gy, int64_t ldg, const float* h,
+                               int64_t ldh, int64_t n_rows, int32_t feat, float* out, pgsd_stream_t stream) {
+  if (n_rows <= 0 || feat <= 0) return PGSD_OK;
+  PGSD_REQUIRE(row_ptr && gy && h && out, "sddmm_rows: null pointer");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  PGSD_REQUIRE(feat % 4 == 0 && feat <= 256 && al16(gy) && al16(h) && ldg % 4 == 0 && ldh % 4 == 0,
+               "sddmm_rows: feat must be a multiple of 4 (<= 256) with 16-byte aligned rows");
+  int64_t grid = ceil_div<int64_t>(n_rows, 16);
+  if (grid > int64_t(sm_count()) * 8) grid = int64_t(sm_count()) * 8;
+  sddmm_rows_kernel<<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(row_ptr, col, gy, ldg, h, ldh, n_rows,
+                                                                                 feat, out);
+  PGSD_LAUNCH_CHECK("sddmm_rows_kernel");
+  return PGSD_OK;
+}
+
 
 extern "C" int pgsd_gat_aggregate(const int32_t* row_ptr, const int32_t* col, const float* s_src, const float* s_dst,
                                   float negative_slope, const float* h, int64_t ldh, int32_t feat, int64_t n_rows,

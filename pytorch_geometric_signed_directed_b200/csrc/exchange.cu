@@ -357,6 +357,42 @@ extern "C" int pgsd_shard_push(const pgsd_push_args* a, pgsd_stream_t stream) {
   return PGSD_OK;
 }
 
+// ---- content fingerprint of a device buffer (plan-cache validation, plan.py PlanCache) --------------------------
+// Two wrap-around sums over the 32-bit words in ONE pass: the plain sum and a position-weighted sum (odd
+// multipliers), so single-word edits, compensating edits and permutations all change the result.
+__global__ void __launch_bounds__(256) fingerprint_kernel(const uint32_t* __restrict__ w, int64_t n,
+                                                          unsigned long long* __restrict__ out) {
+  unsigned long long s0 = 0, s1 = 0;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t v = __ldg(w + i);
+    s0 += v;
+    s1 += (unsigned long long)v * (uint32_t(i) * 2654435761u | 1u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, s0);
+    atomicAdd(out + 1, s1);
+  }
+}
+
+extern "C" int pgsd_fingerprint(const void* data, int64_t n_bytes, uint64_t* out2, pgsd_stream_t stream) {
+  PGSD_REQUIRE(out2 != nullptr, "fingerprint: out is null");
+  const int64_t n = n_bytes / 4;
+  if (n <= 0) return PGSD_OK;
+  PGSD_REQUIRE(data != nullptr && reinterpret_cast<uintptr_t>(data) % 4 == 0, "fingerprint: data must be 4-byte aligned");
+  int64_t grid = ceil_div<int64_t>(n, 256 * 8);
+  if (grid > int64_t(sm_count()) * 8) grid = int64_t(sm_count()) * 8;
+  fingerprint_kernel<<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint32_t*>(data), n, reinterpret_cast<unsigned long long*>(out2));
+  PGSD_LAUNCH_CHECK("fingerprint_kernel");
+  return PGSD_OK;
+}
+
 // ---- copy-engine transport (engine 2 of the Python exchange): plain peer copies + a one-word signal ----------
 __global__ void signal_flags_kernel(uint32_t* flag, uint32_t seq) {
   __threadfence_system();

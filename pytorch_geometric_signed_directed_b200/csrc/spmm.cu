@@ -47,6 +47,7 @@ struct SpmmParams {
   int shared_x;        // n_ops == 2 and both operators read the same matrix: gather once
   int grid_reserve;    // resident-CTA slots left free for a collective kernel running beside this launch
   int smem_carveout;   // preferred shared-memory carve-out in percent (0 = driver default); see launch_groups
+  int tanh_out;        // apply tanh to the finished row (SGCN applies it right after the layer, SGCN.py:93-96)
 };
 
 // ---- W-word vector load of a gathered feature row, expanded to fp32 -----------------------
@@ -231,6 +232,10 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_rows_kernel(const SpmmPara
 #pragma unroll
           for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + l * EPL + i);
         }
+        if (p.tanh_out) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] = tanhf(out[i]);
+        }
         RV::store(p.y[k] + row * p.ldy_bytes[k] + lane_off, out, pol_stream);
       }
     }
@@ -370,6 +375,10 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
           if (p.bias != nullptr) {
 #pragma unroll
             for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + l * EPL + i);
+          }
+          if (p.tanh_out) {
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) out[i] = tanhf(out[i]);
           }
           RV::store(p.y[k] + row * p.ldy_bytes[k] + lane_off, out, pol_stream);
         }
@@ -520,6 +529,7 @@ __global__ void __launch_bounds__(256) spmm_rows_scalar_kernel(const SpmmParams 
         float out = p.alpha_op[k] * (acc * inv);
         if (p.z[k]) out = fmaf(p.beta, rd(p.z[k], p.ldz_bytes[k], row, f), out);
         if (p.bias) out += p.bias[f];
+        if (p.tanh_out) out = tanhf(out);
         char* q = p.y[k] + row * p.ldy_bytes[k];
         if constexpr (BF16)
           reinterpret_cast<__nv_bfloat16*>(q)[f] = __float2bfloat16_rn(out);
@@ -677,7 +687,8 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   SpmmParams p{};
   p.n_rows = a->n_rows;
   p.feat = a->feat;
-  p.mean = a->mean;
+  p.mean = a->mean & 1;
+  p.tanh_out = (a->mean >> 1) & 1;
   p.row_ptr = a->row_ptr;
   p.col = a->col;
   p.alpha = a->alpha;
@@ -691,6 +702,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   for (int k = 0; k < a->n_ops; ++k) {
     PGSD_REQUIRE(a->x[k] && a->y[k], "spmm: x[%d]/y[%d] is null", k, k);
     PGSD_REQUIRE(a->ldx[k] >= a->feat && a->ldy[k] >= a->feat, "spmm: leading dim < feat");
+    PGSD_REQUIRE(a->z[k] == nullptr || a->ldz[k] >= a->feat, "spmm: leading dim of z < feat");
     PGSD_REQUIRE(a->ldx[k] * es < (int64_t(1) << 32), "spmm: row stride of x must be below 4 GiB");
     p.val[k] = a->val[k];
     p.diag[k] = a->diag[k];

@@ -100,6 +100,7 @@ class _MagneticChebConv(torch.nn.Module):
         if value is not None:
             raise AttributeError("cached_result is derived from the CSR plan; assign None to reset")
         self._plan, self._cached_result = None, None
+        self._rebuild_cache.clear()
 
     def _q_value(self) -> float:
         return float(self.q.detach().item()) if isinstance(self.q, Tensor) else float(self.q)
@@ -182,9 +183,6 @@ class _MagneticChebConv(torch.nn.Module):
         p = self._plan
         w = self.weight
         k1 = w.size(0)
-        if 2 * k1 > DENSE_MAX_TERMS:
-            raise NotImplementedError(
-                f"K = {k1 - 1}: the fused transform takes at most {DENSE_MAX_TERMS // 2 - 1} Chebyshev orders")
         dt = x_real.dtype
         if dt not in (torch.float32, torch.bfloat16):
             raise TypeError(f"MagNetConv kernels take float32 or bfloat16 features, got {dt}")
@@ -206,8 +204,21 @@ class _MagneticChebConv(torch.nn.Module):
                 t2 = ag.spmm(p, t1, (0, 1), alpha=2.0, beta=-1.0, zs=t0, q=q)  # MagNetConv.py:214-216
                 terms += [(t2[0], w[k], 0), (t2[1], w[k], 1)]
                 t0, t1 = t1, t2
-        out_real, out_imag = ag.dense(terms, self.out_channels, bias=self.bias, combine=True,
-                                      relu_mode=1 if self.fused_complex_relu else 0)
+        if len(terms) <= DENSE_MAX_TERMS:
+            out_real, out_imag = ag.dense(terms, self.out_channels, bias=self.bias, combine=True,
+                                          relu_mode=1 if self.fused_complex_relu else 0)
+            return out_real, out_imag
+        # K > 7 (the reference's loop, MagNetConv.py:213-240, has no limit): the transform takes 16 terms per
+        # launch, so the Chebyshev orders are summed chunk by chunk; the complex ReLU then runs unfused
+        out_real = out_imag = None
+        for c0 in range(0, len(terms), DENSE_MAX_TERMS):
+            pr, pi = ag.dense(terms[c0:c0 + DENSE_MAX_TERMS], self.out_channels,
+                              bias=self.bias if c0 == 0 else None, combine=True)
+            out_real = pr if out_real is None else out_real + pr
+            out_imag = pi if out_imag is None else out_imag + pi
+        if self.fused_complex_relu:
+            mask = (out_real >= 0).to(out_real.dtype)
+            out_real, out_imag = out_real * mask, out_imag * mask
         return out_real, out_imag
 
     def __repr__(self):

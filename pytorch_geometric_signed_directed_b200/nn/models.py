@@ -57,6 +57,17 @@ class DiGCN_Inception_Block_node_classification(torch.nn.Module):
         return F.log_softmax(x, dim=1)
 
 
+class _LinkSignEntropyParams(torch.nn.Module):
+    """Parameter container with the names of the reference's `Link_Sign_Entropy_Loss` (utils/signed/link_sign_loss.py:
+    `lin = Linear(2 * emb_dim, 3)`), so a reference SGCN state_dict (`lsp_loss.lin.{weight,bias}`) loads with
+    strict=True.  The loss itself (PyG negative sampling on the CPU side of the training loop) is outside the hot
+    path and stays with the reference."""
+
+    def __init__(self, emb_dim: int):
+        super().__init__()
+        self.lin = torch.nn.Linear(2 * emb_dim, 3)
+
+
 class SGCN(torch.nn.Module):
     def __init__(self, node_num: int, edge_index_s: Tensor, in_dim: int = 64, out_dim: int = 64,
                  layer_num: int = 2, init_emb: Optional[Tensor] = None, init_emb_grad: bool = False,
@@ -78,6 +89,7 @@ class SGCN(torch.nn.Module):
             self.convs.append(SGCNConv(out_dim // 2, out_dim // 2, first_aggr=False, norm_emb=norm_emb))
         for conv in [self.conv1, *self.convs]:
             conv.fused_tanh = True
+        self.lsp_loss = _LinkSignEntropyParams(out_dim)       # state_dict compatibility (SGCN.py:75)
         self.reset_parameters()
 
     def reset_parameters(self):

@@ -10,7 +10,8 @@ for every node, LeakyReLU(0.2) scores) with PyG's parameter names (`lin.weight [
 
 Kernels per GATConv: `pgsd_dense_transform` (h = x W^T), `pgsd_dense_transform` with n_out = 2
 (the two attention scores per node), `pgsd_edge_softmax` (alpha per stored entry) and
-`pgsd_spmm_csr` with val = alpha (+ bias).  Forward only (the attention path has no backward yet).
+`pgsd_spmm_csr` with val = alpha (+ bias).  When gradients are required the layers run the same kernels through
+`autograd.py` (`pgsd_edge_softmax_backward`, `pgsd_sddmm_rows`, transposed aggregation).
 """
 from __future__ import annotations
 
@@ -20,7 +21,7 @@ from typing import List
 import torch
 from torch import Tensor
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, ops, plan as _plan
 from ..plan import CSRPlan
 
 
@@ -92,9 +93,29 @@ class GATConv(torch.nn.Module):
             return ops.spmm(weighted, [h], (0,), beta=1.0, zs=[accumulate_into], out=[accumulate_into])[0]
         return ops.spmm(weighted, [h], (0,), bias=self.bias, out=None if out is None else [out])[0]
 
+    def requires_grad_path(self, x: Tensor) -> bool:
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
+    def forward_train(self, x: Tensor, edge_index: Tensor) -> Tensor:
+        """The same arithmetic on the autograd path (`ag.dense` for h = x W^T and the two scores, `ag.gat_attend` for
+        softmax + weighted sum): gradients reach x, lin.weight, att_src, att_dst and bias."""
+        w = self.lin.weight.t().float()                                                   # [in, C]
+        h = ag.dense([(x, w, 0)], self.out_channels)[0]
+        att = torch.stack([self.att_src.view(-1), self.att_dst.view(-1)], dim=1).float()   # [C, 2]
+        width = 32 if x.dtype == torch.bfloat16 else 16
+        sw = torch.nn.functional.pad(w @ att, (0, width - 2))
+        s = ag.dense([(x, sw, 0)], width)[0].float()
+        p = self._plan_for(edge_index, h.size(0))
+        return ag.gat_attend(p, s[:, 0].contiguous(), s[:, 1].contiguous(), h, self.negative_slope, bias=self.bias)
+
     def forward(self, x: Tensor, edge_index: Tensor, out: Tensor = None) -> Tensor:
         """`out`: optional [N, out_channels] destination (may be a column slice of a wider buffer)."""
         _plan.require_cuda(x, "x")
+        if self.requires_grad_path(x):
+            y = self.forward_train(x, edge_index)
+            if out is not None:
+                raise RuntimeError("GATConv: preallocated outputs are not supported when gradients are required")
+            return y
         with torch.no_grad():
             h, s = gat_transforms(x, [self])
             return self.aggregate(h[0], s[0][0], s[0][1], edge_index, out)
@@ -154,6 +175,12 @@ class SDRLayer(torch.nn.Module):
         concatenation and the [N, (k+1) C] x [(k+1) C, out] transform (whose weights do not fit the tensor-core
         kernel's shared memory) never exist; the attention scores still come from h_k = x W_k^T."""
         _plan.require_cuda(x, "x")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training: the reference's own order (SDGNN.py:57-64) on the differentiable primitives
+            feats = torch.cat([x] + [agg.forward_train(x, e) for e, agg in zip(self.edge_lists, self.aggs)], dim=1)
+            l0, l2 = self.mlp_layer[0], self.mlp_layer[2]
+            hid = torch.tanh(ag.dense([(feats, l0.weight.t(), 0)], l0.out_features, bias=l0.bias)[0])
+            return ag.dense([(hid, l2.weight.t(), 0)], l2.out_features, bias=l2.bias)[0]
         with torch.no_grad():
             l0, l2 = self.mlp_layer[0], self.mlp_layer[2]
             k, fi = len(self.aggs), x.size(1)

@@ -78,6 +78,8 @@ class SGCNConv(torch.nn.Module):
         neg = self._plan_for(neg_edge_index, n_dst, n_src)
         fi, fo = self.in_dim, self.out_dim
         wb, wu = self.lin_b.weight.t(), self.lin_u.weight.t()          # [mult*in, out] views
+        if self.first_aggr and x_src is x_dst and fo <= fi and (fo * x_src.element_size()) % 16 == 0:
+            return self._first_layer_folded(x_src, pos, neg, wb, wu)
         m_pos = ag.spmm(pos, [x_src], (0,), mean=True)[0]
         m_neg = ag.spmm(neg, [x_src], (0,), mean=True)[0]
         # Both halves of the output in ONE transform launch: lin_b and lin_u become the two column blocks
@@ -100,6 +102,36 @@ class SGCNConv(torch.nn.Module):
         fuse = self.fused_tanh and not self.norm_emb and not ag._needs_grad(
             [t for t, _, _ in terms] + [self.lin_b.weight, self.lin_u.weight, bias])
         out = ag.dense(terms, 2 * fo, bias=bias, relu_mode=2 if fuse else 0)[0]
+        if self.norm_emb:
+            out = F.normalize(out, p=2, dim=-1)
+        if self.fused_tanh and not fuse:
+            out = torch.tanh(out)
+        return out
+
+    def _first_layer_folded(self, x: Tensor, pos, neg, wb: Tensor, wu: Tensor) -> Tensor:
+        """First layer with the Linear folded THROUGH the mean aggregations (both are linear):
+            out_b = mean+(x) Wb1 + x Wb2 + bb = mean+(x Wb1) + (x Wb2 + bb),   out_u likewise with mean-.
+        One transform writes [x Wb1 | x Wu1 | x Wb2 + bb | x Wu2 + bu]; each sign then aggregates its own
+        out-wide block (half the gathered bytes of aggregating x itself when out = in / 2, SGCN.py:68-73) and adds
+        the self block in the aggregation epilogue -- the [N, in] means of the reference (SGCNConv.py:100-104) and
+        their `cat` never exist.  tanh (applied by SGCN right after the layer) rides in the same epilogue."""
+        fi, fo = self.in_dim, self.out_dim
+        w = torch.cat([wb[:fi], wu[:fi], wb[fi:], wu[fi:]], 1)                 # [in, 4*out]
+        bias = None
+        if self.lin_b.bias is not None:
+            bias = torch.cat([self.lin_b.bias.new_zeros(2 * fo), self.lin_b.bias, self.lin_u.bias])
+        ps = ag.dense([(x, w, 0)], 4 * fo, bias=bias)[0]
+        grad = ag._needs_grad([ps])
+        fuse = self.fused_tanh and not self.norm_emb and not grad
+        if grad:
+            out = torch.cat([ag.spmm(pos, [ps[:, :fo]], (0,), mean=True, beta=1.0, zs=[ps[:, 2 * fo:3 * fo]])[0],
+                             ag.spmm(neg, [ps[:, fo:2 * fo]], (0,), mean=True, beta=1.0, zs=[ps[:, 3 * fo:]])[0]], 1)
+        else:
+            out = torch.empty((x.size(0), 2 * fo), dtype=x.dtype, device=x.device)
+            ops.spmm(pos, [ps[:, :fo]], (0,), mean=True, beta=1.0, zs=[ps[:, 2 * fo:3 * fo]], out=[out[:, :fo]],
+                     tanh_out=fuse)
+            ops.spmm(neg, [ps[:, fo:2 * fo]], (0,), mean=True, beta=1.0, zs=[ps[:, 3 * fo:]], out=[out[:, fo:]],
+                     tanh_out=fuse)
         if self.norm_emb:
             out = F.normalize(out, p=2, dim=-1)
         if self.fused_tanh and not fuse:

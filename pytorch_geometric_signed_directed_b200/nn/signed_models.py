@@ -4,7 +4,7 @@ Reference: nn/signed/SDGNN.py:66-260 and nn/signed/SiGAT.py:11-205 -- same const
 (`SDRLayer_{i}.agg_{k}.*`, `SDRLayer_{i}.mlp_layer.{0,2}.*`; `agg_{k}.*`, `mlp_layer.{0,2}.*`), forward() without
 arguments.  The motif mining of `build_adj_lists` (Python set loops over every edge upstream) runs on the GPU
 (`utils/signed.py` -> `pgsd_signed_triangle_counts`); the attention layers are `nn.GATConv` (edge-softmax kernel +
-aggregation kernel).  Forward only, like the attention layers themselves; `init_emb` must be given (the TSVD
+aggregation kernel); with gradients enabled the layers take their autograd path.  `init_emb` must be given (the TSVD
 initialiser is CPU preprocessing outside the hot path) and the loss modules stay with the reference.
 """
 from __future__ import annotations
@@ -14,7 +14,7 @@ from typing import List, Optional
 import torch
 from torch import Tensor
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, ops, plan as _plan
 from ..utils import signed as _signed
 from .sdr_layer import GATConv, SDRLayer, gat_transforms
 
@@ -107,6 +107,12 @@ class SiGAT(torch.nn.Module):
     def forward(self) -> Tensor:
         x = self.x
         _plan.require_cuda(x, "x")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: SiGAT.py:190-199 on the differentiable primitives
+            feats = torch.cat([x] + [agg.forward_train(x, e) for e, agg in zip(self.edge_lists, self.aggs)], dim=1)
+            l0, l2 = self.mlp_layer[0], self.mlp_layer[2]
+            hid = torch.tanh(ag.dense([(feats, l0.weight.t(), 0)], l0.out_features, bias=l0.bias)[0])
+            return ag.dense([(hid, l2.weight.t(), 0)], l2.out_features, bias=l2.bias)[0]
         with torch.no_grad():
             n, k, c = x.size(0), len(self.aggs), self.out_dim
             # cat([x0] + neigh_feats) (SiGAT.py:196-197) is the layout of one wide buffer: every GATConv writes

@@ -10,6 +10,8 @@ feature x_p[i] * alpha_e (quirk Q7), so  out[i] = x_0[i] * sum_{type 0} alpha + 
 sum_{type 1} alpha.  Here the Linear splits into two per-node scalars (s_src = X a_j,
 s_dst = X a_i + c), computed by `pgsd_dense_transform`, and `pgsd_edge_softmax` does the
 per-row softmax sums -- scalar gathers instead of the reference's [nnz, 2*out] temporaries.
+Training: when gradients are required the same kernels run under `autograd.py`'s Functions
+(`pgsd_edge_softmax_backward` for the attention, the transform's own backward for the Linears).
 Edge bookkeeping follows the reference exactly: self-loops are removed, then re-added for the
 nodes 0..max(remaining edge ids) only (add_self_loops without num_nodes, :88-89,110-111);
 negative edges never get self-loops in the deep layer (:112).
@@ -21,7 +23,7 @@ from typing import Tuple, Union
 import torch
 from torch import Tensor
 
-from .. import ops, plan as _plan
+from .. import autograd as ag, ops, plan as _plan
 
 
 class SNEAConv(torch.nn.Module):
@@ -88,7 +90,37 @@ class SNEAConv(torch.nn.Module):
         ss = [(s_all[:, 2 * i].contiguous(), s_all[:, 2 * i + 1].contiguous()) for i in range(k)]
         return hs, ss
 
+    def _transforms_train(self, x: Tensor, specs):
+        """The same two launches on the autograd path: the block-structured weights are assembled with differentiable
+        torch ops (pads and sums of the layer's own parameters, a few KB), the launches are `ag.dense`."""
+        fi, fo = self.in_dim, self.out_dim
+        k, kin = len(specs), x.size(1)
+        width = 16 if 2 * k <= 16 else 32
+        pad = torch.nn.functional.pad
+        w_all = b_all = sw = sb = None
+        add = lambda acc, t: t if acc is None else acc + t
+        for i, (lin, c0, alpha_lin) in enumerate(specs):
+            wt = lin.weight.t().float()                                              # [in, out]
+            a = alpha_lin.weight.view(2, fo).t().float()                             # [out, 2]: (a_j, a_i)
+            rows = (0, 0, c0, kin - c0 - fi)                                         # place rows c0 .. c0+in
+            w_all = add(w_all, pad(wt, (i * fo, (k - 1 - i) * fo) + rows[2:]))
+            sw = add(sw, pad(wt @ a, (2 * i, width - 2 * i - 2) + rows[2:]))
+            bvec = lin.bias.float() if lin.bias is not None else wt.new_zeros(fo)
+            b_all = add(b_all, pad(bvec, (i * fo, (k - 1 - i) * fo)))
+            sc = bvec @ a + pad(alpha_lin.bias.float().view(1), (1, 0))               # (b.a_j, b.a_i + c)
+            sb = add(sb, pad(sc, (2 * i, width - 2 * i - 2)))
+        h_all = ag.dense([(x, w_all, 0)], k * fo, bias=b_all)[0]
+        s_all = ag.dense([(x, sw, 0)], width, bias=sb)[0]
+        hs = [h_all[:, i * fo:(i + 1) * fo] for i in range(k)]
+        ss = [(s_all[:, 2 * i].contiguous(), s_all[:, 2 * i + 1].contiguous()) for i in range(k)]
+        return hs, ss
+
+    def _needs_grad(self, x: Tensor) -> bool:
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
     def _attend(self, plans, hs, ss) -> Tensor:
+        if ag._needs_grad(list(hs) + [t for pair in ss for t in pair]):
+            return ag.edge_softmax_sum(plans, [s[0] for s in ss], [s[1] for s in ss], list(hs), act="tanh")
         y, _ = ops.edge_softmax(plans, [s[0] for s in ss], [s[1] for s in ss], act="tanh", xd=hs)
         return y
 
@@ -98,15 +130,17 @@ class SNEAConv(torch.nn.Module):
             raise NotImplementedError("SNEAConv kernels take a single feature tensor")
         _plan.require_cuda(x, "x")
         n = x.size(0)
-        with torch.no_grad():
+        train = self._needs_grad(x)
+        transforms = self._transforms_train if train else self._transforms
+        with torch.enable_grad() if train else torch.no_grad():
             if self.first_aggr:
-                hs, ss = self._transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_u, 0, self.alpha_u)])
+                hs, ss = transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_u, 0, self.alpha_u)])
                 out_b = self._attend([self._plan_for(pos_edge_index, n, True)], hs[:1], ss[:1])
                 out_u = self._attend([self._plan_for(neg_edge_index, n, True)], hs[1:], ss[1:])
             else:
                 fi = self.in_dim                       # x = [h_b | h_u]
-                hs, ss = self._transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_b, fi, self.alpha_b),
-                                              (self.lin_u, fi, self.alpha_u), (self.lin_u, 0, self.alpha_u)])
+                hs, ss = transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_b, fi, self.alpha_b),
+                                        (self.lin_u, fi, self.alpha_u), (self.lin_u, 0, self.alpha_u)])
                 plans = [self._plan_for(pos_edge_index, n, True), self._plan_for(neg_edge_index, n, False)]
                 out_b = self._attend(plans, hs[:2], ss[:2])
                 out_u = self._attend(plans, hs[2:], ss[2:])

@@ -75,7 +75,7 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
          alpha: float = 1.0, beta: float = 0.0, zs: Optional[Sequence[Tensor]] = None,
          bias: Optional[Tensor] = None, out: Optional[Sequence[Tensor]] = None,
          variant: Optional[int] = None, op_scale: Optional[Sequence[float]] = None,
-         grid_reserve: int = 0) -> List[Tensor]:
+         grid_reserve: int = 0, tanh_out: bool = False) -> List[Tensor]:
     """y_k = alpha * (diag_k x_k[r] + sum val_k x_k[col]) (/len if mean) + beta * z_k + bias
     for the plan operators listed in `ops` (1 or 2 of them), one kernel launch.
     xs/zs/out may be column slices of wider row-major buffers.  grid_reserve = resident-CTA slots
@@ -87,7 +87,7 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
     feat, dt = xs[0].size(1), _dtype_code(xs[0])
     dev = xs[0].device
     a = _lib.SpmmArgs()
-    a.n_rows, a.feat, a.n_ops, a.dtype, a.mean = plan.n_dst, feat, n_ops, dt, int(mean)
+    a.n_rows, a.feat, a.n_ops, a.dtype, a.mean = plan.n_dst, feat, n_ops, dt, int(mean) | (2 if tanh_out else 0)
     a.row_ptr, a.col = plan.row_ptr.data_ptr(), plan.col.data_ptr()
     a.alpha, a.beta = float(alpha), float(beta)
     a.variant = SPMM_VARIANT if variant is None else variant
@@ -97,6 +97,8 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
         for k, sc in enumerate(op_scale):
             a.op_scale[k] = float(sc)
     hubs = plan.hub_rows()
+    if tanh_out and hubs is not None:
+        raise ValueError("spmm: the tanh epilogue cannot be combined with hub rows (their sums arrive by atomics)")
     if hubs is not None and dt == _lib.PGSD_F32:
         a.long_rows, a.long_chunk_ptr = hubs[0].data_ptr(), hubs[1].data_ptr()
         a.n_long_rows, a.long_row_threshold, a.long_chunk = hubs[0].numel(), HUB_ROW_THRESHOLD, HUB_ROW_CHUNK
@@ -118,6 +120,9 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
         a.x[k], a.ldx[k] = x.data_ptr(), x.stride(0)
         if zs is not None and zs[k] is not None:
             z = _rows2d(zs[k].detach(), "z")
+            if z.dtype != x.dtype or z.size(0) < plan.n_dst or z.size(1) != feat:
+                raise ValueError(f"spmm: z[{k}] must be [{plan.n_dst}+, {feat}] of {x.dtype}, got "
+                                 f"{tuple(z.shape)} of {z.dtype}")
             keep.append(z)
             a.z[k], a.ldz[k] = z.data_ptr(), z.stride(0)
         if out is not None and out[k] is not None:
@@ -130,6 +135,8 @@ def spmm(plan: CSRPlan, xs: Sequence[Tensor], ops: Sequence[int] = (0,), *, mean
         outs.append(y)
     if bias is not None:
         b = bias.detach().float().contiguous()
+        if b.numel() < feat:
+            raise ValueError(f"spmm: bias has {b.numel()} entries, the rows are {feat} wide")
         keep.append(b)
         a.bias = b.data_ptr()
     lib = _lib.load()
@@ -172,6 +179,8 @@ def dense(terms: Sequence[Tuple[Tensor, Tensor, int]], n_out: int, *, bias: Opti
         a.w[t], a.ldw_k[t], a.ldw_n[t] = w.data_ptr(), w.stride(0), w.stride(1)
     if bias is not None:
         b = bias.detach().float().contiguous()
+        if b.numel() < n_out:
+            raise ValueError(f"dense: bias has {b.numel()} entries, n_out = {n_out}")
         keep.append(b)
         a.bias = b.data_ptr()
     n_outs = 2 if combine else 1
@@ -312,6 +321,80 @@ def edge_softmax(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Seque
                    "pgsd_edge_softmax")
     LAUNCHES += 1
     return y, alphas
+
+
+def edge_softmax_backward(plans: Sequence[CSRPlan], s_src: Sequence[Tensor], s_dst: Sequence[Tensor], *,
+                          act: str = "tanh", slope: float = 0.2, dalpha: Optional[Sequence[Tensor]] = None,
+                          row_coef: Optional[Sequence[Tensor]] = None, want_type_sum: bool = False):
+    """Backward of the segment softmax (`pgsd_edge_softmax_backward`): dL/dalpha per entry (`dalpha[t]`, GAT-style)
+    or per row and type (`row_coef[t]`, SNEAConv) -> (g_s_src [n_src] per type, g_s_dst [n_dst] per type,
+    per-row sums of alpha per type or None)."""
+    global LAUNCHES
+    n_types = len(plans)
+    assert n_types in (1, 2) and (dalpha is None) != (row_coef is None)
+    dev = plans[0].device
+    a = _lib.AttnBwdArgs()
+    a.n_rows, a.n_types = plans[0].n_dst, n_types
+    a.act, a.slope = (0 if act == "tanh" else 1), float(slope)
+    keep, g_src, g_dst, sums = [], [], [], []
+    for t in range(n_types):
+        ss = s_src[t].detach().float().contiguous().view(-1)
+        sd = s_dst[t].detach().float().contiguous().view(-1)
+        if ss.numel() < plans[t].n_src or sd.numel() < plans[t].n_dst:
+            raise ValueError("edge_softmax_backward: score vectors shorter than the plan's node ranges")
+        gs = torch.zeros(ss.numel(), dtype=torch.float32, device=dev)
+        gd = torch.zeros(sd.numel(), dtype=torch.float32, device=dev)
+        keep += [ss, sd]
+        a.row_ptr[t], a.col[t] = plans[t].row_ptr.data_ptr(), plans[t].col.data_ptr()
+        a.s_src[t], a.s_dst[t] = ss.data_ptr(), sd.data_ptr()
+        a.g_s_src[t], a.g_s_dst[t] = gs.data_ptr(), gd.data_ptr()
+        if dalpha is not None:
+            da = dalpha[t].detach().float().contiguous().view(-1)
+            if da.numel() < plans[t].nnz:
+                raise ValueError("edge_softmax_backward: dalpha shorter than the plan's entry list")
+            keep.append(da)
+            a.dalpha[t] = da.data_ptr() if da.numel() else None
+            if not da.numel():                      # a plan without entries: nothing to read, coefficient 0
+                a.row_coef[t] = gd.data_ptr()
+        else:
+            rc = row_coef[t].detach().float().contiguous().view(-1)
+            keep.append(rc)
+            a.row_coef[t] = rc.data_ptr()
+        if want_type_sum:
+            sm = torch.zeros(plans[t].n_dst, dtype=torch.float32, device=dev)
+            a.type_sum[t] = sm.data_ptr()
+            sums.append(sm)
+        g_src.append(gs)
+        g_dst.append(gd)
+    lib = _lib.load()
+    with torch.cuda.device(dev), _Timed("edge_softmax_bwd", dev):
+        _lib.check(lib.pgsd_edge_softmax_backward(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
+                   "pgsd_edge_softmax_backward")
+    LAUNCHES += 1
+    return g_src, g_dst, (sums if want_type_sum else None)
+
+
+def sddmm_rows(plan: CSRPlan, gy: Tensor, h: Tensor) -> Tensor:
+    """out[k] = <gy[row(k)], h[col[k]]> for every stored entry (`pgsd_sddmm_rows`); fp32.  Shapes the kernel does
+    not take (feature width not a multiple of 4, unaligned rows) are evaluated with torch gathers."""
+    global LAUNCHES
+    gy, h = _rows2d(gy.detach(), "gy"), _rows2d(h.detach(), "h")
+    f = gy.size(1)
+    out = torch.empty(max(plan.nnz, 1), dtype=torch.float32, device=gy.device)[:plan.nnz]
+    if plan.nnz == 0:
+        return out
+    ok = lambda t: t.dtype == torch.float32 and t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0
+    if f % 4 or f > 256 or not (ok(gy) and ok(h)):
+        counts = (plan.row_ptr[1:] - plan.row_ptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(plan.n_dst, device=gy.device), counts)
+        return (gy.float()[rows] * h.float()[plan.col.long()]).sum(1)
+    lib = _lib.load()
+    with torch.cuda.device(gy.device), _Timed("sddmm", gy.device):
+        _lib.check(lib.pgsd_sddmm_rows(plan.row_ptr.data_ptr(), plan.col.data_ptr(), gy.data_ptr(), gy.stride(0),
+                                       h.data_ptr(), h.stride(0), plan.n_dst, f, out.data_ptr(),
+                                       torch.cuda.current_stream(gy.device).cuda_stream), "pgsd_sddmm_rows")
+    LAUNCHES += 1
+    return out
 
 
 # 1: GATConv aggregates with the softmax inside one kernel (pgsd_gat_aggregate); 0 (default): edge_softmax +

@@ -191,3 +191,99 @@ def test_trainable_q_gradient_wide_rows():
         p_r, p_i = port.magnet_conv(xr, xi, ei, ew, conv.weight.detach().cpu(), conv.bias.detach().cpu(), q, "sym")
         ((p_r * r1).sum() + (p_i * r2).sum()).backward()
         assert_close_rel(conv.q.grad, q.grad, 2e-4, f"d q, F={f}")
+
+
+# ------------------------------------------------------------------ attention layers
+def _snea_params(m):
+    return [m.lin_b.weight, m.lin_b.bias, m.lin_u.weight, m.lin_u.bias,
+            m.alpha_b.weight, m.alpha_b.bias, m.alpha_u.weight, m.alpha_u.bias]
+
+
+@pytest.mark.parametrize("fin,fout", [(64, 32), (12, 8), (6, 5)])
+def test_snea_two_layer_gradients(fin, fout):
+    """Training through SNEAConv (nn/signed/SNEAConv.py:81-146): gradients of a two-layer stack w.r.t. the input and
+    every parameter (lin_b / lin_u / alpha_b / alpha_u) against torch autograd of the oracle."""
+    n = 3000
+    pos, neg, _ = synthetic.ssbm_edges(n, 3, num_entries=50_000, eta=0.1, seed=7)
+    g = torch.Generator().manual_seed(fin)
+    x = torch.randn(n, fin, generator=g)
+    r = torch.randn(n, 2 * fout, generator=g)
+    torch.manual_seed(fin + 1)
+    c1 = nn.SNEAConv(fin, fout, first_aggr=True).to(DEV)
+    c2 = nn.SNEAConv(fout, fout, first_aggr=False).to(DEV)
+    w1 = [_leaf(t.cpu()) for t in _snea_params(c1)]
+    w2 = [_leaf(t.cpu()) for t in _snea_params(c2)]
+    cx = _leaf(x)
+    ref = port.snea_conv(torch.tanh(port.snea_conv(cx, pos, neg, *w1, True)), pos, neg, *w2, False)
+    (ref * r).sum().backward()
+    dx = _leaf(x, DEV)
+    out = c2(torch.tanh(c1(dx, pos.to(DEV), neg.to(DEV))), pos.to(DEV), neg.to(DEV))
+    (out * r.to(DEV)).sum().backward()
+    assert_close_rel(out, ref, 1e-5, "forward")
+    assert_close_rel(dx.grad, cx.grad, TOL, "d x")
+    names = ["lin_b.weight", "lin_b.bias", "lin_u.weight", "lin_u.bias", "alpha_b.weight", "alpha_b.bias",
+             "alpha_u.weight", "alpha_u.bias"]
+    for layer, conv, ws in ((1, c1, w1), (2, c2, w2)):
+        for nm, p, w in zip(names, _snea_params(conv), ws):
+            if layer == 1 and nm.startswith("alpha"):
+                # first layer: one edge type per softmax, the weights of a row sum to 1 -> zero gradient (both sides)
+                assert float(p.grad.abs().max()) <= 1e-3 and float(w.grad.abs().max()) <= 1e-3
+                continue
+            assert_close_rel(p.grad, w.grad, TOL, f"layer {layer} d {nm}")
+
+
+@pytest.mark.parametrize("n,e,c", [(3000, 40_000, 64), (2000, 15_000, 12), (700, 5_000, 10)])
+def test_gat_conv_gradients(n, e, c):
+    """Training through the GATConv of SDGNN / SiGAT (nn/signed/SDGNN.py:35-41): edge-softmax backward + SDDMM +
+    transposed weighted aggregation against torch autograd of the oracle's GATConv."""
+    g = torch.Generator().manual_seed(n + c)
+    ei = torch.randint(0, n - 5, (2, e), generator=g)
+    ei[1, :300] = 2
+    x = torch.randn(n, c, generator=g)
+    r = torch.randn(n, c, generator=g)
+    gat = nn.GATConv(c, c).to(DEV)
+    with torch.no_grad():
+        gat.bias.uniform_(-0.3, 0.3)
+    prm = [gat.lin.weight, gat.att_src, gat.att_dst, gat.bias]
+    ws = [_leaf(t.cpu()) for t in prm]
+    cx = _leaf(x)
+    ref = port.gat_conv(cx, ei, ws[0], ws[1].view(-1), ws[2].view(-1), ws[3])
+    (ref * r).sum().backward()
+    dx = _leaf(x, DEV)
+    out = gat(dx, ei.to(DEV))
+    (out * r.to(DEV)).sum().backward()
+    assert_close_rel(out, ref, 1e-5, "forward")
+    assert_close_rel(dx.grad, cx.grad, TOL, "d x")
+    for nm, p, w in zip(("lin.weight", "att_src", "att_dst", "bias"), prm, ws):
+        assert_close_rel(p.grad, w.grad.view_as(p.grad), TOL, f"d {nm}")
+
+
+def test_sdr_layer_gradients_and_training_step():
+    """SDRLayer (4 GATConv + MLP, nn/signed/SDGNN.py:57-64): gradients against the oracle, and an optimiser step
+    changes the attention parameters (the layers used to return detached tensors)."""
+    gen = torch.Generator().manual_seed(21)
+    n, c = 1500, 12
+    lists = [torch.randint(0, n, (2, 9000), generator=gen) for _ in range(4)]
+    x = torch.randn(n, c, generator=gen)
+    r = torch.randn(n, c, generator=gen)
+    layer = nn.SDRLayer(c, c, [e.to(DEV) for e in lists]).to(DEV)
+    gp = [[_leaf(t.cpu()) for t in (a.lin.weight, a.att_src, a.att_dst, a.bias)] for a in layer.aggs]
+    l0, l2 = layer.mlp_layer[0], layer.mlp_layer[2]
+    mp = [_leaf(t.cpu()) for t in (l0.weight, l0.bias, l2.weight, l2.bias)]
+    cx = _leaf(x)
+    ref = port.sdr_layer(cx, lists, [(w, a.view(-1), b.view(-1), bb) for w, a, b, bb in gp], *mp)
+    (ref * r).sum().backward()
+    dx = _leaf(x, DEV)
+    out = layer(dx)
+    assert out.requires_grad
+    (out * r.to(DEV)).sum().backward()
+    assert_close_rel(out, ref, 1e-5, "forward")
+    assert_close_rel(dx.grad, cx.grad, TOL, "d x")
+    for k, (a, ws) in enumerate(zip(layer.aggs, gp)):
+        for nm, p, w in zip(("lin.weight", "att_src", "att_dst", "bias"), (a.lin.weight, a.att_src, a.att_dst, a.bias), ws):
+            assert_close_rel(p.grad, w.grad.view_as(p.grad), TOL, f"agg_{k} d {nm}")
+    for nm, p, w in zip(("mlp0.weight", "mlp0.bias", "mlp2.weight", "mlp2.bias"), (l0.weight, l0.bias, l2.weight, l2.bias), mp):
+        assert_close_rel(p.grad, w.grad, TOL, f"d {nm}")
+    before = layer.aggs[0].att_src.detach().clone()
+    torch.optim.SGD(layer.parameters(), lr=0.1).step()
+    assert not torch.equal(before, layer.aggs[0].att_src.detach())

@@ -57,13 +57,17 @@ def test_sdgnn_and_sigat_models_golden():
     m = nn.SDGNN(90, g["edge_index_s"], in_dim=12, out_dim=12, layer_num=2, init_emb=g["x"].clone()).to(DEV).eval()
     m.load_state_dict({k.replace("__", "."): v for k, v in g.items()
                        if k.startswith(("SDRLayer_", "x"))})
-    assert_close_rel(m(), g["out"], 1e-5)
+    assert_close_rel(m(), g["out"], 1e-5, "SDGNN autograd path")
+    with torch.no_grad():
+        assert_close_rel(m(), g["out"], 1e-5, "SDGNN inference path")
     tw = m.tri_weight
     assert tw.shape == (90, 90) and int(tw.sum()) == int(g["tri_val"].sum())
     s = load_golden("sigat_model", DEV)
     sm = nn.SiGAT(90, s["edge_index_s"], in_dim=12, out_dim=12, init_emb=s["x"].clone()).to(DEV).eval()
     sm.load_state_dict({k.replace("__", "."): v for k, v in s.items() if k.startswith(("agg_", "mlp_layer", "x"))})
-    assert_close_rel(sm(), s["out"], 1e-5)
+    assert_close_rel(sm(), s["out"], 1e-5, "SiGAT autograd path")
+    with torch.no_grad():
+        assert_close_rel(sm(), s["out"], 1e-5, "SiGAT inference path")
     # widths the vector kernels cannot write in place (out_dim = 10: 40-byte column blocks)
     torch.manual_seed(0)
     odd = nn.SiGAT(90, s["edge_index_s"], in_dim=10, out_dim=10, init_emb=torch.randn(90, 10, device=DEV)).to(DEV).eval()
@@ -72,6 +76,8 @@ def test_sdgnn_and_sigat_models_golden():
     ref = port.sigat_forward(odd.x.detach().cpu(), [e.cpu() for e in odd.edge_lists], params,
                              odd.mlp_layer[0].weight.detach().cpu(), odd.mlp_layer[0].bias.detach().cpu(),
                              odd.mlp_layer[2].weight.detach().cpu(), odd.mlp_layer[2].bias.detach().cpu())
-    assert_close_rel(odd(), ref, 1e-5)
+    assert_close_rel(odd(), ref, 1e-5, "odd width, autograd path")
+    with torch.no_grad():
+        assert_close_rel(odd(), ref, 1e-5, "odd width, inference path")
     with pytest.raises(NotImplementedError):
         nn.SiGAT(90, s["edge_index_s"])

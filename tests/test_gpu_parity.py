@@ -228,8 +228,14 @@ def test_sgcn_two_layer_vs_oracle_wide():
     x = torch.randn(n, 64, generator=gen)
     c1 = nn.SGCNConv(64, 32, first_aggr=True).to(DEV)
     c2 = nn.SGCNConv(32, 32, first_aggr=False).to(DEV)
-    z1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))
-    z2 = c2(torch.tanh(z1), pos.to(DEV), neg.to(DEV))
+    with torch.no_grad():
+        z1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))
+        z2 = c2(torch.tanh(z1), pos.to(DEV), neg.to(DEV))
+    t1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))                          # autograd path, same numbers
+    t2 = c2(torch.tanh(t1), pos.to(DEV), neg.to(DEV))
+    assert t2.requires_grad
+    assert_close_rel(t1, z1, 2e-6, "layer 1: autograd path vs inference path")
+    assert_close_rel(t2, z2, 2e-6, "layer 2: autograd path vs inference path")
     cpu = lambda m: [m.lin_b.weight.detach().cpu(), m.lin_b.bias.detach().cpu(),
                      m.lin_u.weight.detach().cpu(), m.lin_u.bias.detach().cpu()]
     r1 = port.sgcn_conv(x, pos, neg, *cpu(c1), True)
@@ -418,8 +424,13 @@ def _make_snea(g, first):
 @pytest.mark.parametrize("name,first", [("snea_first", True), ("snea_second", False)])
 def test_snea_golden(name, first):
     g = load_golden(name, DEV)
-    y = _make_snea(g, first)(g["x"], g["pos_edge_index"], g["neg_edge_index"])
-    assert_close_rel(y, g["out"], 1e-5)
+    conv = _make_snea(g, first)
+    y = conv(g["x"], g["pos_edge_index"], g["neg_edge_index"])          # parameters require grad: autograd path
+    assert y.requires_grad
+    assert_close_rel(y, g["out"], 1e-5, "autograd path")
+    with torch.no_grad():                                                 # inference path (raw kernels)
+        y = conv(g["x"], g["pos_edge_index"], g["neg_edge_index"])
+    assert_close_rel(y, g["out"], 1e-5, "inference path")
 
 
 def test_snea_two_layer_vs_oracle_wide():
@@ -429,8 +440,14 @@ def test_snea_two_layer_vs_oracle_wide():
     torch.manual_seed(3)
     c1 = nn.SNEAConv(64, 32, first_aggr=True).to(DEV)
     c2 = nn.SNEAConv(32, 32, first_aggr=False).to(DEV)
-    z1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))
-    z2 = c2(torch.tanh(z1), pos.to(DEV), neg.to(DEV))
+    with torch.no_grad():
+        z1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))
+        z2 = c2(torch.tanh(z1), pos.to(DEV), neg.to(DEV))
+    t1 = c1(x.to(DEV), pos.to(DEV), neg.to(DEV))                          # autograd path, same numbers
+    t2 = c2(torch.tanh(t1), pos.to(DEV), neg.to(DEV))
+    assert t2.requires_grad
+    assert_close_rel(t1, z1, 2e-6, "layer 1: autograd path vs inference path")
+    assert_close_rel(t2, z2, 2e-6, "layer 2: autograd path vs inference path")
     cpu = lambda m: [t.detach().cpu() for t in (m.lin_b.weight, m.lin_b.bias, m.lin_u.weight, m.lin_u.bias,
                                                 m.alpha_b.weight, m.alpha_b.bias, m.alpha_u.weight, m.alpha_u.bias)]
     r1 = port.snea_conv(x, pos, neg, *cpu(c1), True)
@@ -555,7 +572,9 @@ def test_sdr_layer_golden_and_wide():
     layer = nn.SDRLayer(12, 12, lists).to(DEV)
     layer.load_state_dict({k.replace("__", "."): v for k, v in g.items()
                            if k not in ("x", "out") and not k.startswith("edges_")})
-    assert_close_rel(layer(g["x"]), g["out"], 1e-5)
+    assert_close_rel(layer(g["x"]), g["out"], 1e-5, "autograd path")
+    with torch.no_grad():
+        assert_close_rel(layer(g["x"]), g["out"], 1e-5, "inference path (Linear folded through the aggregations)")
     # a GATConv on its own against the oracle at a width the vector kernels take
     gen = torch.Generator().manual_seed(12)
     n = 4000
@@ -564,10 +583,11 @@ def test_sdr_layer_golden_and_wide():
     conv = nn.GATConv(64, 64).to(DEV)
     with torch.no_grad():
         conv.bias.uniform_(-0.2, 0.2)
-    y = conv(x.to(DEV), ei.to(DEV))
     ref = port.gat_conv(x, ei, conv.lin.weight.detach().cpu(), conv.att_src.detach().cpu(),
                         conv.att_dst.detach().cpu(), conv.bias.detach().cpu())
-    assert_close_rel(y, ref, 1e-5)
+    assert_close_rel(conv(x.to(DEV), ei.to(DEV)), ref, 1e-5, "autograd path")
+    with torch.no_grad():
+        assert_close_rel(conv(x.to(DEV), ei.to(DEV)), ref, 1e-5, "inference path")
 
 
 def test_magnet_bf16_features():
@@ -854,6 +874,7 @@ def test_gat_aggregation_with_inkernel_softmax(n, e, c):
                         gat.att_dst.detach().cpu().view(-1), gat.bias.detach().cpu())
     xd, eid = x.to(DEV), ei.to(DEV)
     old = ops.GAT_FUSED
+    torch.set_grad_enabled(False)              # the inference kernels (with gradients the layer takes autograd.py)
     try:
         ops.GAT_FUSED = 1
         fused = gat(xd, eid)
@@ -865,6 +886,7 @@ def test_gat_aggregation_with_inkernel_softmax(n, e, c):
         two = gat(xd, eid)
     finally:
         ops.GAT_FUSED = old
+        torch.set_grad_enabled(True)
     assert_close_rel(fused, ref, 1e-5, "fused vs oracle")
     assert_close_rel(fused, two, 2e-6, "fused vs two-kernel route")
     assert_close_rel(acc - acc0, fused - gat.bias.detach(), 2e-6, "accumulating epilogue")
