@@ -198,7 +198,8 @@ typedef struct pgsd_spmm_args {
   int32_t variant;           /* 0 = library default; bits 0-3 loads in flight (2/4/8), 0x10 /
                                 0x20 prefer 128- / 256-bit gathers, 0x80 warp-per-row kernel
                                 instead of the default group-per-row kernel, 0x400 gather twice
-                                even when both operators read one tensor (A/B timing); bits 12-14:
+                                even when both operators read one tensor (A/B timing); 0x800 bulk-copy (TMA)
+                                gathers + segmented reduction (fp32 rows of 128/256/512 bytes); bits 12-14:
                                 preferred shared-memory carve-out of the launch in steps of 14 % of
                                 the SM's 228 KB (0 = driver default), so that a kernel which needs
                                 shared memory (bulk-copy shard push) can be co-resident            */

@@ -17,7 +17,7 @@
 // warp shuffles; the G partial sums are combined with an xor-shuffle tree at the end of the
 // row.  Feature gathers carry an L2 evict_last policy (each x row is re-read ~deg times and
 // x is 4x larger than L2 at the north-star size); index/value/output streams carry evict_first.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pgsd {
 
@@ -396,6 +396,166 @@ __global__ void __launch_bounds__(THREADS, MINB) spmm_groups_kernel(const SpmmPa
   }
 }
 
+// ---- bulk-copy (TMA) gather variant: the north-star's "TMA-staged feature tiles + warp-level segmented reduction" ------
+// Every neighbour row travels global -> shared memory as ONE cp.async.bulk (row_bytes, 128..512) onto an mbarrier instead
+// of LPR register loads; a warp owns a contiguous range of destination rows and walks its ENTRY stream in batches of
+// B entries regardless of row boundaries (segmented reduction: the lanes split the feature columns, so a row is finished
+// by a warp-uniform flush, no cross-lane reduction), S batches in flight per warp.  Selected by variant bit 0x800 (fp32,
+// row_bytes % 128 == 0, no hub rows); kept for the measurement recorded in DESIGN.md 4.1 / tools/sweep_spmm.py -- the
+// register-gather kernels above stay the default.
+template <int NOPS, int EPL>
+__global__ void __launch_bounds__(256) spmm_bulk_kernel(const SpmmParams p, const int row_bytes, const int rows_per_chunk) {
+  constexpr int B = 16, S = 3;
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = uint32_t(B) * NOPS * row_bytes;
+  const uint32_t tiles = tc::smem_u32(bulk_smem) + uint32_t(warp) * S * stage_bytes;
+  const uint32_t bars = tc::smem_u32(bulk_smem) + 8u * S * stage_bytes + uint32_t(warp) * S * 8;
+  if (lane == 0)
+    for (int i = 0; i < S; ++i) tc::mbar_init(bars + 8 * i, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const uint64_t pol_stream = policy_evict_first();
+  const int64_t n_chunks = (p.n_rows + rows_per_chunk - 1) / rows_per_chunk;
+  const int64_t warps_total = int64_t(gridDim.x) * 8;
+  uint32_t n_issued = 0, n_done = 0;                       // batches issued / consumed by this warp (ring position)
+
+  for (int64_t ck = int64_t(blockIdx.x) * 8 + warp; ck < n_chunks; ck += warps_total) {
+    const int64_t r0 = ck * rows_per_chunk;
+    const int64_t r1 = (r0 + rows_per_chunk < p.n_rows) ? r0 + rows_per_chunk : p.n_rows;
+    const int e0 = __ldg(p.row_ptr + r0), e1 = __ldg(p.row_ptr + r1);
+    // issue batch `b` (entries [e0 + b*B, ...)): lane l < cnt*NOPS copies entry l % B of operand l / B
+    auto issue = [&](int b) {
+      const int base = e0 + b * B;
+      const int cnt = min(B, e1 - base);
+      const uint32_t st = n_issued % S;
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + 8 * st),
+                     "r"(uint32_t(cnt) * NOPS * row_bytes)
+                     : "memory");
+      __syncwarp();
+      const int j = lane % B, k = lane / B;
+      if (j < cnt && k < NOPS) {
+        const int c = ld_stream_i32(p.col + base + j, pol_stream);
+        const char* src = row_addr(p.x[k], c, uint32_t(p.ldx_bytes[k]));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         tiles + st * stage_bytes + uint32_t(k * B + j) * row_bytes),
+                     "l"(src), "r"(uint32_t(row_bytes)), "r"(bars + 8 * st)
+                     : "memory");
+      }
+      ++n_issued;
+    };
+    const int n_batches = (e1 - e0 + B - 1) / B;
+    for (int b = 0; b < min(n_batches, S - 1); ++b) issue(b);
+
+    int64_t row = r0;
+    int row_end = __ldg(p.row_ptr + row + 1), row_start = e0;
+    float acc[NOPS][EPL];
+#pragma unroll
+    for (int k = 0; k < NOPS; ++k)
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) acc[k][i] = 0.f;
+    auto flush = [&]() {                                    // finishes `row` (warp-uniform)
+      const float inv = p.mean ? 1.f / float(max(row_end - row_start, 1)) : 1.f;
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k) {
+        const bool has_diag = p.diag[k] != nullptr;
+        const float dg = has_diag ? __ldg(p.diag[k] + row) : p.diag_const[k];
+        float out[EPL];
+        if (has_diag || dg != 0.f) {
+          const float* xr = reinterpret_cast<const float*>(p.x[k] + (row + p.diag_row_offset) * p.ldx_bytes[k]) + lane * EPL;
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(dg, __ldg(xr + i), acc[k][i]);
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) out[i] = p.alpha_op[k] * (acc[k][i] * inv);
+        if (p.z[k] != nullptr) {
+          const float* zr = reinterpret_cast<const float*>(p.z[k] + row * p.ldz_bytes[k]) + lane * EPL;
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] = fmaf(p.beta, zr[i], out[i]);
+        }
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] += __ldg(p.bias + lane * EPL + i);
+        }
+        if (p.tanh_out) {
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) out[i] = tanhf(out[i]);
+        }
+        float* y = reinterpret_cast<float*>(p.y[k] + row * p.ldy_bytes[k]) + lane * EPL;
+        if constexpr (EPL == 4) *reinterpret_cast<float4*>(y) = make_float4(out[0], out[1], out[2], out[3]);
+        else if constexpr (EPL == 2) *reinterpret_cast<float2*>(y) = make_float2(out[0], out[1]);
+        else y[0] = out[0];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) acc[k][i] = 0.f;
+      }
+      ++row;
+      row_start = row_end;
+      if (row < r1) row_end = __ldg(p.row_ptr + row + 1);
+    };
+
+    int e = e0;
+    for (int b = 0; b < n_batches; ++b) {
+      if (b + S - 1 < n_batches) issue(b + S - 1);
+      const int base = e0 + b * B;
+      const int cnt = min(B, e1 - base);
+      float v[NOPS];
+#pragma unroll
+      for (int k = 0; k < NOPS; ++k)
+        v[k] = (lane < cnt && p.val[k]) ? ld_stream_f32(p.val[k] + base + lane, pol_stream) : 1.f;
+      const uint32_t st = n_done % S;
+      tc::mbar_wait(bars + 8 * st, (n_done / S) & 1u);
+      const uint32_t tile = tiles + st * stage_bytes + uint32_t(lane) * (EPL * 4);
+      for (int j = 0; j < cnt; ++j, ++e) {
+        while (e == row_end) flush();                       // also walks over empty rows
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k) {
+          const float vj = __shfl_sync(FULL, v[k], j);
+          const uint32_t a = tile + uint32_t(k * B + j) * row_bytes;
+          float d[EPL];
+          if constexpr (EPL == 4) {
+            const float4 t = tc::lds_v4(a);
+            d[0] = t.x, d[1] = t.y, d[2] = t.z, d[3] = t.w;
+          } else if constexpr (EPL == 2) {
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(d[0]), "=f"(d[1]) : "r"(a));
+          } else {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d[0]) : "r"(a));
+          }
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) acc[k][i] = fmaf(vj, d[i], acc[k][i]);
+        }
+      }
+      ++n_done;
+      __syncwarp();                                         // every lane is done with this tile before it is refilled
+    }
+    while (row < r1) flush();                               // last row of the chunk + trailing empty rows
+  }
+}
+
+template <int NOPS>
+static int launch_bulk(const SpmmParams& p, int row_bytes, cudaStream_t st) {
+  constexpr int B = 16, S = 3;
+  const size_t smem = size_t(8) * S * B * NOPS * row_bytes + 8 * S * 8;
+  if (smem > 220 * 1024) return fail(PGSD_ERR_INVALID, "spmm (bulk-copy variant): rows too wide for shared memory");
+  const int epl = row_bytes / 128;
+  int64_t grid = sm_count() * int64_t((220 * 1024) / smem >= 2 ? 2 : 1) - p.grid_reserve;
+  const int rows_per_chunk = 64;
+  const int64_t need = ceil_div<int64_t>(ceil_div<int64_t>(p.n_rows, rows_per_chunk), 8);
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+#define PGSD_BULK(E)                                                                                            \
+  {                                                                                                             \
+    auto kern = spmm_bulk_kernel<NOPS, E>;                                                                      \
+    PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));              \
+    kern<<<unsigned(grid), 256, smem, st>>>(p, row_bytes, rows_per_chunk);                                      \
+  }
+  if (epl == 4) PGSD_BULK(4) else if (epl == 2) PGSD_BULK(2) else PGSD_BULK(1)
+#undef PGSD_BULK
+  PGSD_LAUNCH_CHECK("spmm_bulk_kernel");
+  return PGSD_OK;
+}
+
 // ---- hub rows -------------------------------------------------------------------------------
 // Rows longer than `long_thr` (power-law graphs: one node with 10^5..10^6 neighbours) would pin a
 // single lane group for milliseconds.  The main kernels skip their entries (they still write the
@@ -770,6 +930,9 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   const bool hubs = a->n_long_rows > 0 && a->long_rows && a->long_chunk_ptr && a->long_row_threshold > 0 &&
                     a->long_chunk > 0 && a->dtype == PGSD_F32;
   p.long_thr = hubs ? a->long_row_threshold : 0;
+  // variant bit 0x800: bulk-copy (TMA) gathers + segmented reduction (fp32, rows of 128 / 256 / 512 bytes, no hub rows)
+  if ((a->variant & 0x800) && a->dtype == PGSD_F32 && !hubs && vec16 && (row_bytes == 128 || row_bytes == 256 || row_bytes == 512))
+    return a->n_ops == 2 ? launch_bulk<2>(p, int(row_bytes), st) : launch_bulk<1>(p, int(row_bytes), st);
   int rc = dispatch_main(a, p, W, U, lpr, st, stream);
   if (rc != PGSD_OK || !hubs) return rc;
   if (a->n_ops == 2) return W == 8 ? launch_long<8, 2>(lpr, p, a, st) : launch_long<4, 2>(lpr, p, a, st);

@@ -135,6 +135,22 @@ def test_spmm_variants_agree_and_fused_relu():
         assert_close_rel(got[1], base[1], 2e-6, f"variant {variant:#x} op1")
     one = ops.spmm(p, [x1], (1,))
     assert_close_rel(one[0], base[1], 2e-6, "single-operator launch")
+    # bulk-copy (TMA) gathers + segmented reduction (variant bit 0x800): every epilogue, 1 and 2 operators, rows of
+    # 128 / 256 / 512 bytes, empty rows at both ends of a chunk
+    z0, z1 = torch.randn(n, f, generator=g).to(DEV), torch.randn(n, f, generator=g).to(DEV)
+    bias = torch.randn(f, generator=g).to(DEV)
+    kw = dict(alpha=2.0, beta=-1.0, zs=[z0, z1], bias=bias)
+    want = ops.spmm(p, [x0, x1], (0, 1), **kw)
+    got = ops.spmm(p, [x0, x1], (0, 1), variant=0x800, **kw)
+    assert_close_rel(got[0], want[0], 2e-6, "bulk variant, Chebyshev epilogue op0")
+    assert_close_rel(got[1], want[1], 2e-6, "bulk variant, Chebyshev epilogue op1")
+    assert_close_rel(ops.spmm(p, [x1], (1,), variant=0x800)[0], base[1], 2e-6, "bulk variant, one operator")
+    for width in (32, 128):
+        ei2 = torch.randint(5, n - 300, (2, 30_000), generator=g).to(DEV)          # first / last rows are empty
+        q2 = planmod.build_csr(ei2, torch.rand(30_000, generator=g).to(DEV), n, n, "source_to_target")
+        xw = torch.randn(n, width, generator=g).to(DEV)
+        assert_close_rel(ops.spmm(q2, [xw], (0,), mean=True, variant=0x800)[0], ops.spmm(q2, [xw], (0,), mean=True)[0],
+                         2e-6, f"bulk variant, mean, width {width}")
     conv = nn.MagNetConv(f, f, K=1, q=0.25, trainable_q=False).to(DEV)
     r, i = conv(x0, x1, ei)
     conv.fused_complex_relu = True
@@ -329,11 +345,34 @@ def test_magnet_full_size_properties(n, e):
     assert abs(a - b) <= 1e-6 * nrm(xi) * nrm(t[0])
     c = (xr.double() * t[1].double()).sum().item(); d = (u[1].double() * xi.double()).sum().item()
     assert abs(c + d) <= 1e-6 * nrm(xr) * nrm(t[1])
-    # row-subset oracle on 3000 random destination rows
+    # The OPERATOR against the oracle, built by the oracle from the edge list (not from the GPU plan):
+    #   * 200k / 4M: the whole cached_result against port.magnet_norm -- indices bit-exact, values 1e-6;
+    #   * 1M / 20M : the entries aggregated into 3000 random rows against port.magnet_norm_rows (the full
+    #     2E-key sort takes minutes on the CPU), same bars.
     gen = torch.Generator().manual_seed(1)
-    sel = torch.randperm(n, generator=gen)[:3000]
+    sel = torch.randperm(n, generator=gen)[:3000].sort().values
     cr = [c_.cpu() for c_ in conv.cached_result]
-    o_r, o_i = port.magnet_conv_rows(sel, xr.cpu(), xi.cpu(), cr, conv.weight.detach().cpu(),
+    ei_cpu = ei.cpu()
+    if n <= 200_000:
+        ref = port.magnet_norm(ei_cpu, None, n, 0.25, "sym", 2.0)
+        for k in (0, 1):
+            assert torch.equal(cr[k], ref[k]), f"cached_result index tensor {k} differs from the oracle's"
+        for k in (2, 3):
+            assert (cr[k] - ref[k]).abs().max().item() <= 1e-6 * ref[k].abs().max().item(), f"operator values {k}"
+        oracle_rows = port.magnet_norm_rows(sel, ei_cpu, None, n, 0.25, "sym", 2.0)
+    else:
+        oracle_rows = port.magnet_norm_rows(sel, ei_cpu, None, n, 0.25, "sym", 2.0)
+        nnz = cr[1].size(1) - n
+        pick = torch.zeros(n, dtype=torch.bool)
+        pick[sel] = True
+        keep = pick[cr[1][1, :nnz]]
+        m = int(keep.sum())
+        assert torch.equal(cr[1][:, :nnz][:, keep], oracle_rows[1][:, :m]), "operator entries of the sampled rows"
+        for k in (2, 3):
+            got, want = cr[k][:nnz][keep], oracle_rows[k][:m]
+            assert (got - want).abs().max().item() <= 1e-6 * want.abs().max().item(), f"operator values {k}"
+    # the layer's outputs on those rows against the oracle's op sequence on the ORACLE's operator rows
+    o_r, o_i = port.magnet_conv_rows(sel, xr.cpu(), xi.cpu(), oracle_rows, conv.weight.detach().cpu(),
                                      conv.bias.detach().cpu())
     scale_r, scale_i = out_r.abs().max().item(), out_i.abs().max().item()
     assert (out_r[sel.to(DEV)].cpu() - o_r).abs().max().item() <= 1e-5 * scale_r

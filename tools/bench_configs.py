@@ -81,7 +81,9 @@ with torch.no_grad():
     z1 = torch.tanh(c1(x, pos, neg))
     c2(z1, pos, neg)
     nnz = pos.size(1) + neg.size(1)
-    b1 = nnz * 4 + 2 * (n + 1) * 4 + nnz * 64 * 4 + n * 64 * 4 * (2 + 1 + 1)     # 2 mean outs, x read, out
+    # col index per entry, two row_ptr arrays, one 64-wide gather per entry, x read once, out written once
+    # (intermediates the implementation may write are NOT algorithmic bytes)
+    b1 = nnz * 4 + 2 * (n + 1) * 4 + nnz * 64 * 4 + n * 64 * 4 * 2
     ms1 = timeit(lambda: c1(x, pos, neg))
     ms2 = timeit(lambda: c2(z1, pos, neg))
     emit(config="C4 SGCNConv layer 1 2M/40M/64 fp32", ms=ms1, edges_per_s=nnz / ms1 * 1e3, alg_gb=b1 / 1e9,
@@ -93,17 +95,39 @@ with torch.no_grad():
     s2 = nn.SNEAConv(32, 32, first_aggr=False).to(dev)
     zs = s1(x, pos, neg)
     s2(zs, pos, neg)
+    # Algorithmic bytes of the attention kernels: edge softmax = per stored entry the column index and
+    # ONE scalar score gather (4 + 4 B; the 32-byte sector a scalar gather really moves is traffic, not algorithm),
+    # per row and type row_ptr + s_dst (8 B), plus what the mode writes: SNEAConv (mode A) reads the target's feature
+    # row per type and writes the output row; GAT-style (mode B) writes alpha per entry (4 B).
+    def softmax_bytes_snea(plans, feat):
+        return sum(p.nnz * 8 + p.n_dst * (8 + feat * 4) for p in plans) + plans[0].n_dst * feat * 4
+
+    p_pos, p_neg = s1._plan_for(pos, n, True), s1._plan_for(neg, n, True)
+    p_neg2 = s2._plan_for(neg, n, False)
+    att_bytes = {"SNEAConv layer 1 2M/40M/64 fp32": softmax_bytes_snea([p_pos], 32) + softmax_bytes_snea([p_neg], 32),
+                 "SNEAConv layer 2 2M/40M/(32|32) fp32": 2 * softmax_bytes_snea([p_pos, p_neg2], 32)}
     for nm, fn in (("SNEAConv layer 1 2M/40M/64 fp32", lambda: s1(x, pos, neg)),
                    ("SNEAConv layer 2 2M/40M/(32|32) fp32", lambda: s2(zs, pos, neg))):
         ms_ = timeit(fn)
-        emit(config=nm, ms=ms_, edges_per_s=nnz / ms_ * 1e3, kernels_ms=breakdown(fn))
+        kb = breakdown(fn)
+        sm = kb.get("edge_softmax", 0.0)
+        emit(config=nm, ms=ms_, edges_per_s=nnz / ms_ * 1e3, kernels_ms=kb,
+             edge_softmax={"alg_gb": att_bytes[nm] / 1e9, "ms": sm,
+                           "frac": att_bytes[nm] / sm / 1e6 / PEAK if sm else None})
     del s1, s2, zs
     # SDRLayer (row a9): 4 GATConv over the pos/neg in/out lists of the same graph + MLP, 64 -> 64
     sdr = nn.SDRLayer(64, 64, [pos, pos.flip(0), neg, neg.flip(0)]).to(dev)
     sdr(x)
     ms_ = timeit(lambda: sdr(x))
-    emit(config="SDRLayer 4 x GATConv 2M/2x40M/64 fp32", ms=ms_, edges_per_s=2 * nnz / ms_ * 1e3,
-         kernels_ms=breakdown(lambda: sdr(x)))
+    kb = breakdown(lambda: sdr(x))
+    gp = [a._plan_for(e_, n) for a, e_ in zip(sdr.aggs, sdr.edge_lists)]
+    b_sm = sum(p.nnz * (8 + 4) + p.n_dst * 8 for p in gp)                       # mode B: + alpha written per entry
+    b_ag = sum(p.nnz * (4 + 4 + 64 * 4) + (p.n_dst + 1) * 4 + 2 * p.n_dst * 64 * 4 for p in gp)   # val = alpha, z and y
+    emit(config="SDRLayer 4 x GATConv 2M/2x40M/64 fp32", ms=ms_, edges_per_s=2 * nnz / ms_ * 1e3, kernels_ms=kb,
+         edge_softmax={"alg_gb": b_sm / 1e9, "ms": kb.get("edge_softmax"),
+                       "frac": b_sm / kb["edge_softmax"] / 1e6 / PEAK if kb.get("edge_softmax") else None},
+         gat_aggregation={"alg_gb": b_ag / 1e9, "ms": kb.get("spmm"),
+                          "frac": b_ag / kb["spmm"] / 1e6 / PEAK if kb.get("spmm") else None})
     del sdr
     torch.cuda.empty_cache()
     # C4 as a model: SGCN(in=64, out=64, 2 layers), tanh fused into each layer's transform

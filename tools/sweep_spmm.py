@@ -52,6 +52,23 @@ emit(what="plan_build_ms", ms=timeit(lambda: planmod.build_magnetic(ei, None, N,
 nnz = p.nnz
 b_alg = nnz * (12 + 2 * F * 4) + (N + 1) * 4 + 2 * N * F * 4
 yr, yi = torch.empty_like(xr), torch.empty_like(xi)
+if os.environ.get("SWEEP_ONLY") == "bulk":
+    # x1 of VERDICT r1: the bulk-copy (cp.async.bulk per neighbour row) gather beside the register-gather default, on
+    # the full-size launch and on the short-row column blocks of the sharded path (8 blocks, ~5 entries per row)
+    from pytorch_geometric_signed_directed_b200 import distributed as pgd
+    for variant in (0, 0x800):
+        ms = timeit(lambda: ops.spmm(p, [xr, xi], (0, 1), out=[yr, yi], variant=variant))
+        emit(what="spmm2", variant=hex(variant), kernel="bulk-copy gather" if variant else "register gather (default)",
+             ms=ms, gbs=b_alg / ms / 1e6, frac_of_peak=b_alg / ms / 1e6 / 6547.2)
+        ms = timeit(lambda: ops.spmm(p, [xr], (0,), out=[yr], variant=variant))
+        emit(what="spmm1", variant=hex(variant), ms=ms)
+    bounds = pgd.node_bounds(N, 8)
+    blocks = pgd.split_columns_by_owner(p, bounds, own_rank=0)
+    for variant in (0, 0x800):
+        ms = timeit(lambda: ops.spmm(blocks[3], [xr[bounds[3]:bounds[4]], xi[bounds[3]:bounds[4]]], (0, 1), beta=1.0,
+                                     zs=[yr, yi], out=[yr, yi], variant=variant))
+        emit(what="spmm2_column_block_1_of_8", variant=hex(variant), nnz=blocks[3].nnz, ms=ms)
+    sys.exit(0)
 for variant in (0x80 | 0x10 | 4, 0x80 | 0x20 | 2, 0x10 | 2, 0x10 | 4, 0x20 | 2, 0x20 | 4):
     ms = timeit(lambda: ops.spmm(p, [xr, xi], (0, 1), out=[yr, yi], variant=variant))
     emit(what="spmm2", variant=hex(variant), ms=ms, gbs=b_alg / ms / 1e6, nnz=nnz)
