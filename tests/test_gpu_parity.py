@@ -756,8 +756,11 @@ def test_sgcn_model_golden(name, norm_emb):
     m = nn.SGCN(140, g["edge_index_s"], in_dim=12, out_dim=16, layer_num=3, init_emb=g["x"].clone(),
                 norm_emb=norm_emb).to(DEV).eval()
     assert torch.equal(m.pos_edge_index, g["pos_edge_index"]) and torch.equal(m.neg_edge_index, g["neg_edge_index"])
-    m.load_state_dict({k.replace("__", "."): v for k, v in g.items()
-                       if k not in ("out", "edge_index_s", "pos_edge_index", "neg_edge_index")})
+    res = m.load_state_dict({k.replace("__", "."): v for k, v in g.items()
+                             if k not in ("out", "edge_index_s", "pos_edge_index", "neg_edge_index")}, strict=False)
+    # the fixture holds the layers' parameters; the loss head of the reference (SGCN.py:75, lsp_loss.lin) exists here
+    # as a parameter container so that full reference state_dicts load with strict=True
+    assert not res.unexpected_keys and sorted(res.missing_keys) == ["lsp_loss.lin.bias", "lsp_loss.lin.weight"]
     with torch.no_grad():
         z = m()
     assert_close_rel(z, g["out"], 1e-5)
@@ -768,7 +771,7 @@ def test_sgcn_model_golden(name, norm_emb):
     z2 = m()
     assert_close_rel(z2, g["out"], 1e-5)
     z2.sum().backward()
-    assert all(p.grad is not None for n_, p in m.named_parameters() if n_ != "x")
+    assert all(p.grad is not None for n_, p in m.named_parameters() if n_ != "x" and not n_.startswith("lsp_loss"))
     with pytest.raises(NotImplementedError):
         nn.SGCN(140, g["edge_index_s"], in_dim=12, out_dim=16)
 
