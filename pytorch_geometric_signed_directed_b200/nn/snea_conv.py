@@ -50,7 +50,7 @@ class SNEAConv(torch.nn.Module):
         self._plans.clear()
 
     # remove_self_loops [+ add_self_loops over 0..max id] -> CSR by target
-    def _plan_for(self, edge_index: Tensor, n: int, with_loops: bool) -> _plan.CSRPlan:
+    def _request(self, edge_index: Tensor, n: int, with_loops: bool):
         def build():
             keep = edge_index[0] != edge_index[1]
             ei = edge_index[:, keep]
@@ -59,7 +59,10 @@ class SNEAConv(torch.nn.Module):
                 loops = torch.arange(m, device=ei.device, dtype=ei.dtype)
                 ei = torch.cat([ei, torch.stack([loops, loops])], dim=1)
             return _plan.build_csr(ei.contiguous(), None, n, n, "source_to_target")
-        return self._plans.get((edge_index,), (n, with_loops), build)
+        return ((edge_index,), (n, with_loops), build)
+
+    def _plan_for(self, edge_index: Tensor, n: int, with_loops: bool) -> _plan.CSRPlan:
+        return self._plans.get(*self._request(edge_index, n, with_loops))
 
     def _transforms(self, x: Tensor, specs):
         """All Linear applications of one forward in TWO launches.  specs = [(lin, first input column, alpha_lin)]:
@@ -133,15 +136,19 @@ class SNEAConv(torch.nn.Module):
         train = self._needs_grad(x)
         transforms = self._transforms_train if train else self._transforms
         with torch.enable_grad() if train else torch.no_grad():
+            # the transforms are enqueued before the plans are validated (one fingerprint read-back for both)
             if self.first_aggr:
                 hs, ss = transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_u, 0, self.alpha_u)])
-                out_b = self._attend([self._plan_for(pos_edge_index, n, True)], hs[:1], ss[:1])
-                out_u = self._attend([self._plan_for(neg_edge_index, n, True)], hs[1:], ss[1:])
+                p_pos, p_neg = self._plans.get_many([self._request(pos_edge_index, n, True),
+                                                     self._request(neg_edge_index, n, True)])
+                out_b = self._attend([p_pos], hs[:1], ss[:1])
+                out_u = self._attend([p_neg], hs[1:], ss[1:])
             else:
                 fi = self.in_dim                       # x = [h_b | h_u]
                 hs, ss = transforms(x, [(self.lin_b, 0, self.alpha_b), (self.lin_b, fi, self.alpha_b),
                                         (self.lin_u, fi, self.alpha_u), (self.lin_u, 0, self.alpha_u)])
-                plans = [self._plan_for(pos_edge_index, n, True), self._plan_for(neg_edge_index, n, False)]
+                plans = self._plans.get_many([self._request(pos_edge_index, n, True),
+                                              self._request(neg_edge_index, n, False)])
                 out_b = self._attend(plans, hs[:2], ss[:2])
                 out_u = self._attend(plans, hs[2:], ss[2:])
         return torch.cat([out_b, out_u], dim=-1)

@@ -314,38 +314,58 @@ class PlanCache:
 
     @staticmethod
     def _fingerprint(tensors):
-        live = [t for t in tensors if t is not None and t.numel() and t.is_cuda]
+        """One (sum, weighted sum) pair per tensor, `()` for None / empty / CPU tensors; one read-back for all."""
+        live = [i for i, t in enumerate(tensors) if t is not None and t.numel() and t.is_cuda]
+        res = [()] * len(tensors)
         if not live:
-            return ()
-        dev = live[0].device
+            return res
+        dev = tensors[live[0]].device
         out = torch.zeros(2 * len(live), dtype=torch.int64, device=dev)
         lib = _lib.load()
         with torch.cuda.device(dev):
-            for i, t in enumerate(live):
-                w = t.detach()
+            for k, i in enumerate(live):
+                w = tensors[i].detach()
                 if not w.is_contiguous():
                     w = w.contiguous()
                 _lib.check(lib.pgsd_fingerprint(w.data_ptr(), w.numel() * w.element_size(),
-                                                out.data_ptr() + 16 * i, _stream_ptr(dev)), "pgsd_fingerprint")
-        return tuple(out.tolist())
+                                                out.data_ptr() + 16 * k, _stream_ptr(dev)), "pgsd_fingerprint")
+        vals = out.tolist()
+        for k, i in enumerate(live):
+            res[i] = (vals[2 * k], vals[2 * k + 1])
+        return res
 
     def get(self, tensors, extra, builder):
+        return self.get_many([(tensors, extra, builder)])[0]
+
+    def get_many(self, requests):
+        """[(tensors, extra, builder)] -> [plan]; the fingerprints of all requests are read back with ONE
+        device->host synchronisation (SGCNConv / SNEAConv ask for the positive and the negative plan together)."""
         import os
         mode = os.environ.get("PGSD_PLAN_REUSE", "fingerprint")
         if mode == "off":
-            return builder()
-        key = (tuple(self._key(t) for t in tensors), extra)
-        fp = self._fingerprint(tensors) if mode == "fingerprint" else None
-        hit = self._items.get(key)
-        if hit is not None and hit[2] == fp:
-            return hit[0]
-        plan = builder()
-        self._items.pop(key, None)
-        if len(self._items) >= self.capacity:
-            self._items.pop(next(iter(self._items)))
-        # keep the key tensors alive so a recycled data_ptr cannot alias a stale plan
-        self._items[key] = (plan, tensors, fp)
-        return plan
+            return [b() for _, _, b in requests]
+        keys = [(tuple(self._key(t) for t in ts), extra) for ts, extra, _ in requests]
+        fps = [None] * len(requests)
+        if mode == "fingerprint":
+            per_tensor = self._fingerprint([t for ts, _, _ in requests for t in ts])
+            pos = 0
+            for r, (ts, _, _) in enumerate(requests):
+                fps[r] = tuple(per_tensor[pos:pos + len(ts)])
+                pos += len(ts)
+        out = []
+        for key, fp, (ts, _, builder) in zip(keys, fps, requests):
+            hit = self._items.get(key)
+            if hit is not None and hit[2] == fp:
+                out.append(hit[0])
+                continue
+            plan = builder()
+            self._items.pop(key, None)
+            if len(self._items) >= self.capacity:
+                self._items.pop(next(iter(self._items)))
+            # keep the key tensors alive so a recycled data_ptr cannot alias a stale plan
+            self._items[key] = (plan, ts, fp)
+            out.append(plan)
+        return out
 
     def clear(self):
         self._items.clear()

@@ -46,8 +46,7 @@ case "$R" in
     K=$1; O=$2; shift 3
     timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$K" -c 1 -s ${NCU_SKIP:-2} \
       -o gpurun_out/$O -f "$@" > gpurun_out/$O.log 2>&1
-    tail -3 gpurun_out/$O.log
-    python tools/ncu_summary.py gpurun_out/$O.ncu-rep > gpurun_out/${O}_summary.json 2>/dev/null; cat gpurun_out/${O}_summary.json ;;
+    tail -3 gpurun_out/$O.log; ls -la gpurun_out/$O.ncu-rep ;;   # summarise here: python tools/ncu_summary.py <rep> <out.json> "<cmd>" "<note>"
   seq)         # seq 'recipe args' 'recipe args' ...: several recipes in one call
     for step in "$@"; do bash tools/gpu_session.sh $step; done ;;
   *) echo "recipes: tests bench dist distbench probe sweep configs launches ncu seq" ;;
