@@ -364,11 +364,19 @@ __global__ void __launch_bounds__(256) fingerprint_kernel(const uint32_t* __rest
                                                           unsigned long long* __restrict__ out) {
   unsigned long long s0 = 0, s1 = 0;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t v = __ldg(w + i);
+  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto add = [&](uint32_t v, int64_t i) {
     s0 += v;
     s1 += (unsigned long long)v * (uint32_t(i) * 2654435761u | 1u);
+  };
+  // 128-bit loads over the 16-byte aligned body (torch allocations are), scalar loads over the tail
+  const int64_t n4 = (reinterpret_cast<uintptr_t>(w) % 16 == 0) ? n / 4 : 0;
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  for (int64_t i = tid; i < n4; i += stride) {
+    const uint4 v = __ldg(w4 + i);
+    add(v.x, 4 * i), add(v.y, 4 * i + 1), add(v.z, 4 * i + 2), add(v.w, 4 * i + 3);
   }
+  for (int64_t i = 4 * n4 + tid; i < n; i += stride) add(__ldg(w + i), i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -385,7 +393,7 @@ extern "C" int pgsd_fingerprint(const void* data, int64_t n_bytes, uint64_t* out
   const int64_t n = n_bytes / 4;
   if (n <= 0) return PGSD_OK;
   PGSD_REQUIRE(data != nullptr && reinterpret_cast<uintptr_t>(data) % 4 == 0, "fingerprint: data must be 4-byte aligned");
-  int64_t grid = ceil_div<int64_t>(n, 256 * 8);
+  int64_t grid = ceil_div<int64_t>(n, 256 * 16);
   if (grid > int64_t(sm_count()) * 8) grid = int64_t(sm_count()) * 8;
   fingerprint_kernel<<<unsigned(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint32_t*>(data), n, reinterpret_cast<unsigned long long*>(out2));

@@ -932,3 +932,35 @@ def test_gat_aggregation_with_inkernel_softmax(n, e, c):
     assert_close_rel(fused, ref, 1e-5, "fused vs oracle")
     assert_close_rel(fused, two, 2e-6, "fused vs two-kernel route")
     assert_close_rel(acc - acc0, fused - gat.bias.detach(), 2e-6, "accumulating epilogue")
+
+
+def test_plan_cache_follows_content_not_only_identity(monkeypatch):
+    """a layer that re-normalises on every call upstream (MagNetConv cached=False, MagNetConv.py:158-181)
+    reuses its last plan only while the edge tensors' CONTENT is unchanged -- a write through `.data` (no version
+    bump, same storage) must be seen; PGSD_PLAN_REUSE=off rebuilds every call."""
+    g = torch.Generator().manual_seed(3)
+    n, e, f = 2000, 30_000, 16
+    ei = torch.randint(0, n, (2, e), generator=g).to(DEV)
+    xr, xi = torch.randn(n, f, generator=g).to(DEV), torch.randn(n, f, generator=g).to(DEV)
+    conv = nn.MagNetConv(f, f, K=1, q=0.25, trainable_q=False, cached=False).to(DEV)
+    with torch.no_grad():
+        a = conv(xr, xi, ei)
+        plan_a = conv._plan
+        conv(xr, xi, ei)
+        assert conv._plan is plan_a                                  # identical tensors: the plan is reused
+        version = ei._version
+        ei.data[:, :5000] = torch.randint(0, n, (2, 5000), generator=g).to(DEV)
+        assert ei._version == version                                # the write is invisible to the version counter
+        b = conv(xr, xi, ei)
+        assert conv._plan is not plan_a
+        fresh = nn.MagNetConv(f, f, K=1, q=0.25, trainable_q=False, cached=False).to(DEV)
+        fresh.load_state_dict(conv.state_dict())
+        c = fresh(xr, xi, ei)
+        assert_close_rel(b[0], c[0], 1e-6, "result follows the modified edges")
+        assert (a[0] - b[0]).abs().max().item() > 1e-3
+        monkeypatch.setenv("PGSD_PLAN_REUSE", "off")
+        plan_b = conv._plan
+        conv(xr, xi, ei)
+        assert conv._plan is not plan_b
+        conv.cached_result = None
+        assert conv._plan is None and not conv._rebuild_cache._items
