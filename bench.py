@@ -33,7 +33,10 @@ import tempfile
 import threading
 import time
 
-import torch
+# one hardware queue per stream (compute, exchange, copy-engine streams, e2e side streams): with the default of 8
+# connections streams can alias and serialise behind each other; must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
