@@ -84,11 +84,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def recorded_traffic(name="spmm_dram_traffic.json"):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture."""
+def recorded_traffic(name="spmm_dram_traffic.json", kernel=None):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture -- only when the capture
+    is of the kernel instantiation that was just timed (`kernel` = pgsd_last_spmm_kernel()); a stale capture is
+    reported as null rather than as this run's traffic."""
     try:
         with open(os.path.join(ROOT, "profiles", name)) as fh:
-            return float(json.load(fh)["dram_bytes_per_launch"])
+            rec = json.load(fh)
+        if kernel is not None and rec.get("kernel") != kernel:
+            log(f"roofline.traffic dropped: capture is of {rec.get('kernel')}, this run launched {kernel}")
+            return None
+        return float(rec["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -383,6 +389,8 @@ def run_gpu_arm(args, rank, world):
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
+    from pytorch_geometric_signed_directed_b200 import _lib as _pl
+    spmm_kernel = (_pl.load().pgsd_last_spmm_kernel() or b"").decode() or "spmm kernel"
     launches = ops.LAUNCHES - launches0
     timing, ops.TIMING = ops.TIMING, None
     clocks = sampler.stop()
@@ -613,9 +621,10 @@ def run_gpu_arm(args, rank, world):
                 "share_of_step": fused_ms / ms_per_step}
         roof["frac"] = roof["achieved"] / peak
     else:
-        roof = {"bound": "hbm", "kernel": "spmm_groups_kernel (pgsd_spmm_csr, n_ops=2)", "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": f"{spmm_kernel} (pgsd_spmm_csr, n_ops=2)", "unit": "GB/s",
                 "peak": peak, "peak_source": peak_src, "algorithmic_bytes": b_spmm,
-                "traffic": recorded_traffic()}
+                # the capture is of ONE launch over the whole shard: not comparable with the per-block launches of N > 1
+                "traffic": recorded_traffic(kernel=spmm_kernel) if world == 1 else None}
         if spmm_ms:
             roof["achieved"] = b_spmm / (spmm_ms * 1e-3) / 1e9
             roof["frac"] = roof["achieved"] / peak

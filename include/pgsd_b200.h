@@ -222,6 +222,10 @@ typedef struct pgsd_spmm_args {
 } pgsd_spmm_args;
 
 PGSD_API int pgsd_spmm_csr(const pgsd_spmm_args* args, pgsd_stream_t stream);
+/* Name of the kernel template instantiation the calling thread's last pgsd_spmm_csr launched (e.g.
+ * "spmm_groups_kernel<4,16,2,2,4,0,256,3>" = <words per load, lanes per row, operators, gathered matrices, loads in
+ * flight, bf16, threads, min CTAs per SM>): lets a harness check that a recorded profile belongs to the kernel it times. */
+PGSD_API const char* pgsd_last_spmm_kernel(void);
 
 /* ------------------------------------------------------------------------------------
  * Dense feature transform next to the aggregation:

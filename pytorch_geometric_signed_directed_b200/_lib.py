@@ -118,6 +118,7 @@ _PROTOTYPES = {
     "pgsd_magnetic_q_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _i64,
                                        _vp, _i64, _vp, _i64, C.c_double, _vp, _vp]),
     "pgsd_spmm_csr": (C.c_int, [C.POINTER(SpmmArgs), _vp]),
+    "pgsd_last_spmm_kernel": (C.c_char_p, []),
     "pgsd_dense_transform": (C.c_int, [C.POINTER(DenseArgs), _vp]),
     "pgsd_magnet_fused_supported": (C.c_int, [_i32, _i32, _i32]),
     "pgsd_sizeof_magnet_fused_args": (C.c_size_t, []),

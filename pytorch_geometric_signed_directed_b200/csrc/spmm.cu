@@ -21,6 +21,13 @@
 
 namespace pgsd {
 
+// Template instantiation chosen by the last pgsd_spmm_csr call of this thread (pgsd_last_spmm_kernel): lets a
+// harness check that a recorded ncu capture still belongs to the kernel it is timing.
+inline char* last_kernel_buf() {
+  static thread_local char buf[96] = {0};
+  return buf;
+}
+
 struct SpmmParams {
   int64_t n_rows;
   int32_t feat;
@@ -539,6 +546,7 @@ static int launch_bulk(const SpmmParams& p, int row_bytes, cudaStream_t st) {
   const size_t smem = size_t(8) * S * B * NOPS * row_bytes + 8 * S * 8;
   if (smem > 220 * 1024) return fail(PGSD_ERR_INVALID, "spmm (bulk-copy variant): rows too wide for shared memory");
   const int epl = row_bytes / 128;
+  snprintf(last_kernel_buf(), 96, "spmm_bulk_kernel<%d,%d>", NOPS, epl);
   int64_t grid = sm_count() * int64_t((220 * 1024) / smem >= 2 ? 2 : 1) - p.grid_reserve;
   const int rows_per_chunk = 64;
   const int64_t need = ceil_div<int64_t>(ceil_div<int64_t>(p.n_rows, rows_per_chunk), 8);
@@ -724,6 +732,7 @@ static int launch_groups(const SpmmParams& p, cudaStream_t st) {
   constexpr int MINB = (NX * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
   constexpr int G = 32 / LPR;
   auto kern = spmm_groups_kernel<W, LPR, NOPS, NX, U, BF16, THREADS, MINB>;
+  snprintf(last_kernel_buf(), 96, "spmm_groups_kernel<%d,%d,%d,%d,%d,%d,%d,%d>", W, LPR, NOPS, NX, U, int(BF16), THREADS, MINB);
   // The kernel itself uses no shared memory, so the driver configures its SMs with the smallest carve-out; a
   // kernel that needs shared memory (the bulk-copy shard push, 64 KB per CTA) then cannot become resident on
   // those SMs before they drain.  The sharded path asks for a carve-out that leaves room for it.
@@ -752,6 +761,7 @@ static int launch_rows(const SpmmParams& p, cudaStream_t st) {
   // register budget: keep >= 3 CTAs (24 warps) resident when the tile is small
   constexpr int MINB = (NOPS * U * W >= 64) ? 2 : 3;   // 32-bit words in flight per lane
   auto kern = spmm_rows_kernel<W, LPR, NOPS, U, BF16, THREADS, MINB>;
+  snprintf(last_kernel_buf(), 96, "spmm_rows_kernel<%d,%d,%d,%d,%d,%d,%d>", W, LPR, NOPS, U, int(BF16), THREADS, MINB);
   int occ = 0;
   PGSD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
   if (occ < 1) occ = 1;
@@ -832,6 +842,8 @@ static int dispatch_main(const pgsd_spmm_args* a, const SpmmParams& p, int W, in
   if (U == 8) return dispatch_lpr<4, 1, 8, false>(lpr, p, st);
   return dispatch_lpr<4, 1, 4, false>(lpr, p, st);
 }
+
+extern "C" const char* pgsd_last_spmm_kernel(void) { return last_kernel_buf(); }
 
 extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
   PGSD_REQUIRE(a != nullptr, "spmm: args is null");
@@ -916,6 +928,7 @@ extern "C" int pgsd_spmm_csr(const pgsd_spmm_args* a, pgsd_stream_t stream) {
       spmm_rows_scalar_kernel<true><<<(unsigned)grid, 256, 0, st>>>(p, a->n_ops);
     else
       spmm_rows_scalar_kernel<false><<<(unsigned)grid, 256, 0, st>>>(p, a->n_ops);
+    snprintf(last_kernel_buf(), 96, "spmm_rows_scalar_kernel<%d>", int(a->dtype == PGSD_BF16));
     PGSD_LAUNCH_CHECK("spmm_rows_scalar_kernel");
     return PGSD_OK;
   }
