@@ -95,7 +95,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 
 // TANH: the tanh epilogue (SGCN.py:93-96) is a compile-time variant -- as a run-time branch its inlined
 // tanhf cost the epilogue-bound bf16 instantiation 20 % (0.19 -> 0.235 ms, session 32)
-template <int N_OUT, int GROUPS, bool BF16, bool TANH>
+// WIDE (fp32 only): [W_hi | W_lo] is ONE B operand of 2 * N_OUT rows, so hi * W_hi and hi * W_lo are a single MMA into
+// two TMEM column ranges (summed in the epilogue) and the landed chunk is read by the tensor core ONCE as `hi` --
+// RAW, without the in-place TF32 rounding: kind::tf32 ignores the 13 low mantissa bits, i.e. hi = trunc19(x), and the
+// converters only produce lo = tf32(x - trunc19(x)) (one shared-memory write per chunk instead of two).  The kernel is
+// shared-memory-bandwidth bound (ncu: LSU-shared 48 %, ~1.2 MB of shared-memory traffic per 128-row tile of a MagNet
+// layer); this removes a fifth of it.  Error budget per product: (lo - tf32(lo)) w_hi <= 2^-21, hi (w_lo - tf32(w_lo))
+// <= 2^-22, dropped lo * w_lo <= 2^-21 -- fp32-class, checked against fp64 at 2e-6 like the other paths.
+template <int N_OUT, int GROUPS, bool BF16, bool TANH, bool WIDE>
 __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32, 1)
     dense_tma_kernel(const __grid_constant__ Params p) {
   constexpr int NCV = BF16 ? 0 : CONV_WARPS;
@@ -107,7 +114,9 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   constexpr int HALF = N_OUT * 128;
   constexpr int SLAB_BYTES = BF16 ? HALF : 2 * HALF;
   constexpr int UMMA_K_BYTES = 32;
-  constexpr int ACC_COLS = GROUPS * N_OUT;
+  static_assert(!WIDE || !BF16, "WIDE is the fp32 (3xTF32) path");
+  constexpr int GCOLS = WIDE ? 2 * N_OUT : N_OUT;   // TMEM columns per group
+  constexpr int ACC_COLS = GROUPS * GCOLS;
   // output rows of at least 128 B leave through TMA stores; narrower ones through per-lane stores
   constexpr bool TMA_STORE = N_OUT * ES >= 128;
   constexpr int CBR = 128 / (16 * ES);           // 16-column blocks per 128-byte box row: 2 (fp32) / 4 (bf16)
@@ -116,6 +125,8 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
   constexpr uint32_t FMT = BF16 ? 1u : 2u;
   constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | (uint32_t(N_OUT >> 3) << 17) |
                              (uint32_t(TILE_M >> 4) << 24);
+  constexpr uint32_t IDESC_WIDE = (1u << 4) | (FMT << 7) | (FMT << 10) | (uint32_t((2 * N_OUT) >> 3) << 17) |
+                                  (uint32_t(TILE_M >> 4) << 24);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -201,9 +212,40 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
       const uint32_t acc = it & 1;
       if (it >= 2) mbar_wait_relaxed(bar_acc_empty + 8 * acc, ((it >> 1) - 1) & 1);   // epilogue drained this buffer
       for (int c = 0; c < p.n_chunks; ++c, ++uses) {
+        const uint32_t d = tmem_base + acc * ACC_COLS + uint32_t(p.group[c]) * GCOLS;
+        if constexpr (WIDE) {
+          // hi MMAs as soon as the chunk has LANDED (they read the raw words), lo MMAs once the converters are done
+          const uint32_t da_hi = a_lo32 + stage * (STAGE_BYTES >> 4);
+          const uint32_t da_lo = l_lo32 + ls * (CHUNK_BYTES >> 4);
+          const uint32_t dw = w_lo32 + uint32_t(p.slab[c]) * (SLAB_BYTES >> 4);
+          const uint32_t acc0 = p.first[c] ? 0u : 1u;
+          mbar_wait_relaxed(bar_full + 8 * stage, (uses / S) & 1);
+          tc_fence_after();
+          if (elect_one() && !(p.dbg & 4)) {
+#pragma unroll
+            for (int j = 0; j < 128 / UMMA_K_BYTES; ++j)
+              mma_lo<false>(d, da_hi + j * KSTEP, dw + j * KSTEP, IDESC_WIDE, j == 0 ? acc0 : 1u);
+          }
+          __syncwarp();
+          mbar_wait_relaxed(bar_conv + 8 * stage, (uses / S) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(p.dbg & 4)) {
+#pragma unroll
+              for (int j = 0; j < 128 / UMMA_K_BYTES; ++j)
+                mma_lo<false>(d, da_lo + j * KSTEP, dw + j * KSTEP, IDESC, 1u);
+            }
+            tc_commit(bar_empty + 8 * stage);
+            tc_commit(bar_lo_empty + 8 * ls);
+            if (c == p.n_chunks - 1) tc_commit(bar_acc_full + 8 * acc);
+          }
+          __syncwarp();
+          stage = (stage + 1 == uint32_t(S)) ? 0u : stage + 1;
+          ls = (ls + 1 == uint32_t(L)) ? 0u : ls + 1;
+          continue;
+        }
         mbar_wait_relaxed((BF16 ? bar_full : bar_conv) + 8 * stage, (uses / S) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * ACC_COLS + uint32_t(p.group[c]) * N_OUT;
         const uint32_t da_hi = a_lo32 + stage * (STAGE_BYTES >> 4);
         const uint32_t da_lo = l_lo32 + ls * (CHUNK_BYTES >> 4);
         const uint32_t dw_hi = w_lo32 + uint32_t(p.slab[c]) * (SLAB_BYTES >> 4), dw_lo = dw_hi + (HALF >> 4);
@@ -267,7 +309,20 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
             for (int n = 0; n < NCI; ++n) {
               const int cb = rd * RB * CBR + kk0 + n;
               tmem_ld<16>(taddr + cb * 16, a[n]);
-              if (GROUPS == 2) tmem_ld<16>(taddr + N_OUT + cb * 16, b[n]);
+              if (GROUPS == 2) tmem_ld<16>(taddr + GCOLS + cb * 16, b[n]);
+            }
+            if constexpr (WIDE) {
+              // second column range of every group: hi * W_lo (NCI == 1 on the fp32 path)
+              float a2[16], b2[16];
+              const int cb = rd * RB * CBR + kk0;
+              tmem_ld<16>(taddr + N_OUT + cb * 16, a2);
+              if (GROUPS == 2) tmem_ld<16>(taddr + GCOLS + N_OUT + cb * 16, b2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                a[0][i] += a2[i];
+                if (GROUPS == 2) b[0][i] += b2[i];
+              }
             }
 #pragma unroll
             for (int n = 0; n < NCI; ++n)
@@ -422,10 +477,17 @@ __global__ void __launch_bounds__((2 + EPI_WARPS + (BF16 ? 0 : CONV_WARPS)) * 32
                 for (int i = 0; i < 4; ++i) {
                   // the split is position-independent: unit q of the landed (swizzled) image stays unit q
                   float4 vh, vl;
-                  vh.x = to_tf32(v[i].x), vh.y = to_tf32(v[i].y), vh.z = to_tf32(v[i].z), vh.w = to_tf32(v[i].w);
-                  vl.x = to_tf32(v[i].x - vh.x), vl.y = to_tf32(v[i].y - vh.y);
-                  vl.z = to_tf32(v[i].z - vh.z), vl.w = to_tf32(v[i].w - vh.w);
-                  sts_v4(hi + ob + i * gstride, vh);
+                  if constexpr (WIDE) {
+                    // hi = what the tensor core sees of the raw word (13 low mantissa bits ignored): nothing to store
+                    auto trunc19 = [](float f) { return __uint_as_float(__float_as_uint(f) & 0xffffe000u); };
+                    vl.x = to_tf32(v[i].x - trunc19(v[i].x)), vl.y = to_tf32(v[i].y - trunc19(v[i].y));
+                    vl.z = to_tf32(v[i].z - trunc19(v[i].z)), vl.w = to_tf32(v[i].w - trunc19(v[i].w));
+                  } else {
+                    vh.x = to_tf32(v[i].x), vh.y = to_tf32(v[i].y), vh.z = to_tf32(v[i].z), vh.w = to_tf32(v[i].w);
+                    vl.x = to_tf32(v[i].x - vh.x), vl.y = to_tf32(v[i].y - vh.y);
+                    vl.z = to_tf32(v[i].z - vh.z), vl.w = to_tf32(v[i].w - vh.w);
+                    sts_v4(hi + ob + i * gstride, vh);
+                  }
                   sts_v4(lo + ob + i * gstride, vl);
                 }
               }
@@ -455,7 +517,7 @@ static size_t smem_bytes(int n_slabs, int n_tile, bool bf16, int stages, int lo_
          size_t(n_slabs) * (bf16 ? 1 : 2) * n_tile * 128 + 8 * (3 * MAX_STAGES + MAX_LO + 4) + 16;
 }
 
-template <int N_OUT, int GROUPS, bool BF16, bool TANH = false>
+template <int N_OUT, int GROUPS, bool BF16, bool TANH = false, bool WIDE = false>
 static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int want_cg, int want_epi) {
   // experiment knobs ride in the variant word (bits 8-11: lo slots, bits 12-15: landing stages,
   // bits 20-22: converter groups); 0 = default
@@ -498,7 +560,7 @@ static int launch(Params& p, cudaStream_t st, int want_stages, int want_lo, int 
   p.lo_stages = lo;
   p.epi_rb = rb, p.epi_ns = ns;
   const size_t smem = smem_bytes(p.n_slabs, N_OUT, BF16, stages, lo, out_boxes);
-  auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16, TANH>;
+  auto kern = dense_tma_kernel<N_OUT, GROUPS, BF16, TANH, WIDE>;
   PGSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int64_t n_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
   const int n_col_tiles = (p.n_total + N_OUT - 1) / N_OUT;
@@ -611,19 +673,26 @@ int dense_tma_try(const pgsd_dense_args* a, cudaStream_t st, int* handled) {
   const int wg = (a->variant >> 20) & 7, we = (a->variant >> 24) & 3;
   const bool tanh_epi = a->relu_mode == 2;
   if (tanh_epi && (bf16 || groups == 2)) return PGSD_OK;    // other kernels handle it
-#define PGSD_TMA(N_)                                                                                        \
+  // variant bit 26: the legacy split (hi rounded in place, three MMAs per k-step) for A/B timing
+  const bool wide_ok = !bf16 && ((a->variant >> 26) & 1) == 0;
+#define PGSD_TMA(N_, WG2_, WG1_)                                                                             \
   if (bf16) rc = groups == 2 ? launch<N_, 2, true>(p, st, ws, wl, wg, we) : launch<N_, 1, true>(p, st, ws, wl, wg, we); \
-  else if (groups == 2) rc = launch<N_, 2, false>(p, st, ws, wl, wg, we);                                    \
-  else rc = tanh_epi ? launch<N_, 1, false, true>(p, st, ws, wl, wg, we) : launch<N_, 1, false>(p, st, ws, wl, wg, we); \
+  else if (groups == 2) rc = (wide_ok && WG2_) ? launch<N_, 2, false, false, WG2_>(p, st, ws, wl, wg, we)     \
+                                               : launch<N_, 2, false>(p, st, ws, wl, wg, we);                \
+  else if (tanh_epi) rc = (wide_ok && WG1_) ? launch<N_, 1, false, true, WG1_>(p, st, ws, wl, wg, we)        \
+                                            : launch<N_, 1, false, true>(p, st, ws, wl, wg, we);             \
+  else rc = (wide_ok && WG1_) ? launch<N_, 1, false, false, WG1_>(p, st, ws, wl, wg, we)                     \
+                              : launch<N_, 1, false>(p, st, ws, wl, wg, we);                                 \
   break;
   switch (n_tile) {
     case 16:
       if (groups == 2) rc = launch<16, 2, false>(p, st, ws, wl, wg, we);
       else rc = tanh_epi ? launch<16, 1, false, true>(p, st, ws, wl, wg, we) : launch<16, 1, false>(p, st, ws, wl, wg, we);
       break;
-    case 32: PGSD_TMA(32)
-    case 64: PGSD_TMA(64)
-    default: PGSD_TMA(128)
+    // WIDE needs 2 buffers x groups x 2 x N_OUT TMEM columns <= 512
+    case 32: PGSD_TMA(32, true, true)
+    case 64: PGSD_TMA(64, true, true)
+    default: PGSD_TMA(128, false, true)
   }
 #undef PGSD_TMA
   if (rc == -1) return PGSD_OK;                  // does not fit in shared memory

@@ -10,6 +10,7 @@ from pytorch_geometric_signed_directed_b200 import ops
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TMA = 16
+LEGACY = 16 | (1 << 26)      # round-1 split: hi rounded in place, three MMAs per k-step (kept for A/B timing)
 
 
 @pytest.mark.parametrize("n_rows,ks,n_out,combine", [
@@ -42,6 +43,8 @@ def test_dense_tma_matches_fp64(n_rows, ks, n_out, combine):
     got = ops.dense(terms, n_out, bias=bias, combine=combine, variant=TMA)
     for g_, r in zip(got, ref):
         assert_close_rel(g_, r, 2e-6, "tma 3xTF32 vs fp64")
+    for g_, r in zip(ops.dense(terms, n_out, bias=bias, combine=combine, variant=LEGACY), ref):
+        assert_close_rel(g_, r, 2e-6, "tma 3xTF32 (legacy split) vs fp64")
     # many tiles per CTA: every stage / accumulator mbarrier wraps its phase several times
     big = [(x.repeat(60, 1), w, g) for x, w, g in terms]
     b1 = ops.dense(big, n_out, bias=bias, combine=combine, variant=TMA)
