@@ -282,3 +282,51 @@ def test_row_restricted_operator_matches_the_full_oracle(norm, lam, weighted):
     o_rows = port.magnet_conv_rows(rows, xr, xi, sub, wt, b)
     for a, r in zip(o_full, o_rows):
         assert (a[rows] - r).abs().max() <= 2e-6 * a.abs().max()
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def test_oracle_attention_gradients_match_the_reference_autograd():
+    """The attention layers train upstream (SNEAConv.py:135-146, SDGNN.py:57-64).  Fixtures from torch autograd through the
+    reference's OWN source files (tests/golden/make_golden_attn_grad.py) pin the gradients of oracle/port.py -- which the
+    GPU tests then use as the yardstick for the CUDA backward kernels."""
+    g = load_golden("snea_grad")
+    x = g["x"].clone().requires_grad_(True)
+    prm = {}
+    for tag in ("c1", "c2"):
+        prm[tag] = [g[f"{tag}__{nm}__{wb}"].clone().requires_grad_(True)
+                    for nm in ("lin_b", "lin_u", "alpha_b", "alpha_u") for wb in ("weight", "bias")]
+    order = lambda p: [p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]]   # lin_b w,b, lin_u w,b, alpha_b w,b, alpha_u w,b
+    pos, neg = g["pos_edge_index"], g["neg_edge_index"]
+    z1 = port.snea_conv(x, pos, neg, *order(prm["c1"]), True)
+    out = port.snea_conv(torch.tanh(z1), pos, neg, *order(prm["c2"]), False)
+    assert _rel(out.detach(), g["out"]) <= 2e-6
+    (out * g["r"]).sum().backward()
+    assert _rel(x.grad, g["grad_x"]) <= 1e-5
+    names = [f"{nm}__{wb}" for nm in ("lin_b", "lin_u", "alpha_b", "alpha_u") for wb in ("weight", "bias")]
+    for tag in ("c1", "c2"):
+        for nm, p in zip(names, prm[tag]):
+            ref = g[f"{tag}__{nm}__grad"]
+            if float(ref.abs().max()) < 1e-4:          # first layer's attention: softmax weights of one type sum to 1
+                assert float(p.grad.abs().max()) < 1e-4
+            else:
+                assert _rel(p.grad, ref) <= 2e-5, f"{tag} {nm}"
+
+    s = load_golden("sdr_layer_grad")
+    x = s["x"].clone().requires_grad_(True)
+    lists = [s[f"edges_{i}"] for i in range(4)]
+    leaf = lambda k: s[k].clone().requires_grad_(True)
+    gat = [(leaf(f"agg_{i}__lin__weight"), leaf(f"agg_{i}__att_src"), leaf(f"agg_{i}__att_dst"), leaf(f"agg_{i}__bias"))
+           for i in range(4)]
+    mlp = [leaf("mlp_layer__0__weight"), leaf("mlp_layer__0__bias"), leaf("mlp_layer__2__weight"), leaf("mlp_layer__2__bias")]
+    y = port.sdr_layer(x, lists, [(w, a.view(-1), b.view(-1), bb) for w, a, b, bb in gat], *mlp)
+    assert _rel(y.detach(), s["out"]) <= 2e-6
+    (y * s["r"]).sum().backward()
+    assert _rel(x.grad, s["grad_x"]) <= 1e-5
+    for i, (w, a, b, bb) in enumerate(gat):
+        for nm, p in (("lin__weight", w), ("att_src", a), ("att_dst", b), ("bias", bb)):
+            assert _rel(p.grad, s[f"agg_{i}__{nm}__grad"]) <= 2e-5, f"agg_{i} {nm}"
+    for nm, p in zip(("mlp_layer__0__weight", "mlp_layer__0__bias", "mlp_layer__2__weight", "mlp_layer__2__bias"), mlp):
+        assert _rel(p.grad, s[nm + "__grad"]) <= 2e-5, nm
