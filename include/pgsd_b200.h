@@ -363,6 +363,7 @@ typedef struct pgsd_attn_bwd_args {
   float* g_s_dst[2];
   float* type_sum[2];
 } pgsd_attn_bwd_args;
+PGSD_API size_t pgsd_sizeof_attn_bwd_args(void);
 PGSD_API int pgsd_edge_softmax_backward(const pgsd_attn_bwd_args* args, pgsd_stream_t stream);
 
 /* out[k] = <gy[row(k)], h[col[k]]> for every stored entry k of a CSR plan: dL/dalpha of y[i] = sum_k alpha_k h[col_k]

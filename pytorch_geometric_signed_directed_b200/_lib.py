@@ -124,6 +124,7 @@ _PROTOTYPES = {
     "pgsd_sizeof_magnet_fused_args": (C.c_size_t, []),
     "pgsd_magnet_layer_fused": (C.c_int, [C.POINTER(MagnetFusedArgs), _vp]),
     "pgsd_edge_softmax": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "pgsd_sizeof_attn_bwd_args": (C.c_size_t, []),
     "pgsd_edge_softmax_backward": (C.c_int, [C.POINTER(AttnBwdArgs), _vp]),
     "pgsd_sddmm_rows": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "pgsd_xtg_accumulate": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _vp]),
@@ -169,6 +170,8 @@ def load() -> C.CDLL:
             raise PgsdError("ctypes struct mirror out of sync with include/pgsd_b200.h; rebuild")
         if lib.pgsd_sizeof_magnet_fused_args() != C.sizeof(MagnetFusedArgs):
             raise PgsdError("ctypes mirror of pgsd_magnet_fused_args out of sync with include/pgsd_b200.h; rebuild")
+        if lib.pgsd_sizeof_attn_bwd_args() != C.sizeof(AttnBwdArgs):
+            raise PgsdError("ctypes mirror of pgsd_attn_bwd_args out of sync with include/pgsd_b200.h; rebuild")
         if lib.pgsd_sizeof_push_args() != C.sizeof(PushArgs):
             raise PgsdError("ctypes mirror of pgsd_push_args out of sync with include/pgsd_b200.h; rebuild")
         _lib = lib

@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(256) sddmm_rows_kernel(const int32_t* __restri
 
 using namespace pgsd;
 
+extern "C" size_t pgsd_sizeof_attn_bwd_args(void) { return sizeof(pgsd_attn_bwd_args); }
+
 extern "C" int pgsd_edge_softmax_backward(const pgsd_attn_bwd_args* a, pgsd_stream_t stream) {
   PGSD_REQUIRE(a != nullptr, "edge_softmax_backward: args is null");
   PGSD_REQUIRE(a->n_types == 1 || a->n_types == 2, "edge_softmax_backward: n_types must be 1 or 2");

@@ -31,6 +31,27 @@ def test_ctypes_struct_sizes_match_the_compiled_header():
     a, b = C.c_size_t(0), C.c_size_t(0)
     assert lib.pgsd_sizeof_args(C.byref(a), C.byref(b)) == 0
     assert a.value == C.sizeof(_lib.SpmmArgs) and b.value == C.sizeof(_lib.DenseArgs)
+    assert lib.pgsd_sizeof_magnet_fused_args() == C.sizeof(_lib.MagnetFusedArgs)
+    assert lib.pgsd_sizeof_push_args() == C.sizeof(_lib.PushArgs)
+    assert lib.pgsd_sizeof_attn_bwd_args() == C.sizeof(_lib.AttnBwdArgs)
+
+
+def test_exchange_and_attention_backward_entry_points_validate_arguments():
+    """The entry points added in round 2 fail loudly on bad arguments, without touching the GPU."""
+    lib = _lib.load()
+    assert lib.pgsd_shard_push(None, None) == 1 and b"null" in lib.pgsd_last_error()
+    p = _lib.PushArgs()
+    p.world, p.rank, p.n_tensors, p.n_slices, p.row_bytes = 40, 0, 1, 1, 256
+    assert lib.pgsd_shard_push(C.byref(p), None) == 1 and b"world" in lib.pgsd_last_error()
+    p.world, p.row_bytes = 2, 100
+    assert lib.pgsd_shard_push(C.byref(p), None) == 1 and b"row_bytes" in lib.pgsd_last_error()
+    assert lib.pgsd_wait_flags(None, None, 1, 1, 1000, None, None) == 1
+    assert lib.pgsd_edge_softmax_backward(None, None) == 1
+    b = _lib.AttnBwdArgs()
+    b.n_rows, b.n_types = 5, 3
+    assert lib.pgsd_edge_softmax_backward(C.byref(b), None) == 1 and b"n_types" in lib.pgsd_last_error()
+    assert lib.pgsd_signal_flag(None, 1, None) == 1
+    assert lib.pgsd_last_spmm_kernel() is not None
 
 
 def test_argument_validation_without_gpu():
