@@ -649,6 +649,8 @@ def run_gpu_arm(args, rank, world):
         "data": "synthetic", "config": bench_config(world),
         "roofline": roof, "cpu_baseline": cpu_base, "e2e": e2e, "parity_check": parity, "gpu_launches": launches,
         "clocks": clocks, "edges_total": e_input, "nnz_per_rank": nnz,
+        # neighbour feature rows gathered per second (one per stored entry and operator, all ranks)
+        "messages_per_s": 2 * nnz * world / (ms_per_step * 1e-3),
         "cold_ms_per_step": cold_ms,   # cached=False: plan build + forward (reference: ~48 s on CPU)
         "uncached_same_tensors_ms_per_step": uncached_same_tensors_ms,   # cached=False, identical edge tensors again
         "shared_input": shared,
