@@ -188,3 +188,44 @@ def test_new_model_wrappers_keep_the_reference_contracts():
     with pytest.raises(NotImplementedError):
         sg.loss()
     assert pgd.halo_fraction([torch.arange(2, dtype=torch.int32)] * 2, [0, 4, 8], 0) == 1.0
+
+
+def test_plan_cache_modes_on_host(monkeypatch):
+    """PlanCache: identity key + (on CUDA) content fingerprint; `off` rebuilds every call; capacity evicts the oldest;
+    get_many serves several requests with one read-back.  (CPU tensors have no fingerprint: identity semantics.)"""
+    from pytorch_geometric_signed_directed_b200.plan import PlanCache
+    built = []
+
+    def mk(tag):
+        def build():
+            built.append(tag)
+            return tag
+        return build
+
+    a, b, c = torch.arange(10), torch.arange(6), torch.arange(3)
+    cache = PlanCache(capacity=2)
+    assert cache.get((a,), "k", mk("A")) == "A" and cache.get((a,), "k", mk("A'")) == "A"
+    assert cache.get((a,), "other extra", mk("A2")) == "A2"
+    a.add_(1)                                                    # in-place write bumps the version counter
+    assert cache.get((a,), "k", mk("A3")) == "A3"
+    assert cache.get_many([((b,), 1, mk("B")), ((c,), 1, mk("C"))]) == ["B", "C"]
+    assert len(cache._items) == 2                                # capacity: the two oldest entries are gone
+    monkeypatch.setenv("PGSD_PLAN_REUSE", "off")
+    assert cache.get((b,), 1, mk("B again")) == "B again"
+    monkeypatch.setenv("PGSD_PLAN_REUSE", "identity")
+    assert cache.get((b,), 1, mk("never")) == "B"
+    cache.clear()
+    assert not cache._items
+    assert built == ["A", "A2", "A3", "B", "C", "B again"]
+
+
+def test_push_exchange_slice_defaults():
+    from pytorch_geometric_signed_directed_b200 import distributed as pgd
+    assert pgd.stage_fractions(world=2) == [0.0, 1.0]
+    assert pgd.stage_fractions(world=4) == [0.0, 0.5, 1.0]
+    assert pgd.stage_fractions(world=8) == [0.0, 0.25, 0.5, 0.75, 1.0]
+    assert pgd.stage_fractions("1,1,2") == [0.0, 0.25, 0.5, 1.0]
+    for n in (0, 1, 7, 1000):
+        for cum in (pgd.stage_fractions(3), pgd.stage_fractions("0.22,0.2,0.18,0.16,0.14,0.1")):
+            r = pgd.slice_rows(n, cum)
+            assert r[0] == 0 and r[-1] == n and all(y >= x for x, y in zip(r, r[1:]))
