@@ -355,7 +355,7 @@ class PlanCache:
         out = []
         for key, fp, (ts, _, builder) in zip(keys, fps, requests):
             hit = self._items.get(key)
-            if hit is not None and hit[2] == fp:
+            if hit is not None and (fp is None or hit[2] is None or hit[2] == fp):
                 out.append(hit[0])
                 continue
             plan = builder()
