@@ -63,15 +63,13 @@ class SGCNConv(torch.nn.Module):
         self._plans.clear()
 
     def _plan_for(self, edge_index: Tensor, n_dst: int, n_src: int):
-        if not isinstance(edge_index, Tensor):
-            raise NotImplementedError("SparseTensor adjacency is not supported; pass COO edge_index")
+        edge_index = _plan.as_edge_index(edge_index)
         return self._plans.get((edge_index,), (n_dst, n_src),
                                lambda: _plan.build_csr(edge_index, None, n_dst, n_src, "source_to_target"))
 
     def _plans_for(self, pos_edge_index: Tensor, neg_edge_index: Tensor, n_dst: int, n_src: int):
-        for ei in (pos_edge_index, neg_edge_index):
-            if not isinstance(ei, Tensor):
-                raise NotImplementedError("SparseTensor adjacency is not supported; pass COO edge_index")
+        # a SparseTensor / torch sparse adjacency (SGCNConv.py:131-134) is read as adj_t[target, source]
+        pos_edge_index, neg_edge_index = _plan.as_edge_index(pos_edge_index), _plan.as_edge_index(neg_edge_index)
         mk = lambda ei: ((ei,), (n_dst, n_src), lambda: _plan.build_csr(ei, None, n_dst, n_src, "source_to_target"))
         return self._plans.get_many([mk(pos_edge_index), mk(neg_edge_index)])
 

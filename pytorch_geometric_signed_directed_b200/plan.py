@@ -96,6 +96,27 @@ def _prep_edges(edge_index: Tensor, edge_weight: Optional[Tensor]) -> Tuple[Tens
     return ei, ew
 
 
+def as_edge_index(adj) -> Tensor:
+    """COO `edge_index` [2, E] (row 0 = source, row 1 = target) of an adjacency given the way PyG's `Adj` allows
+    (nn/signed/SGCNConv.py:94-95,131-134): a dense [2, E] tensor is returned as is; a torch sparse tensor (COO / CSR
+    layout) or a torch_sparse-style `SparseTensor` (anything with `.coo() -> (row, col, value)`) is read as the
+    TRANSPOSED adjacency `adj_t[target, source]` that `message_and_aggregate` multiplies with, entries in stored order."""
+    if isinstance(adj, Tensor):
+        if adj.layout == torch.strided:
+            return adj
+        coo = adj if adj.layout == torch.sparse_coo else adj.to_sparse_coo()
+        idx = coo._indices()
+        if idx.size(0) != 2:
+            raise ValueError("sparse adjacency must be 2-D")
+        return torch.stack([idx[1], idx[0]]).contiguous()
+    coo = getattr(adj, "coo", None)
+    if callable(coo):
+        row, col = adj.coo()[:2]
+        return torch.stack([col, row]).contiguous()
+    raise NotImplementedError(f"unsupported adjacency type {type(adj).__name__}: pass a [2, E] edge_index, a torch "
+                              "sparse tensor or a SparseTensor with .coo()")
+
+
 def _workspace(n: int, e: int, device) -> Tensor:
     lib = _lib.load()
     nbytes = C.c_size_t(0)

@@ -229,3 +229,23 @@ def test_push_exchange_slice_defaults():
         for cum in (pgd.stage_fractions(3), pgd.stage_fractions("0.22,0.2,0.18,0.16,0.14,0.1")):
             r = pgd.slice_rows(n, cum)
             assert r[0] == 0 and r[-1] == n and all(y >= x for x, y in zip(r, r[1:]))
+
+
+def test_sparse_adjacency_inputs_are_read_as_transposed_adjacency():
+    """SGCNConv accepts `Adj` (SGCNConv.py:94-95,131-134): a SparseTensor / torch sparse `adj_t[target, source]` is
+    turned into the same [2, E] (source, target) edge list a COO call passes (reference test: test/signed_test.py:94-111)."""
+    from pytorch_geometric_signed_directed_b200.plan import as_edge_index
+    ei = torch.tensor([[0, 2, 2, 5, 1], [3, 1, 4, 0, 1]])
+    assert as_edge_index(ei) is ei
+    adj_t = torch.sparse_coo_tensor(torch.stack([ei[1], ei[0]]), torch.ones(5), (6, 6))
+    assert torch.equal(as_edge_index(adj_t), ei)
+    got = as_edge_index(adj_t.coalesce().to_sparse_csr())                 # CSR: rows sorted, same edge set
+    key = lambda e: sorted(map(tuple, e.t().tolist()))
+    assert key(got) == key(ei)
+
+    class FakeSparseTensor:                                                # torch_sparse.SparseTensor duck type
+        def coo(self):
+            return ei[1], ei[0], None
+    assert torch.equal(as_edge_index(FakeSparseTensor()), ei)
+    with pytest.raises(NotImplementedError):
+        as_edge_index("not an adjacency")
