@@ -283,6 +283,14 @@ def parity_check(rank, world, dev, ei_cpu, n_total, x_real, x_imag, outs, conv, 
         full = [x_real.cpu(), x_imag.cpu()]
     if rank != 0:
         return None
+    try:
+        return _parity_rows(dev, ei_cpu, n_total, full, outs, conv, row_lo, n_check)
+    except Exception as exc:  # noqa: BLE001 - an extra key must never cost the headline line
+        log(f"parity_check failed: {type(exc).__name__}: {exc}")
+        return {"error": f"{type(exc).__name__}: {exc}"[:300], "ok": False}
+
+
+def _parity_rows(dev, ei_cpu, n_total, full, outs, conv, row_lo, n_check):
     from oracle import port
     t0 = time.time()
     threads = torch.get_num_threads()
@@ -414,6 +422,7 @@ def run_gpu_arm(args, rank, world):
     # ---- end-to-end: host (pinned) features in, host (pinned) outputs back, every step
     e2e = None
     if world > 1:
+      try:
         # every rank uploads its shard from pinned host memory, runs the sharded forward and downloads its
         # rows of the outputs; max over ranks
         hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
@@ -439,6 +448,9 @@ def run_gpu_arm(args, rank, world):
                                        "exchange + aggregation + transform) -> D2H of its output rows, every step; "
                                        "serial on each rank's stream, max over ranks; bytes are summed over ranks"}
         del hx_r, hx_i, ho_r, ho_i, dx_r, dx_i
+      except Exception as exc:  # noqa: BLE001 - keep the device-resident line even if the host leg fails
+        log(f"[rank {rank}] e2e leg failed: {type(exc).__name__}: {exc}")
+        e2e = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if world == 1:
         hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
         ho_r = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
@@ -574,6 +586,7 @@ def run_gpu_arm(args, rank, world):
     # rows instead of the all-gather; timed and parity-checked the same way
     halo = None
     if world > 1 and not args.no_halo:
+      try:
         ei2 = synthetic.locality_edges(n_total, e_total, 50_000, 0.0, seed=1, device=dev)
         sh2 = pgd.ShardedMagNetConv(conv, n_total, rank, world).build(ei2)
         e2_input = ei2.size(1)
@@ -593,6 +606,9 @@ def run_gpu_arm(args, rank, world):
                 "edges_total": e2_input, "parity_check": par2,
                 "graph": "synthetic.locality_edges: |i - j| <= 50k, 1M nodes / 20M edges per rank, unit weights"}
         del sh2
+      except Exception as exc:  # noqa: BLE001 - an extra key must never cost the headline line
+        log(f"[rank {rank}] halo-path leg failed: {type(exc).__name__}: {exc}")
+        halo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         return
