@@ -418,6 +418,9 @@ def run_gpu_arm(args, rank, world):
     parity = parity_check(rank, world, dev, ei_cpu, n_total, x_real, x_imag, outs, conv,
                           0 if world == 1 else sharded.bounds[rank])
     del outs
+    # rank 0 spends seconds on the CPU in the check: the other ranks wait HERE (NCCL barrier), not inside the flag
+    # waits of their next sharded step, which give up after PGSD_WAIT_TIMEOUT_S
+    barrier()
 
     # ---- end-to-end: host (pinned) features in, host (pinned) outputs back, every step
     e2e = None
@@ -600,6 +603,7 @@ def run_gpu_arm(args, rank, world):
         t_h = torch.tensor([time_steps(halo_step, args.steps, args.warmup, barrier)], device=dev)
         dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
         par2 = parity_check(rank, world, dev, ei2_cpu, n_total, x_real, x_imag, halo_step(), conv, sh2.bounds[rank])
+        barrier()
         halo = {"ms_per_step": float(t_h.item()), "value": e2_input / (float(t_h.item()) * 1e-3), "unit": UNIT,
                 "mode": sh2.agg.mode, "halo_fraction": getattr(sh2.agg, "halo_fraction", None),
                 "halo_rows_received_rank0": sh2.agg.halo.n_recv if sh2.agg.halo else None,

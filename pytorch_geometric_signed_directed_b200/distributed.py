@@ -424,14 +424,14 @@ class PushExchange:
                        started_ptr=self.started.data_ptr())
         self.done.record(self.stream)
         # the aggregation launches fill every SM: let the push CTAs become resident first
-        ops.wait_flags(self.started, [0], self.seq, self.status, float(os.environ.get("PGSD_WAIT_TIMEOUT_S", "5")))
+        ops.wait_flags(self.started, [0], self.seq, self.status, float(os.environ.get("PGSD_WAIT_TIMEOUT_S", "20")))
         return self.seq
 
     def wait_slice(self, s: int, seq: int) -> None:
         """The current stream waits until slice s of every peer's shard of step `seq` has landed here."""
         par = seq & 1
         idx = [(par * _MAX_RANKS + b) * _MAX_SLICES + s for b in range(self.world) if b != self.rank]
-        ops.wait_flags(self.flags, idx, seq, self.status, float(os.environ.get("PGSD_WAIT_TIMEOUT_S", "5")))
+        ops.wait_flags(self.flags, idx, seq, self.status, float(os.environ.get("PGSD_WAIT_TIMEOUT_S", "20")))
 
     def finish(self) -> None:
         """The current stream waits for this rank's own push (the source rows may then be reused)."""
