@@ -7,7 +7,7 @@ from conftest import assert_close_rel, load_golden
 from oracle import port
 
 MAGNET_CASES = ["magnet_c1", "magnet_k2_weighted", "magnet_k3_none", "magnet_q0",
-                "magnet_sym_lmax", "msconv_signed", "msconv_nonabs_none"]
+                "magnet_sym_lmax", "msconv_signed", "msconv_nonabs_none", "magnet_k9"]
 
 
 def _magnet_kwargs(name, g):
