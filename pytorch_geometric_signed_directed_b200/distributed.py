@@ -3,18 +3,21 @@
 The reference is single-process/single-device (no torch.distributed anywhere); this module has
 no reference counterpart.  The path shards by DESTINATION ROWS: rank r owns the nodes
 [bounds[r], bounds[r+1]), their CSR rows, their slice of x_real/x_imag and of the outputs.
-Rows are independent given x, so the only exchange is the feature rows a rank's columns point
-at.  On the randomly permuted DSBM graphs of the benchmark every rank references ~all remote
-nodes, so the halo is the whole matrix and the exchange is an all-gather; it is run as a RING
-of world-1 point-to-point rounds (NCCL send/recv over NVLink) so that the shard that arrived in
-round s is aggregated (one column-block SpMM launch, accumulating into the output through the
-kernel's `beta * z` epilogue) while round s+1 is in flight:
+Rows are independent given x, so the only exchange is the feature rows a rank's columns point at.
 
-    compute stream :  pack | block[r] | wait(1) block[r-1] | wait(2) block[r-2] | ...
-    NCCL stream    :       | round 1  | round 2            | round 3            | ...
+All-gather path (permuted graphs: every rank references ~all remote nodes).  `PushExchange`
+(csrc/exchange.cu): every rank STORES its rows into the peers' [n_total, F] receive planes in
+symmetric memory (push kernel with LSU or bulk-copy/TMA engine, or the copy engines), in row
+slices published by flags; the row shard's entries are split into stage blocks -- own columns
+first, then the columns of every slice as it lands -- that accumulate through the aggregation
+kernel's `beta * z` epilogue:
 
-Real and imaginary features travel interleaved as one [n_local, 2F] buffer, so each neighbour
-gather touches one contiguous 2F*4-byte row.
+    exchange stream :  push slice 0 | slice 1 | slice 2 | ...            (flags per slice)
+    compute stream  :  own block    | wait(0) stage 1 | wait(1) stage 2 | ... | transform
+
+Receive planes and flags are double-buffered by step parity, so there is no per-step barrier.
+Fallbacks behind PGSD_EXCHANGE: copy-engine pulls of whole shards + per-owner column blocks
+(round 1), NCCL send/recv ring (also what the gloo CPU tests drive).
 
 Graphs whose edge list shards naturally (locality-ordered node ids: most columns of a row shard
 are local, the rest touch a thin band of each peer) take the HALO path instead (`mode="halo"`,
@@ -23,7 +26,7 @@ plan is analysed once -- sorted unique remote columns per owner, request lists e
 all-to-all -- and every step packs the rows each peer asked for (`pgsd_gather_rows`), exchanges
 them with ONE `all_to_all_single` (NCCL over NVLink) that runs while the local-column block is
 aggregated, and then aggregates the remote-column block straight from the received buffer (its
-columns are compact indices into that buffer).
+columns are compact indices into that buffer).  DESIGN.md §7 has the measurements behind the defaults.
 """
 from __future__ import annotations
 
