@@ -424,8 +424,8 @@ def run_gpu_arm(args, rank, world):
 
     # ---- end-to-end: host (pinned) features in, host (pinned) outputs back, every step
     e2e = None
-    if world > 1:
-      try:
+
+    def e2e_sharded():
         # every rank uploads its shard from pinned host memory, runs the sharded forward and downloads its
         # rows of the outputs; max over ranks
         hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
@@ -445,15 +445,20 @@ def run_gpu_arm(args, rank, world):
         t_e2e = torch.tensor([time_steps(e2e_step_sharded, n_e2e, 2, barrier)], device=dev)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e_ms = float(t_e2e.item())
-        e2e = {"value": e_input / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+        res = {"value": e_input / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": 2 * n_local * FEAT * 4 * world, "d2h_bytes_per_step": 2 * n_local * FEAT * 4 * world,
                "steps": n_e2e, "note": "per rank: pinned host shard of x_real/x_imag -> H2D -> sharded forward (push "
                                        "exchange + aggregation + transform) -> D2H of its output rows, every step; "
                                        "serial on each rank's stream, max over ranks; bytes are summed over ranks"}
-        del hx_r, hx_i, ho_r, ho_i, dx_r, dx_i
-      except Exception as exc:  # noqa: BLE001 - keep the device-resident line even if the host leg fails
-        log(f"[rank {rank}] e2e leg failed: {type(exc).__name__}: {exc}")
-        e2e = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        return res
+
+    if world > 1:
+        try:
+            e2e = e2e_sharded()
+        except Exception as exc:  # noqa: BLE001 - keep the device-resident line even if the host leg fails
+            log(f"[rank {rank}] e2e leg failed: {type(exc).__name__}: {exc}")
+            e2e = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if world == 1:
         hx_r, hx_i = x_real.cpu().pin_memory(), x_imag.cpu().pin_memory()
         ho_r = torch.empty((n_local, FEAT), dtype=torch.float32).pin_memory()
@@ -588,8 +593,8 @@ def run_gpu_arm(args, rank, world):
     # locality (|i - j| <= 50k), the same 1M nodes / 20M edges per rank -- takes the all-to-all of packed halo
     # rows instead of the all-gather; timed and parity-checked the same way
     halo = None
-    if world > 1 and not args.no_halo:
-      try:
+
+    def halo_leg():
         ei2 = synthetic.locality_edges(n_total, e_total, 50_000, 0.0, seed=1, device=dev)
         sh2 = pgd.ShardedMagNetConv(conv, n_total, rank, world).build(ei2)
         e2_input = ei2.size(1)
@@ -604,15 +609,19 @@ def run_gpu_arm(args, rank, world):
         dist.all_reduce(t_h, op=dist.ReduceOp.MAX)
         par2 = parity_check(rank, world, dev, ei2_cpu, n_total, x_real, x_imag, halo_step(), conv, sh2.bounds[rank])
         barrier()
-        halo = {"ms_per_step": float(t_h.item()), "value": e2_input / (float(t_h.item()) * 1e-3), "unit": UNIT,
+        res = {"ms_per_step": float(t_h.item()), "value": e2_input / (float(t_h.item()) * 1e-3), "unit": UNIT,
                 "mode": sh2.agg.mode, "halo_fraction": getattr(sh2.agg, "halo_fraction", None),
                 "halo_rows_received_rank0": sh2.agg.halo.n_recv if sh2.agg.halo else None,
                 "edges_total": e2_input, "parity_check": par2,
                 "graph": "synthetic.locality_edges: |i - j| <= 50k, 1M nodes / 20M edges per rank, unit weights"}
-        del sh2
-      except Exception as exc:  # noqa: BLE001 - an extra key must never cost the headline line
-        log(f"[rank {rank}] halo-path leg failed: {type(exc).__name__}: {exc}")
-        halo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        return res
+
+    if world > 1 and not args.no_halo:
+        try:
+            halo = halo_leg()
+        except Exception as exc:  # noqa: BLE001 - an extra key must never cost the headline line
+            log(f"[rank {rank}] halo-path leg failed: {type(exc).__name__}: {exc}")
+            halo = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         return
