@@ -142,7 +142,9 @@ class SGCNConv(torch.nn.Module):
         ps = ag.dense([(x, w, 0)], 4 * fo, bias=bias)[0]
         pos, neg = self._plans_for(pos_edge_index, neg_edge_index, x.size(0), x.size(0))
         grad = ag._needs_grad([ps])
-        fuse = self.fused_tanh and not self.norm_emb and not grad
+        # hub rows (> 4096 entries) are finished by a second launch with atomics: no tanh epilogue there
+        fuse = (self.fused_tanh and not self.norm_emb and not grad
+                and pos.hub_rows() is None and neg.hub_rows() is None)
         if grad:
             out = torch.cat([ag.spmm(pos, [ps[:, :fo]], (0,), mean=True, beta=1.0, zs=[ps[:, 2 * fo:3 * fo]])[0],
                              ag.spmm(neg, [ps[:, fo:2 * fo]], (0,), mean=True, beta=1.0, zs=[ps[:, 3 * fo:]])[0]], 1)
