@@ -268,6 +268,7 @@ class _GatAttendFn(torch.autograd.Function):
         alpha = alphas[0]
         weighted = CSRPlan(plan.n_dst, plan.n_src, plan.nnz, plan.num_input_edges, plan.row_ptr, plan.col, [alpha],
                            [None], [0.0])
+        weighted._hubs = plan.hub_rows()
         y = ops.spmm(weighted, [h], (0,), bias=bias)[0]
         ctx.save_for_backward(s_src, s_dst, h, alpha)
         ctx.cfg = (plan, slope, has_bias)

@@ -89,6 +89,7 @@ class GATConv(torch.nn.Module):
         _, alphas = ops.edge_softmax([p], [s_src], [s_dst], act="leaky_relu", slope=self.negative_slope,
                                      want_alpha=True)
         weighted = CSRPlan(p.n_dst, p.n_src, p.nnz, p.num_input_edges, p.row_ptr, p.col, [alphas[0]], [None], [0.0])
+        weighted._hubs = p.hub_rows()          # same rows: no second device->host look at the row lengths
         if accumulate_into is not None:
             return ops.spmm(weighted, [h], (0,), beta=1.0, zs=[accumulate_into], out=[accumulate_into])[0]
         return ops.spmm(weighted, [h], (0,), bias=self.bias, out=None if out is None else [out])[0]
